@@ -1,0 +1,274 @@
+// Sparse convolution forward on CUDA cores (fp32 FMA), output-stationary, fused epilogue.
+//
+// Replaces the host-driven loop of indiceConv<T> (pcdet/ops/spconv/include/spconv/spconv_ops.h:
+// 294-357): per kernel offset a gather kernel, a cuBLAS GEMM and a scatter-add kernel (up to 79
+// launches and one D2H sync per layer), followed by separate bias / BatchNorm1d / ReLU kernels
+// (conv.py:223-224, spconv_backbone.py:25-27).  Here one launch per layer: a CTA owns 64 output rows,
+// walks the kernel offsets that have at least one neighbour in its tile, gathers the input rows named
+// by the output-major neighbour map into shared memory, accumulates in registers, and applies
+// bias + folded BatchNorm + residual + ReLU before the only store.  No scatter, no atomics.
+//
+// This is the any-shape path: arbitrary cin/cout, fp32 or bf16 storage, exact fp32 accumulation.  It
+// serves the first layer (cin = 4/5), odd channel counts through the module API, and is the
+// reference point the tensor-core kernels (conv_tc.cu) are validated against.
+#include "common.cuh"
+
+namespace fv2p {
+namespace {
+
+constexpr int kTileRows = 64;
+constexpr int kChunkK = 32;  // input channels staged per step
+
+template <typename T>
+__device__ __forceinline__ float to_f32(T v);
+template <>
+__device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T>
+__device__ __forceinline__ T from_f32(float v);
+template <>
+__device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// CT = output-channel tile, RM x RN = outputs per thread; (kTileRows/RM) * (CT/RN) == kThreads.
+template <typename InT, typename OutT, int CT, int RM, int RN>
+__global__ void __launch_bounds__(kThreads)
+conv_simt_kernel(const InT *__restrict__ features, const float *__restrict__ weight,
+                 const int *__restrict__ nbr, int64_t nbr_stride, int kvol, int64_t n_out_cap,
+                 const int *__restrict__ n_out_dev, int cin, int cout, const float *__restrict__ bias,
+                 const float *__restrict__ scale, const float *__restrict__ shift,
+                 const OutT *__restrict__ residual, int relu, OutT *__restrict__ out) {
+  static_assert((kTileRows / RM) * (CT / RN) == kThreads, "thread tiling must cover the CTA");
+  __shared__ float a_s[kTileRows][kChunkK + 1];
+  __shared__ __align__(16) float w_s[kChunkK][CT];
+  __shared__ int rows_s[kTileRows];
+
+  int n_out = n_out_dev ? *n_out_dev : (int)n_out_cap;
+  if (n_out > n_out_cap) n_out = (int)n_out_cap;
+  const int col_tiles = (cout + CT - 1) / CT;
+  const int row_tiles = (n_out + kTileRows - 1) / kTileRows;
+  const int tx = threadIdx.x % (CT / RN);  // column group
+  const int ty = threadIdx.x / (CT / RN);  // row group
+
+  for (int tile = blockIdx.x; tile < row_tiles * col_tiles; tile += gridDim.x) {
+    const int row0 = (tile / col_tiles) * kTileRows;
+    const int col0 = (tile % col_tiles) * CT;
+    float acc[RM][RN];
+#pragma unroll
+    for (int r = 0; r < RM; ++r)
+#pragma unroll
+      for (int c = 0; c < RN; ++c) acc[r][c] = 0.0f;
+
+    for (int k = 0; k < kvol; ++k) {
+      int src = -1;
+      if (threadIdx.x < kTileRows) {
+        const int row = row0 + threadIdx.x;
+        if (row < n_out) src = __ldg(&nbr[(size_t)k * nbr_stride + row]);
+      }
+      // skip offsets that feed nothing in this tile (also a barrier before rows_s is rewritten)
+      if (!__syncthreads_or(src >= 0)) continue;
+      if (threadIdx.x < kTileRows) rows_s[threadIdx.x] = src;
+      const float *wk = weight + (size_t)k * cin * cout;
+      for (int c0 = 0; c0 < cin; c0 += kChunkK) {
+        __syncthreads();  // rows_s visible; previous chunk fully consumed
+        for (int e = threadIdx.x; e < kTileRows * kChunkK; e += kThreads) {
+          const int r = e / kChunkK, c = e % kChunkK;
+          const int s = rows_s[r];
+          float v = 0.0f;
+          if (s >= 0 && c0 + c < cin) v = to_f32<InT>(features[(size_t)s * cin + c0 + c]);
+          a_s[r][c] = v;
+        }
+        for (int e = threadIdx.x; e < kChunkK * CT; e += kThreads) {
+          const int c = e / CT, o = e % CT;
+          float v = 0.0f;
+          if (c0 + c < cin && col0 + o < cout) v = __ldg(&wk[(size_t)(c0 + c) * cout + col0 + o]);
+          w_s[c][o] = v;
+        }
+        __syncthreads();
+        const int steps = min(kChunkK, cin - c0);
+        for (int c = 0; c < steps; ++c) {
+          float a[RM], w[RN];
+#pragma unroll
+          for (int r = 0; r < RM; ++r) a[r] = a_s[ty * RM + r][c];
+#pragma unroll
+          for (int q = 0; q < RN; ++q) w[q] = w_s[c][tx * RN + q];
+#pragma unroll
+          for (int r = 0; r < RM; ++r)
+#pragma unroll
+            for (int q = 0; q < RN; ++q) acc[r][q] = fmaf(a[r], w[q], acc[r][q]);
+        }
+      }
+    }
+    // epilogue: conv.py:223-224 bias, eval BatchNorm folded to scale/shift, residual, ReLU
+#pragma unroll
+    for (int r = 0; r < RM; ++r) {
+      const int row = row0 + ty * RM + r;
+      if (row >= n_out) continue;
+#pragma unroll
+      for (int q = 0; q < RN; ++q) {
+        const int col = col0 + tx * RN + q;
+        if (col >= cout) continue;
+        float v = acc[r][q];
+        if (bias) v += __ldg(&bias[col]);
+        if (scale) v = fmaf(v, __ldg(&scale[col]), __ldg(&shift[col]));
+        if (residual) v += to_f32<OutT>(residual[(size_t)row * cout + col]);
+        if (relu) v = fmaxf(v, 0.0f);
+        out[(size_t)row * cout + col] = from_f32<OutT>(v);
+      }
+    }
+    __syncthreads();  // rows_s / a_s reuse by the next tile
+  }
+}
+
+template <typename InT, typename OutT>
+int launch_simt(const void *features, const float *weight, const int *nbr, int64_t nbr_stride, int kvol,
+                int64_t n_out_cap, const int *n_out_dev, int cin, int cout, const float *bias, const float *scale,
+                const float *shift, const void *residual, int relu, void *out, cudaStream_t stream) {
+  const InT *f = static_cast<const InT *>(features);
+  const OutT *res = static_cast<const OutT *>(residual);
+  OutT *o = static_cast<OutT *>(out);
+  const int grid = persistent_grid(2);
+#define FV2P_SIMT(CT, RM, RN)                                                                                  \
+  conv_simt_kernel<InT, OutT, CT, RM, RN><<<grid, kThreads, 0, stream>>>(f, weight, nbr, nbr_stride, kvol,      \
+                                                                         n_out_cap, n_out_dev, cin, cout, bias, \
+                                                                         scale, shift, res, relu, o)
+  if (cout > 64) {
+    FV2P_SIMT(128, 8, 4);
+  } else if (cout > 32) {
+    FV2P_SIMT(64, 4, 4);
+  } else if (cout > 16) {
+    FV2P_SIMT(32, 4, 2);
+  } else {
+    FV2P_SIMT(16, 2, 2);
+  }
+#undef FV2P_SIMT
+  return cuda_status(cudaGetLastError(), "conv_fwd(simt)");
+}
+
+__global__ void __launch_bounds__(kThreads) cast_f32_bf16_kernel(const float *src, __nv_bfloat16 *dst, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] = __float2bfloat16_rn(src[i]);
+}
+__global__ void __launch_bounds__(kThreads) cast_bf16_f32_kernel(const __nv_bfloat16 *src, float *dst, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] = __bfloat162float(src[i]);
+}
+
+// SparseConvTensor.dense(): out[b][c][z][y][x] = features[row][c]
+__global__ void __launch_bounds__(kThreads)
+dense_ncdhw_kernel(const float *__restrict__ features, const int4 *__restrict__ indices, int64_t n_cap,
+                   const int *n_dev, int channels, int D, int H, int W, float *dense) {
+  int n = n_dev ? *n_dev : (int)n_cap;
+  if (n > n_cap) n = (int)n_cap;
+  const int64_t total = (int64_t)n * channels;
+  const size_t vol = (size_t)D * H * W;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    const int row = (int)(e / channels), c = (int)(e % channels);
+    const int4 q = __ldg(&indices[row]);
+    dense[((size_t)q.x * channels + c) * vol + ((size_t)q.y * H + q.z) * W + q.w] = features[e];
+  }
+}
+
+}  // namespace
+
+// implemented in conv_tc.cu
+int launch_conv_tc(const void *features, const void *weight, const int *nbr, int64_t nbr_stride, int kvol,
+                   int64_t n_out_cap, const int *n_out_dev, int cin, int cout, const float *bias,
+                   const float *scale, const float *shift, const void *residual, int relu, int mode, void *out,
+                   cudaStream_t stream);
+
+}  // namespace fv2p
+
+using namespace fv2p;
+
+extern "C" int fv2p_conv_fwd(const void *features, const void *weight, const int32_t *nbr, int64_t nbr_stride,
+                             int kvol, int64_t n_out_cap, const int32_t *n_out_dev, int cin, int cout,
+                             const float *bias, const float *scale, const float *shift, const void *residual,
+                             int relu, int mode, void *out, fv2p_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  FV2P_REQUIRE(kvol >= 1 && kvol <= FV2P_MAX_KVOL, "conv_fwd: kernel volume %d out of range", kvol);
+  FV2P_REQUIRE(cin >= 1 && cout >= 1 && cin <= 4096 && cout <= 4096, "conv_fwd: bad channel counts");
+  FV2P_REQUIRE(n_out_cap >= 0 && nbr_stride >= n_out_cap, "conv_fwd: nbr_stride < n_out_cap");
+  FV2P_REQUIRE((scale == nullptr) == (shift == nullptr), "conv_fwd: scale and shift come together");
+  if (n_out_cap == 0) return FV2P_OK;
+  FV2P_REQUIRE(features && weight && nbr && out, "conv_fwd: null pointer argument");
+  switch (mode) {
+    case FV2P_MODE_F32:
+      return launch_simt<float, float>(features, static_cast<const float *>(weight), nbr, nbr_stride, kvol,
+                                       n_out_cap, n_out_dev, cin, cout, bias, scale, shift, residual, relu, out,
+                                       stream);
+    case FV2P_MODE_BF16_SIMT:
+      return launch_simt<__nv_bfloat16, __nv_bfloat16>(features, static_cast<const float *>(weight), nbr,
+                                                       nbr_stride, kvol, n_out_cap, n_out_dev, cin, cout, bias,
+                                                       scale, shift, residual, relu, out, stream);
+    case FV2P_MODE_F32_IN_BF16_OUT:
+      return launch_simt<float, __nv_bfloat16>(features, static_cast<const float *>(weight), nbr, nbr_stride,
+                                               kvol, n_out_cap, n_out_dev, cin, cout, bias, scale, shift,
+                                               residual, relu, out, stream);
+    case FV2P_MODE_BF16_TC:
+    case FV2P_MODE_TF32X3_TC:
+      return launch_conv_tc(features, weight, nbr, nbr_stride, kvol, n_out_cap, n_out_dev, cin, cout, bias, scale,
+                            shift, residual, relu, mode, out, stream);
+    default:
+      set_error("conv_fwd: unknown mode %d", mode);
+      return FV2P_ERR_INVALID;
+  }
+}
+
+extern "C" size_t fv2p_indice_conv_workspace_bytes(int kvol, int64_t num_act_out) {
+  if (kvol < 1 || num_act_out < 0) return 0;
+  return (size_t)kvol * (size_t)(num_act_out > 0 ? num_act_out : 1) * sizeof(int) + 256;
+}
+
+extern "C" int fv2p_indice_conv_fp32(const float *features, const float *filters, const int32_t *pairs,
+                                     const int32_t *pair_num, int64_t pair_stride, int64_t num_act_out,
+                                     int inverse, int subm, int kvol, int cin, int cout, float *out,
+                                     void *workspace, size_t workspace_bytes, fv2p_stream_t stream_) {
+  (void)subm;  // the centre-offset shortcut of spconv_ops.h:300-304 is an implementation detail there
+  FV2P_REQUIRE(num_act_out >= 0, "indice_conv: negative output count");
+  if (num_act_out == 0) return FV2P_OK;
+  if (!workspace || workspace_bytes < fv2p_indice_conv_workspace_bytes(kvol, num_act_out)) {
+    set_error("indice_conv: workspace too small");
+    return FV2P_ERR_WORKSPACE;
+  }
+  int *nbr = static_cast<int *>(workspace);
+  int st = fv2p_pairs_to_nbr(pairs, pair_num, kvol, pair_stride, inverse, num_act_out, nbr, num_act_out, stream_);
+  if (st) return st;
+  return fv2p_conv_fwd(features, filters, nbr, num_act_out, kvol, num_act_out, nullptr, cin, cout, nullptr, nullptr,
+                       nullptr, nullptr, 0, FV2P_MODE_F32, out, stream_);
+}
+
+extern "C" int fv2p_dense_ncdhw(const float *features, const int32_t *indices, int64_t n_cap, const int32_t *n_dev,
+                                int channels, const int32_t *shape3, float *dense, fv2p_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  FV2P_REQUIRE(shape3 && channels >= 1 && n_cap >= 0, "dense: bad arguments");
+  if (n_cap == 0) return FV2P_OK;
+  FV2P_REQUIRE(features && indices && dense, "dense: null pointer argument");
+  dense_ncdhw_kernel<<<persistent_grid(), kThreads, 0, stream>>>(features, reinterpret_cast<const int4 *>(indices),
+                                                                n_cap, n_dev, channels, shape3[0], shape3[1],
+                                                                shape3[2], dense);
+  FV2P_LAUNCH_CHECK("dense");
+  return FV2P_OK;
+}
+
+extern "C" int fv2p_cast_f32_to_bf16(const float *src, void *dst, int64_t count, fv2p_stream_t stream_) {
+  if (count <= 0) return FV2P_OK;
+  FV2P_REQUIRE(src && dst, "cast: null pointer argument");
+  cast_f32_bf16_kernel<<<persistent_grid(), kThreads, 0, static_cast<cudaStream_t>(stream_)>>>(
+      src, static_cast<__nv_bfloat16 *>(dst), count);
+  FV2P_LAUNCH_CHECK("cast");
+  return FV2P_OK;
+}
+
+extern "C" int fv2p_cast_bf16_to_f32(const void *src, float *dst, int64_t count, fv2p_stream_t stream_) {
+  if (count <= 0) return FV2P_OK;
+  FV2P_REQUIRE(src && dst, "cast: null pointer argument");
+  cast_bf16_f32_kernel<<<persistent_grid(), kThreads, 0, static_cast<cudaStream_t>(stream_)>>>(
+      static_cast<const __nv_bfloat16 *>(src), dst, count);
+  FV2P_LAUNCH_CHECK("cast");
+  return FV2P_OK;
+}

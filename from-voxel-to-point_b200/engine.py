@@ -1,0 +1,372 @@
+"""Sync-free execution of a whole sparse backbone (eval mode).
+
+The module API (spconv/conv.py) runs the way the reference does: one rulebook build with a host
+round-trip per strided conv, conv + bias, then BatchNorm1d and ReLU as separate kernels
+(pcdet/ops/spconv/conv.py:113-229, modules.py:125-137).  The engine runs the same layer graph B200-style:
+
+  * geometry pre-pass -- rulebooks depend on coordinates only, so all 8/9 of them are built first, level by
+    level, with every row count kept in a device scalar (SURVEY.md section 7 "data-dependent shapes");
+  * feature pass -- one fused kernel per conv layer: gather + contraction + bias + folded BatchNorm
+    (+ residual) + ReLU, reading the output-major neighbour map;
+  * ONE device->host copy of the five row counts at the end, to hand out correctly shaped tensors.
+
+Nothing in between touches the host, so the whole step can be captured in a CUDA graph (pipeline.py).
+All buffers live in a grow-only arena sized by capacity bounds; the library itself never allocates.
+"""
+import numpy as np
+import torch
+from torch import nn
+
+from . import _lib
+from .spconv import ops
+from .spconv.conv import SparseConvolution
+from .spconv.modules import SparseSequential
+from .spconv.structure import SparseConvTensor
+
+
+class _Step(object):
+    __slots__ = ("conv", "bn", "relu", "key", "subm", "in_level", "out_level", "in_buf", "out_buf", "res_buf",
+                 "export", "cin", "cout", "kvol")
+
+
+class _Book(object):
+    __slots__ = ("key", "subm", "in_level", "out_level", "ksize", "stride", "pad", "dil", "kvol", "fanout")
+
+
+def fold_bn(bn):
+    """Eval BatchNorm1d as y = x*scale + shift (fp32): scale = gamma/sqrt(var+eps), shift = beta - mean*scale."""
+    with torch.no_grad():
+        inv = torch.rsqrt(bn.running_var.float() + bn.eps)
+        g = bn.weight.float() if bn.weight is not None else torch.ones_like(inv)
+        b = bn.bias.float() if bn.bias is not None else torch.zeros_like(inv)
+        scale = (g * inv).contiguous()
+        shift = (b - bn.running_mean.float() * scale).contiguous()
+    return scale, shift
+
+
+def trace_backbone(net):
+    """Flattens a VoxelBackBone8x-style module tree into fused conv steps.
+
+    Recognised patterns: SparseSequential(SparseConvolution, BatchNorm1d, ReLU) (post_act_block,
+    spconv_backbone.py:10-29) and SparseBasicBlock (spconv_backbone.py:32-68).  Returns None when the tree
+    contains anything else, in which case callers use the plain module path.
+    """
+    from .spconv_backbone import SparseBasicBlock
+    steps, books, levels = [], {}, [list(int(s) for s in net.sparse_shape)]
+    exports = {"conv1": "x_conv1", "conv2": "x_conv2", "conv3": "x_conv3", "conv4": "x_conv4", "conv_out": "out"}
+    state = dict(level=0, buf=-1, nbuf=0)  # buf -1 = the caller's voxel_features
+
+    def add_conv(conv, bn, relu, res_buf):
+        if conv.transposed or conv.inverse or conv.conv1x1 or conv.ndim != 3:
+            return False
+        key = conv.indice_key if conv.indice_key is not None else "_anon%d" % len(steps)
+        if key in books:
+            bk = books[key]
+            if bk.in_level != state["level"]:
+                return False
+        else:
+            bk = _Book()
+            bk.key, bk.subm, bk.in_level = key, conv.subm, state["level"]
+            bk.ksize = list(conv.kernel_size)
+            bk.dil = list(conv.dilation)
+            bk.kvol = int(np.prod(bk.ksize))
+            if conv.subm:
+                bk.stride, bk.pad = [1, 1, 1], [k // 2 for k in bk.ksize]  # spconv_ops.h:76-80
+                bk.out_level, bk.fanout = state["level"], 1
+            else:
+                bk.stride, bk.pad = list(conv.stride), list(conv.padding)
+                out_shape = ops.get_conv_output_size(levels[state["level"]], bk.ksize, bk.stride, bk.pad, bk.dil)
+                levels.append([int(s) for s in out_shape])
+                bk.out_level = len(levels) - 1
+                bk.fanout = ops.candidate_fanout(bk.ksize, bk.stride, bk.pad, bk.dil)
+            if bk.kvol > _lib.MAX_KVOL:
+                return False
+            books[key] = bk
+        st = _Step()
+        st.conv, st.bn, st.relu, st.key, st.subm = conv, bn, relu, key, conv.subm
+        st.in_level, st.out_level = bk.in_level, bk.out_level
+        st.in_buf, st.res_buf = state["buf"], res_buf
+        st.out_buf = state["nbuf"]
+        st.cin, st.cout, st.kvol = conv.in_channels, conv.out_channels, bk.kvol
+        st.export = None
+        state["nbuf"] += 1
+        state["buf"], state["level"] = st.out_buf, bk.out_level
+        steps.append(st)
+        return True
+
+    def walk(seq):
+        mods = list(seq._modules.values())
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            if isinstance(m, SparseBasicBlock):
+                if m.downsample is not None:
+                    return False
+                identity = state["buf"]
+                if identity < 0:
+                    return False
+                if not add_conv(m.conv1, m.bn1, True, None):
+                    return False
+                if not add_conv(m.conv2, m.bn2, True, identity):
+                    return False
+                i += 1
+            elif isinstance(m, SparseConvolution):
+                bn = relu = None
+                j = i + 1
+                if j < len(mods) and isinstance(mods[j], nn.BatchNorm1d):
+                    bn = mods[j]
+                    j += 1
+                if j < len(mods) and isinstance(mods[j], nn.ReLU):
+                    relu = True
+                    j += 1
+                if not add_conv(m, bn, bool(relu), None):
+                    return False
+                i = j
+            elif isinstance(m, SparseSequential):
+                if not walk(m):
+                    return False
+                i += 1
+            else:
+                return False
+        return True
+
+    for name, child in net.named_children():
+        if not isinstance(child, SparseSequential) or not walk(child):
+            return None
+        if name in exports and steps:
+            steps[-1].export = exports[name]
+    return steps, list(books.values()), levels
+
+
+class BackboneEngine(object):
+    """Runs a traced backbone.  precision: 'fp32' (fp32 storage, fp32-accurate arithmetic) or 'bf16'
+    (bf16 storage, fp32 accumulation; the entry layer reads fp32 voxel features)."""
+
+    def __init__(self, net, precision="fp32", materialize_pairs=True, use_tensor_cores=True):
+        traced = trace_backbone(net)
+        if traced is None:
+            raise NotImplementedError("backbone layout not recognised by the fused engine")
+        self.steps, self.books, self.level_shapes = traced
+        self.net = net
+        self.precision = precision
+        self.materialize_pairs = materialize_pairs
+        self.use_tensor_cores = use_tensor_cores
+        self.arena = None
+        self._param_key = None
+        self._params = None
+        # liveness of feature buffers: last step reading each one (exports live forever)
+        last_read = {}
+        for i, st in enumerate(self.steps):
+            last_read[st.in_buf] = i
+            if st.res_buf is not None:
+                last_read[st.res_buf] = i
+        self._last_read = last_read
+
+    # ------------------------------------------------------------------ parameters
+    def _prepare_params(self, device):
+        key = tuple((p.data_ptr(), p._version) for p in self.net.parameters()) + \
+            tuple((b.data_ptr(), b._version) for b in self.net.buffers()) + (str(device), self.precision)
+        if key == self._param_key:
+            return self._params
+        prm = []
+        lib = _lib.load()
+        for st in self.steps:
+            w = st.conv.weight.detach()
+            if not w.is_cuda:
+                raise ValueError("backbone parameters must live on the CUDA device")
+            w = w.float().reshape(st.kvol, st.cin, st.cout).contiguous()
+            bias = st.conv.bias.detach().float().contiguous() if st.conv.bias is not None else None
+            scale = shift = None
+            if st.bn is not None:
+                scale, shift = fold_bn(st.bn)
+            mode = self._mode_for(st)
+            packed = None
+            if mode in (_lib.MODE_BF16_TC, _lib.MODE_TF32X3_TC):
+                nbytes = lib.fv2p_pack_weight_bytes(st.kvol, st.cin, st.cout, mode)
+                packed = torch.empty(nbytes, dtype=torch.uint8, device=device)
+                _lib.check(lib.fv2p_pack_weight(_lib.ptr(w), st.kvol, st.cin, st.cout, mode, _lib.ptr(packed),
+                                                _lib.stream_ptr(device)), "pack_weight")
+            prm.append(dict(w=w, packed=packed, bias=bias, scale=scale, shift=shift, mode=mode))
+        self._params, self._param_key = prm, key
+        return prm
+
+    def _mode_for(self, st):
+        first = st.in_buf < 0
+        tc_ok = self.use_tensor_cores and st.cin % 16 == 0 and st.cout % 16 == 0 and st.cin <= 128 and \
+            16 <= st.cout <= 128 and _tc_available()
+        if self.precision == "bf16":
+            if first:
+                return _lib.MODE_F32_IN_BF16_OUT
+            return _lib.MODE_BF16_TC if tc_ok else _lib.MODE_BF16_SIMT
+        return _lib.MODE_TF32X3_TC if (tc_ok and not first) else _lib.MODE_F32
+
+    # ------------------------------------------------------------------ arena
+    def _caps(self, cap0, batch):
+        caps = [int(cap0)]
+        for bk in self.books:
+            if not bk.subm:
+                vol = int(np.prod(self.level_shapes[bk.out_level])) * int(batch)
+                caps.append(max(1, min(caps[bk.in_level] * bk.fanout, vol)))
+        return caps
+
+    def _ensure_arena(self, device, cap0, batch):
+        a = self.arena
+        if a is not None and a["device"] == device and a["batch"] >= batch and a["caps"][0] >= cap0:
+            return a
+        cap0 = int(cap0 * 1.15) + 256 if a is not None else int(cap0)
+        caps = self._caps(cap0, batch)
+        lib = _lib.load()
+        dt = torch.float32 if self.precision == "fp32" else torch.bfloat16
+        a = dict(device=device, batch=batch, caps=caps)
+        a["counts"] = torch.zeros((len(caps) + 1,), dtype=torch.int32, device=device)  # [levels..., status]
+        a["counts_host"] = torch.zeros((len(caps) + 1,), dtype=torch.int32).pin_memory()
+        a["indices"] = [None] + [torch.empty((c, 4), dtype=torch.int32, device=device) for c in caps[1:]]
+        books = {}
+        ws_bytes = 0
+        for bk in self.books:
+            cin_cap, cout_cap = caps[bk.in_level], caps[bk.out_level]
+            d = dict(nbr=torch.empty((bk.kvol, cout_cap), dtype=torch.int32, device=device),
+                     pair_num=torch.zeros((bk.kvol,), dtype=torch.int32, device=device),
+                     pairs=(torch.empty((bk.kvol, 2, cin_cap), dtype=torch.int32, device=device)
+                            if self.materialize_pairs else None))
+            books[bk.key] = d
+            ws_bytes = max(ws_bytes, lib.fv2p_rulebook_workspace_bytes(cin_cap, cout_cap, bk.kvol))
+        a["books"] = books
+        a["ws"] = torch.empty(ws_bytes + 1024, dtype=torch.uint8, device=device)
+        # feature buffers with liveness-based reuse
+        bufs, free, owner = {}, [], {}
+        for i, st in enumerate(self.steps):
+            shape = (caps[st.out_level], st.cout)
+            pick = None
+            for j, (t, last, exported) in enumerate(free):
+                if not exported and last < i and tuple(t.shape) == shape and st.in_buf != owner[j] and \
+                        st.res_buf != owner[j]:
+                    pick = j
+                    break
+            if pick is None:
+                t = torch.empty(shape, dtype=dt, device=device)
+                free.append([t, 0, False])
+                pick = len(free) - 1
+            free[pick][1] = self._last_read.get(st.out_buf, i)
+            free[pick][2] = st.export is not None
+            owner[pick] = st.out_buf
+            bufs[st.out_buf] = free[pick][0]
+        a["bufs"] = bufs
+        self.arena = a
+        return a
+
+    # ------------------------------------------------------------------ run
+    def launch(self, voxel_features, voxel_coords, batch_size, n0_dev=None, cap0=None):
+        """Enqueues geometry + feature passes on the current stream.  No host sync.
+
+        voxel_features [>=cap0, F] fp32, voxel_coords [>=cap0, 4] int32, both CUDA and contiguous;
+        live row count = *n0_dev (device int32) if given, else cap0 (defaults to voxel_coords.shape[0]).
+        """
+        dev = _lib.require_device(voxel_features)
+        device = voxel_features.device
+        if voxel_coords.dtype != torch.int32 or voxel_features.dtype != torch.float32:
+            raise ValueError("engine expects float32 features and int32 coordinates")
+        if not (voxel_features.is_contiguous() and voxel_coords.is_contiguous()):
+            raise ValueError("engine expects contiguous inputs")
+        cap0 = int(voxel_coords.shape[0] if cap0 is None else cap0)
+        a = self._ensure_arena(device, max(cap0, 1), int(batch_size))
+        prm = self._prepare_params(device)
+        lib = _lib.load()
+        stream = _lib.stream_ptr(device)
+        counts = a["counts"]
+        caps = a["caps"]
+        with torch.cuda.device(dev):
+            counts[len(caps):].zero_()
+            if n0_dev is None:
+                counts[0:1].fill_(cap0)
+                n0_dev = counts[0:1]
+            else:
+                counts[0:1].copy_(n0_dev.view(-1)[0:1])
+            level_ind = [voxel_coords] + a["indices"][1:]
+            level_cap = [cap0] + caps[1:]
+            n_ptr = [_lib.ctypes.c_void_p(counts.data_ptr() + 4 * i) for i in range(len(caps))]
+            status_ptr = _lib.ctypes.c_void_p(counts.data_ptr() + 4 * len(caps))
+            for bk in self.books:
+                d = a["books"][bk.key]
+                pairs = d["pairs"]
+                if bk.subm:
+                    st = lib.fv2p_rulebook_subm(_lib.ptr(level_ind[bk.in_level]), level_cap[bk.in_level],
+                                                n_ptr[bk.in_level], int(batch_size),
+                                                _lib.i32x3(self.level_shapes[bk.in_level]), _lib.i32x3(bk.ksize),
+                                                _lib.i32x3(bk.dil), _lib.ptr(pairs),
+                                                pairs.shape[2] if pairs is not None else 0,
+                                                _lib.ptr(d["pair_num"]) if pairs is not None else None,
+                                                _lib.ptr(d["nbr"]), d["nbr"].shape[1], _lib.ptr(a["ws"]),
+                                                a["ws"].numel(), stream)
+                else:
+                    st = lib.fv2p_rulebook_conv(_lib.ptr(level_ind[bk.in_level]), level_cap[bk.in_level],
+                                                n_ptr[bk.in_level], int(batch_size),
+                                                _lib.i32x3(self.level_shapes[bk.out_level]), _lib.i32x3(bk.ksize),
+                                                _lib.i32x3(bk.stride), _lib.i32x3(bk.pad), _lib.i32x3(bk.dil),
+                                                _lib.ptr(level_ind[bk.out_level]), level_cap[bk.out_level],
+                                                n_ptr[bk.out_level], _lib.ptr(pairs),
+                                                pairs.shape[2] if pairs is not None else 0,
+                                                _lib.ptr(d["pair_num"]) if pairs is not None else None,
+                                                _lib.ptr(d["nbr"]), d["nbr"].shape[1], status_ptr, _lib.ptr(a["ws"]),
+                                                a["ws"].numel(), stream)
+                _lib.check(st, "rulebook[%s]" % bk.key)
+            for st_, p in zip(self.steps, prm):
+                src = voxel_features if st_.in_buf < 0 else a["bufs"][st_.in_buf]
+                res = a["bufs"][st_.res_buf] if st_.res_buf is not None else None
+                out = a["bufs"][st_.out_buf]
+                nbr = a["books"][st_.key]["nbr"]
+                w = p["packed"] if p["packed"] is not None else p["w"]
+                rc = lib.fv2p_conv_fwd(_lib.ptr(src), _lib.ptr(w), _lib.ptr(nbr), nbr.shape[1], st_.kvol,
+                                       level_cap[st_.out_level], n_ptr[st_.out_level], st_.cin, st_.cout,
+                                       _lib.ptr(p["bias"]), _lib.ptr(p["scale"]), _lib.ptr(p["shift"]), _lib.ptr(res),
+                                       int(st_.relu), p["mode"], _lib.ptr(out), stream)
+                _lib.check(rc, "conv_fwd[%s]" % st_.key)
+        return a
+
+    def collect(self, a, voxel_coords, batch_size, sync=True):
+        """One D2H copy of the row counts, then correctly shaped views (valid until the next launch)."""
+        a["counts_host"].copy_(a["counts"], non_blocking=True)
+        if sync:
+            torch.cuda.current_stream(a["device"]).synchronize()
+        return self.views(a, voxel_coords, batch_size)
+
+    def views(self, a, voxel_coords, batch_size):
+        host = a["counts_host"].tolist()
+        n_levels = len(a["caps"])
+        status = host[n_levels]
+        if status:
+            raise RuntimeError("fv2p_b200 engine: capacity overflow (status %d); rows exceed the arena bounds" % status)
+        n = host[:n_levels]
+        level_ind = [voxel_coords[:n[0]]] + [t[:n[i + 1]] for i, t in enumerate(a["indices"][1:])]
+        indice_dict, nbr_dict = {}, {}
+        for bk in self.books:
+            d = a["books"][bk.key]
+            n_in, n_out = n[bk.in_level], n[bk.out_level]
+            nbr_dict[bk.key] = d["nbr"][:, :n_out]
+            if d["pairs"] is not None:
+                indice_dict[bk.key] = (level_ind[bk.out_level], level_ind[bk.in_level], d["pairs"][:, :, :n_in],
+                                       d["pair_num"], self.level_shapes[bk.in_level])
+        outs = {}
+        for st in self.steps:
+            if st.export is None:
+                continue
+            t = SparseConvTensor(a["bufs"][st.out_buf][:n[st.out_level]], level_ind[st.out_level],
+                                 self.level_shapes[st.out_level], batch_size)
+            t.indice_dict, t.nbr_dict = indice_dict, nbr_dict
+            outs[st.export] = t
+        return outs, n
+
+    def __call__(self, voxel_features, voxel_coords, batch_size):
+        a = self.launch(voxel_features, voxel_coords, batch_size)
+        return self.collect(a, voxel_coords, batch_size)[0]
+
+
+_TC_FLAG = None
+
+
+def _tc_available():
+    """True once the tcgen05 kernels are linked into the library (pack_weight_bytes answers non-zero)."""
+    global _TC_FLAG
+    if _TC_FLAG is None:
+        _TC_FLAG = _lib.load().fv2p_pack_weight_bytes(27, 64, 64, _lib.MODE_BF16_TC) > 0
+    return _TC_FLAG

@@ -1,0 +1,185 @@
+"""Op layer: same entry points as pcdet/ops/spconv/ops.py:20-158, backed by libfv2p_b200.so through
+ctypes instead of the pybind ``sparse_conv_ext``."""
+import numpy as np
+import torch
+
+from .. import _lib
+
+
+def get_conv_output_size(input_size, kernel_size, stride, padding, dilation):
+    """ops.py:20-30."""
+    ndim = len(input_size)
+    output_size = []
+    for i in range(ndim):
+        size = (input_size[i] + 2 * padding[i] - dilation[i] * (kernel_size[i] - 1) - 1) // stride[i] + 1
+        if kernel_size[i] == -1:
+            output_size.append(1)
+        else:
+            output_size.append(size)
+    return output_size
+
+
+def get_deconv_output_size(input_size, kernel_size, stride, padding, dilation, output_padding):
+    """ops.py:33-43."""
+    ndim = len(input_size)
+    output_size = []
+    for i in range(ndim):
+        if kernel_size[i] == -1:
+            raise ValueError("deconv don't support kernel_size < 0")
+        size = (input_size[i] - 1) * stride[i] - 2 * padding[i] + kernel_size[i] + output_padding[i]
+        output_size.append(size)
+    return output_size
+
+
+def _listify(v, ndim):
+    return list(v) if isinstance(v, (list, tuple)) else [v] * ndim
+
+
+def candidate_fanout(ksize, stride, padding, dilation):
+    """Upper bound of outputs one input can touch (product of per-axis candidate counts)."""
+    e = 1
+    for k, s, p, d in zip(ksize, stride, padding, dilation):
+        best = 0
+        for pos in range(4 * s * k * d + p + 8):
+            lo = int((pos - (k - 1) * d - 1 + s + p) / s)  # C division truncates toward zero
+            hi = (pos + p) // s
+            best = max(best, int((hi - lo) / d) + 1)
+        e *= best
+    return e
+
+
+def get_indice_pairs(indices, batch_size, spatial_shape, ksize=3, stride=1, padding=0, dilation=1, out_padding=0,
+                     subm=False, transpose=False, grid=None, return_nbr=False):
+    """ops.py:46-105.  Returns (outids, indice_pairs [K,2,N] int32, indice_pair_num [K] int32), bit-identical
+    to the reference's CPU path.  With return_nbr=True also returns the output-major neighbour map [K,Nout]."""
+    ndim = indices.shape[1] - 1
+    ksize, stride, padding, dilation, out_padding = (_listify(v, ndim) for v in
+                                                     (ksize, stride, padding, dilation, out_padding))
+    for d, s in zip(dilation, stride):
+        assert any([s == 1, d == 1]), "don't support this."
+    if ndim != 3:
+        raise NotImplementedError("fv2p_b200 builds the 3D rulebooks of the hot path only (ndim=%d)" % ndim)
+    if transpose:
+        raise NotImplementedError("transposed sparse convolution is outside the hot path")
+    if indices.dtype != torch.int32:
+        raise ValueError("indices must be int32 (reference: check_torch_dtype, torch_utils.h:29-60)")
+    dev = _lib.require_device(indices)
+    lib = _lib.load()
+    indices = indices.contiguous()
+    spatial_shape = [int(s) for s in spatial_shape]
+    n = indices.shape[0]
+    kvol = int(np.prod(ksize))
+    if subm:
+        out_shape = spatial_shape
+        out_cap = n
+    else:
+        out_shape = get_conv_output_size(spatial_shape, ksize, stride, padding, dilation)
+        out_cap = max(1, min(n * candidate_fanout(ksize, stride, padding, dilation),
+                             int(batch_size) * int(np.prod(out_shape))))
+    device = indices.device
+    pairs = torch.empty((kvol, 2, n), dtype=torch.int32, device=device)
+    pair_num = torch.empty((kvol,), dtype=torch.int32, device=device)
+    nbr = torch.empty((kvol, out_cap), dtype=torch.int32, device=device)
+    outids = indices if subm else torch.empty((out_cap, 4), dtype=torch.int32, device=device)
+    ws_bytes = lib.fv2p_rulebook_workspace_bytes(n, out_cap, kvol) + 256
+    ws = _lib.Workspace.get(device, ws_bytes, "rulebook")
+    n_out = (_lib.ctypes.c_int32 * 1)(0)
+    with torch.cuda.device(dev):
+        st = lib.fv2p_get_indice_pairs_3d(_lib.ptr(indices), n, int(batch_size), _lib.i32x3(out_shape),
+                                          _lib.i32x3(spatial_shape), _lib.i32x3(ksize), _lib.i32x3(stride),
+                                          _lib.i32x3(padding), _lib.i32x3(dilation), _lib.i32x3(out_padding),
+                                          int(subm), int(transpose), _lib.ptr(outids), out_cap, _lib.ptr(pairs),
+                                          _lib.ptr(pair_num), _lib.ptr(nbr), out_cap, n_out, _lib.ptr(ws),
+                                          ws.numel(), _lib.stream_ptr(device))
+    _lib.check(st, "get_indice_pairs")
+    n_out = int(n_out[0])
+    if not subm:
+        outids = outids[:n_out]
+        nbr = nbr[:, :n_out]
+    if return_nbr:
+        return outids, pairs, pair_num, nbr
+    return outids, pairs, pair_num
+
+
+def pairs_to_nbr(indice_pairs, indice_pair_num, num_activate_out, inverse=False):
+    """Output-major neighbour map [K,Nout] from a reference-layout pair tensor."""
+    dev = _lib.require_device(indice_pairs)
+    pairs = indice_pairs.contiguous()
+    num = indice_pair_num.to(pairs.device).contiguous()
+    kvol, _, stride = pairs.shape
+    nbr = torch.empty((kvol, max(int(num_activate_out), 1)), dtype=torch.int32, device=pairs.device)
+    with torch.cuda.device(dev):
+        st = _lib.load().fv2p_pairs_to_nbr(_lib.ptr(pairs), _lib.ptr(num), kvol, stride, int(inverse),
+                                           int(num_activate_out), _lib.ptr(nbr), nbr.shape[1],
+                                           _lib.stream_ptr(pairs.device))
+    _lib.check(st, "pairs_to_nbr")
+    return nbr[:, :int(num_activate_out)]
+
+
+def conv_forward(features, weight_flat, nbr, num_activate_out, bias=None, scale=None, shift=None, residual=None,
+                 relu=False, mode=None, n_out_dev=None, out=None):
+    """fv2p_conv_fwd: out = act((sum_k X[nbr[k]] W[k] + bias) * scale + shift + residual)."""
+    dev = _lib.require_device(features)
+    if mode is None:
+        mode = _lib.MODE_F32 if features.dtype == torch.float32 else _lib.MODE_BF16_SIMT
+    kvol = nbr.shape[0]
+    cin = features.shape[1]
+    if mode in (_lib.MODE_F32, _lib.MODE_BF16_SIMT, _lib.MODE_F32_IN_BF16_OUT):
+        assert weight_flat.dtype == torch.float32 and weight_flat.shape[0] == kvol and weight_flat.shape[1] == cin
+        cout = weight_flat.shape[2]
+    else:
+        cout = int(weight_flat.fv2p_cout)
+    out_dtype = torch.float32 if mode in (_lib.MODE_F32, _lib.MODE_TF32X3_TC) else torch.bfloat16
+    n_cap = int(num_activate_out)
+    if out is None:
+        out = torch.empty((n_cap, cout), dtype=out_dtype, device=features.device)
+    assert nbr.stride(1) == 1 and out.is_contiguous() and features.is_contiguous()
+    with torch.cuda.device(dev):
+        st = _lib.load().fv2p_conv_fwd(_lib.ptr(features), _lib.ptr(weight_flat), _lib.ptr(nbr), nbr.stride(0), kvol,
+                                       n_cap, _lib.ptr(n_out_dev), cin, cout, _lib.ptr(bias), _lib.ptr(scale),
+                                       _lib.ptr(shift), _lib.ptr(residual), int(relu), int(mode), _lib.ptr(out),
+                                       _lib.stream_ptr(features.device))
+    _lib.check(st, "conv_fwd")
+    return out
+
+
+def indice_conv(features, filters, indice_pairs, indice_pair_num, num_activate_out, inverse=False, subm=False,
+                nbr=None):
+    """ops.py:108-126 (indice_conv_fp32 / _half).  fp32 -> fp32 FMA path; bf16 supported on top of the
+    reference's dtypes; fp16 is not built."""
+    if filters.dtype not in (torch.float32, torch.bfloat16):
+        raise NotImplementedError("indice_conv: dtype %s is not built (fp32 and bf16 are)" % filters.dtype)
+    _lib.require_device(features)
+    cin, cout = filters.shape[-2], filters.shape[-1]
+    w = filters.reshape(-1, cin, cout).float().contiguous()
+    if nbr is None:
+        nbr = pairs_to_nbr(indice_pairs, indice_pair_num, num_activate_out, inverse)
+    feats = features.contiguous()
+    mode = _lib.MODE_F32 if feats.dtype == torch.float32 else _lib.MODE_BF16_SIMT
+    return conv_forward(feats, w, nbr, num_activate_out, mode=mode)
+
+
+def fused_indice_conv(features, filters, bias, indice_pairs, indice_pair_num, num_activate_out, inverse, subm):
+    """ops.py:129-140: the reference's "fused" op only pre-loads the bias (fused_spconv_ops.h:29-32)."""
+    w = filters.reshape(-1, filters.shape[-2], filters.shape[-1]).float().contiguous()
+    nbr = pairs_to_nbr(indice_pairs, indice_pair_num, num_activate_out, inverse)
+    return conv_forward(features.contiguous(), w, nbr, num_activate_out, bias=bias.float().contiguous())
+
+
+def indice_conv_backward(features, filters, out_bp, indice_pairs, indice_pair_num, inverse=False, subm=False):
+    """ops.py:143-158 / spconv_ops.h:365-457.  NOT on the hot path: composed from
+    torch index ops so that the modules stay trainable; a fused CUDA backward is a later row."""
+    cin, cout = filters.shape[-2], filters.shape[-1]
+    w = filters.reshape(-1, cin, cout)
+    grad_in = torch.zeros_like(features)
+    grad_w = torch.zeros_like(w)
+    nums = indice_pair_num.tolist()
+    for k, hot in enumerate(nums):
+        if hot <= 0:
+            continue
+        src = indice_pairs[k, 1 if inverse else 0, :hot].long()
+        dst = indice_pairs[k, 0 if inverse else 1, :hot].long()
+        go = out_bp[dst]
+        grad_w[k] = features[src].t() @ go
+        grad_in.index_add_(0, src, go @ w[k].t())
+    return grad_in, grad_w.view_as(filters)

@@ -1,0 +1,77 @@
+"""SparseConvTensor -- same holder as the reference (pcdet/ops/spconv/structure.py:21-71)."""
+import numpy as np
+import torch
+
+from .. import _lib
+
+
+def scatter_nd(indices, updates, shape):
+    """Reference helper (structure.py:5-18); kept for callers that import it."""
+    ret = torch.zeros(*shape, dtype=updates.dtype, device=updates.device)
+    ndim = indices.shape[-1]
+    output_shape = list(indices.shape[:-1]) + shape[indices.shape[-1]:]
+    flatted_indices = indices.view(-1, ndim)
+    slices = [flatted_indices[:, i] for i in range(ndim)]
+    slices += [Ellipsis]
+    ret[slices] = updates.view(*output_shape)
+    return ret
+
+
+class SparseConvTensor(object):
+    """features [N,C], indices [N,ndim+1] int32 (batch first), spatial_shape, batch_size.
+
+    ``indice_dict`` maps indice_key -> (outids, indices, indice_pairs [K,2,N], indice_pair_num [K],
+    spatial_shape) exactly like conv.py:180-183 and is shared by reference with every tensor derived from
+    this one (conv.py:227).  ``nbr_dict`` is this package's side cache (indice_key -> output-major
+    neighbour map consumed by the CUDA conv); it is shared the same way.
+    """
+
+    def __init__(self, features, indices, spatial_shape, batch_size, grid=None):
+        self.features = features
+        self.indices = indices
+        if self.indices.dtype != torch.int32:
+            self.indices.int()  # no-op kept from the reference (structure.py:37-38): callers pass int32
+        self.spatial_shape = spatial_shape
+        self.batch_size = batch_size
+        self.indice_dict = {}
+        self.nbr_dict = {}
+        self.grid = grid
+
+    @property
+    def spatial_size(self):
+        return np.prod(self.spatial_shape)
+
+    def find_indice_pair(self, key):
+        if key is None:
+            return None
+        if key in self.indice_dict:
+            return self.indice_dict[key]
+        return None
+
+    def dense(self, channels_first=True):
+        """structure.py:57-66.  fp32 CUDA features go through fv2p_dense_ncdhw."""
+        shape = [int(s) for s in self.spatial_shape]
+        f = self.features
+        if channels_first and len(shape) == 3 and f.is_cuda and f.dtype == torch.float32 and \
+                self.indices.dtype == torch.int32:
+            _lib.require_device(f)
+            f = f.contiguous()
+            ind = self.indices.contiguous()
+            out = torch.zeros([self.batch_size, f.shape[1]] + shape, dtype=f.dtype, device=f.device)
+            if f.shape[0]:
+                _lib.check(_lib.load().fv2p_dense_ncdhw(_lib.ptr(f), _lib.ptr(ind), f.shape[0], None, f.shape[1],
+                                                        _lib.i32x3(shape), _lib.ptr(out), _lib.stream_ptr(f.device)),
+                           "dense")
+            return out
+        output_shape = [self.batch_size] + shape + [f.shape[1]]
+        res = scatter_nd(self.indices.long(), f, output_shape)
+        if not channels_first:
+            return res
+        ndim = len(shape)
+        trans_params = list(range(0, ndim + 1))
+        trans_params.insert(1, ndim + 1)
+        return res.permute(*trans_params).contiguous()
+
+    @property
+    def sparity(self):
+        return self.indices.shape[0] / np.prod(self.spatial_shape) / self.batch_size

@@ -1,0 +1,202 @@
+/*
+ * fv2p_b200.h -- C ABI of libfv2p_b200.so: B200 (sm_100a) voxelization + sparse 3D convolution.
+ *
+ * This is the drop-in boundary for the hot path of jialeli1/From-Voxel-to-Point.  It replaces the
+ * reference's pybind11 module `sparse_conv_ext` (pcdet/ops/spconv/src/all.cc:22-71) for the entries
+ * the path uses, and the numba voxelizer + MeanVFE, with plain `extern "C"` symbols: raw device
+ * pointers, sizes and a cudaStream_t.  No torch types, no pybind.  Citations are relative to
+ * /root/reference.
+ *
+ * Conventions
+ *  - Every pointer named *_dev or documented "device" is a CUDA device pointer; small geometry arrays
+ *    (shape3, ksize3, ...) are HOST pointers read before the call returns.
+ *  - The library never allocates device memory.  The caller passes a workspace whose size comes from
+ *    the matching *_workspace_bytes() function, and output buffers sized for the stated capacity.
+ *  - Calls are stream-ordered on `stream` and never synchronise, except the two reference-shaped
+ *    entries that must return a host count (fv2p_get_indice_pairs_3d, fv2p_voxel_generate).
+ *  - Row counts that depend on the data live in device scalars (int32).  A kernel that would exceed
+ *    a caller-stated capacity sets a bit in `status_dev` (if given) instead of writing out of bounds.
+ *  - Return value: 0 = ok, <0 = FV2P_ERR_*, >0 = cudaError_t.  fv2p_last_error() gives the message
+ *    (thread-local).  There is no CPU fallback: the library only does anything on an sm_100 device.
+ *  - Data layouts are the reference's: indices [N,4] int32 (batch,z,y,x); indice pairs [K,2,N] int32
+ *    padded with -1; pair counts [K] int32; features [N,C] row-major; filters [kD,kH,kW,Cin,Cout].
+ *    K = kD*kH*kW <= FV2P_MAX_KVOL.
+ *  - The neighbour map `nbr` [K, nbr_stride] int32 is this library's own conv operand: nbr[k][i] is
+ *    the INPUT row feeding OUTPUT row i through kernel offset k, or -1.  It carries the same
+ *    information as the pair tensor, output-major.
+ */
+#ifndef FV2P_B200_H_
+#define FV2P_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FV2P_ABI_VERSION 1
+#define FV2P_MAX_KVOL 32
+
+#define FV2P_OK 0
+#define FV2P_ERR_INVALID (-1)     /* bad argument (reference: TV_ASSERT_INVALID_ARG -> ValueError) */
+#define FV2P_ERR_WORKSPACE (-2)   /* workspace too small */
+#define FV2P_ERR_UNSUPPORTED (-3) /* valid in the reference, not built here (e.g. transpose conv) */
+#define FV2P_ERR_DEVICE (-4)      /* no sm_100 device / wrong architecture */
+
+/* bits OR-ed into *status_dev by kernels */
+#define FV2P_STATUS_OUT_OVERFLOW 1   /* more active outputs than out_cap */
+#define FV2P_STATUS_VOXEL_OVERFLOW 2 /* more voxels than the output capacity */
+
+/* conv arithmetic modes */
+#define FV2P_MODE_F32 0      /* fp32 in/out, fp32 FMA on CUDA cores (any channel count)            */
+#define FV2P_MODE_BF16_TC 1  /* bf16 in/out, tcgen05 kind::f16, fp32 accumulation in TMEM          */
+#define FV2P_MODE_TF32X3_TC 2 /* fp32 in/out, tcgen05 kind::tf32 with 3-term split, fp32-accurate  */
+#define FV2P_MODE_BF16_SIMT 3 /* bf16 in/out on CUDA cores (first layer, odd channel counts)       */
+#define FV2P_MODE_F32_IN_BF16_OUT 4 /* fp32 in, bf16 out on CUDA cores (entry layer of bf16 path)  */
+
+typedef void *fv2p_stream_t; /* cudaStream_t */
+
+#if defined(__GNUC__)
+#define FV2P_API __attribute__((visibility("default")))
+#else
+#define FV2P_API
+#endif
+
+FV2P_API int fv2p_abi_version(void);
+FV2P_API const char *fv2p_last_error(void);
+/* Fails with FV2P_ERR_DEVICE unless the current device is compute capability 10.x. */
+FV2P_API int fv2p_device_check(int *sm_count, int *cc_major, int *cc_minor);
+
+/* ---------------------------------------------------------------------------------------------
+ * Voxelization + mean VFE in one pass.
+ * Replaces VoxelGenerator.generate (pcdet/datasets/processor/voxel_generator.py:35-39,75-207, numba,
+ * CPU, one frame per call) followed by MeanVFE.forward (pcdet/models/backbones_3d/vfe/mean_vfe.py:
+ * 14-31), for a whole batch of frames per call, and writes the collate_batch layout
+ * (pcdet/datasets/dataset.py:164-169): coords [M,4] = (batch,z,y,x), frames contiguous.
+ *   points        device [total_points, num_features] fp32, frames concatenated
+ *   frame_offsets device [batch+1] int32, frame b = rows [off[b], off[b+1])
+ *   max_frame_points  host upper bound of the largest frame (used to size the work decomposition)
+ *   range6/vsize3 host fp32 (the reference casts both to fp32, voxel_generator.py:22-24)
+ *   coords        device [cap,4] int32 out
+ *   voxel_features device [cap,num_features] fp32 out (mean of the kept points)
+ *   num_points    device [cap] int32 out, or NULL
+ *   voxels        device [cap,max_points,num_features] fp32 out (the legacy padded tensor), or NULL
+ *   voxel_offsets device [batch+1] int32 out: frame b owns voxel rows [voff[b], voff[b+1]); voff[batch]=M
+ *   cap           rows available in the outputs (>= min(total_points, batch*max_voxels) is always enough)
+ * Semantics are the numba loop's: voxel ids in first-arrival order of the points, at most max_points
+ * lowest-index points kept per voxel, and the `break` when voxel number max_voxels would be opened
+ * (every later point of that frame is dropped).
+ * ------------------------------------------------------------------------------------------- */
+FV2P_API size_t fv2p_voxelize_workspace_bytes(int64_t total_points, int batch, int64_t max_frame_points,
+                                     int max_points, int64_t cap);
+FV2P_API int fv2p_voxelize_mean(const float *points, const int32_t *frame_offsets, int64_t total_points,
+                       int batch, int64_t max_frame_points, int num_features, const float *range6,
+                       const float *vsize3, int max_points, int max_voxels, int32_t *coords,
+                       float *voxel_features, int32_t *num_points, float *voxels,
+                       int32_t *voxel_offsets, int64_t cap, int32_t *status_dev, void *workspace,
+                       size_t workspace_bytes, fv2p_stream_t stream);
+
+/* Reference-shaped single-frame entry (VoxelGenerator.generate): synchronises and returns the voxel
+ * count through *num_voxels_host.  Outputs as above with batch = 1 (coords still [M,4]). */
+FV2P_API int fv2p_voxel_generate(const float *points, int64_t num_points_in, int num_features,
+                        const float *range6, const float *vsize3, int max_points, int max_voxels,
+                        int32_t *coords, float *voxel_features, int32_t *num_points, float *voxels,
+                        int64_t cap, int32_t *num_voxels_host, void *workspace, size_t workspace_bytes,
+                        fv2p_stream_t stream);
+
+/* MeanVFE.forward alone (mean_vfe.py:26-28) for callers that already hold the padded tensor. */
+FV2P_API int fv2p_mean_vfe(const float *voxels, const int32_t *num_points, int64_t num_voxels, int max_points,
+                  int num_features, float *out, fv2p_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Rulebooks (indice pairs).  Replace getIndicePair<3> (include/spconv/spconv_ops.h:28-141) and its
+ * functors (src/indice.cc, src/indice_cuda.cu, include/spconv/indice.cu.h, geometry.h:25-297).
+ * Results are bit-identical to the reference's CPU path (the deterministic one): submanifold pairs
+ * ascending by input row inside each offset; strided outputs in first-touch order.
+ *
+ *   indices   device [n_cap,4] int32;  the live row count is *n_dev if n_dev != NULL, else n_cap
+ *   pairs     device [K,2,pair_stride] int32 out or NULL; rows >= the live count are not touched
+ *             beyond index n-1 (the -1 tail is written up to n)
+ *   pair_num  device [K] int32 out or NULL
+ *   nbr       device [K,nbr_stride] int32 out or NULL (see header comment)
+ * ------------------------------------------------------------------------------------------- */
+FV2P_API size_t fv2p_rulebook_workspace_bytes(int64_t n_in_cap, int64_t n_out_cap, int kvol);
+
+FV2P_API int fv2p_rulebook_subm(const int32_t *indices, int64_t n_cap, const int32_t *n_dev, int batch,
+                       const int32_t *shape3, const int32_t *ksize3, const int32_t *dilation3,
+                       int32_t *pairs, int64_t pair_stride, int32_t *pair_num, int32_t *nbr,
+                       int64_t nbr_stride, void *workspace, size_t workspace_bytes,
+                       fv2p_stream_t stream);
+
+/*   out_indices device [out_cap,4] int32 out;  n_out_dev device int32 out (live output rows)      */
+FV2P_API int fv2p_rulebook_conv(const int32_t *indices, int64_t n_cap, const int32_t *n_dev, int batch,
+                       const int32_t *out_shape3, const int32_t *ksize3, const int32_t *stride3,
+                       const int32_t *pad3, const int32_t *dilation3, int32_t *out_indices,
+                       int64_t out_cap, int32_t *n_out_dev, int32_t *pairs, int64_t pair_stride,
+                       int32_t *pair_num, int32_t *nbr, int64_t nbr_stride, int32_t *status_dev,
+                       void *workspace, size_t workspace_bytes, fv2p_stream_t stream);
+
+/* Reference-shaped entry: sparse_conv_ext.get_indice_pairs_3d (all.cc:26, spconv_ops.h:28-33), same
+ * argument order.  subm != 0 forces stride 1 / padding ksize/2 like spconv_ops.h:76-80 and copies
+ * `indices` to out_indices.  Synchronises; *num_act_out_host receives the output row count.
+ * pairs is [K,2,n] (pair_stride = n).  transpose != 0 -> FV2P_ERR_UNSUPPORTED. */
+FV2P_API int fv2p_get_indice_pairs_3d(const int32_t *indices, int64_t n, int batch, const int32_t *out_shape3,
+                             const int32_t *spatial_shape3, const int32_t *ksize3,
+                             const int32_t *stride3, const int32_t *pad3, const int32_t *dilation3,
+                             const int32_t *out_pad3, int subm, int transpose, int32_t *out_indices,
+                             int64_t out_cap, int32_t *pairs, int32_t *pair_num, int32_t *nbr,
+                             int64_t nbr_stride, int32_t *num_act_out_host, void *workspace,
+                             size_t workspace_bytes, fv2p_stream_t stream);
+
+/* Output-major neighbour map from a reference-layout pair tensor (any producer). */
+FV2P_API int fv2p_pairs_to_nbr(const int32_t *pairs, const int32_t *pair_num, int kvol, int64_t pair_stride,
+                      int inverse, int64_t n_out, int32_t *nbr, int64_t nbr_stride,
+                      fv2p_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Sparse convolution forward with fused epilogue.  Replaces indiceConv<T> (spconv_ops.h:261-362:
+ * per-offset gather -> torch::mm_out -> scatter-add), the bias add of conv.py:223-224, and the
+ * BatchNorm1d(eval) + residual + ReLU that follow in the backbones (spconv_backbone.py:25-27,57-66):
+ *     out[i,:] = act( (sum_k X[nbr[k][i],:] * W[k] + bias) * scale + shift + residual[i,:] )
+ * Any of bias/scale/shift/residual may be NULL.  scale/shift are the folded eval BatchNorm:
+ * scale = gamma / sqrt(var + eps), shift = beta - mean * scale.
+ *   features  device [*,cin]   (fp32 or bf16 by mode)
+ *   weight    device: FV2P_MODE_F32 / *_SIMT: [K,cin,cout] fp32 (the reference layout, flattened);
+ *             tensor-core modes: the packed image written by fv2p_pack_weight
+ *   n_out_cap rows of `out`/`nbr` columns; live count *n_out_dev if given
+ * ------------------------------------------------------------------------------------------- */
+FV2P_API int fv2p_conv_fwd(const void *features, const void *weight, const int32_t *nbr, int64_t nbr_stride,
+                  int kvol, int64_t n_out_cap, const int32_t *n_out_dev, int cin, int cout,
+                  const float *bias, const float *scale, const float *shift, const void *residual,
+                  int relu, int mode, void *out, fv2p_stream_t stream);
+
+/* Packed weight image for the tensor-core modes (done once per layer, device to device). */
+FV2P_API size_t fv2p_pack_weight_bytes(int kvol, int cin, int cout, int mode);
+FV2P_API int fv2p_pack_weight(const float *weight_f32, int kvol, int cin, int cout, int mode, void *packed,
+                     fv2p_stream_t stream);
+
+/* Reference-shaped entry: sparse_conv_ext.indice_conv_fp32 (all.cc:38, spconv_ops.h:261-263) on a
+ * reference-layout pair tensor; workspace holds the temporary neighbour map
+ * (fv2p_indice_conv_workspace_bytes).  Result rows not touched by any pair are zero like the
+ * reference's torch::zeros output (spconv_ops.h:294). */
+FV2P_API size_t fv2p_indice_conv_workspace_bytes(int kvol, int64_t num_act_out);
+FV2P_API int fv2p_indice_conv_fp32(const float *features, const float *filters, const int32_t *pairs,
+                          const int32_t *pair_num, int64_t pair_stride, int64_t num_act_out,
+                          int inverse, int subm, int kvol, int cin, int cout, float *out,
+                          void *workspace, size_t workspace_bytes, fv2p_stream_t stream);
+
+/* SparseConvTensor.dense() (pcdet/ops/spconv/structure.py:57-66) in channels-first layout
+ * [batch, C, D, H, W]; `dense` must be zero-filled by the caller. features fp32. */
+FV2P_API int fv2p_dense_ncdhw(const float *features, const int32_t *indices, int64_t n_cap,
+                     const int32_t *n_dev, int channels, const int32_t *shape3, float *dense,
+                     fv2p_stream_t stream);
+
+/* dtype helpers used by the bf16 path */
+FV2P_API int fv2p_cast_f32_to_bf16(const float *src, void *dst, int64_t count, fv2p_stream_t stream);
+FV2P_API int fv2p_cast_bf16_to_f32(const void *src, float *dst, int64_t count, fv2p_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FV2P_B200_H_ */

@@ -1,0 +1,201 @@
+"""Access to the REAL reference for pinning the oracle and for the reference CPU arm.
+TEST INFRASTRUCTURE ONLY -- never imported by the product package.
+
+Two levels:
+
+* ``load_ext()``: the reference's compiled ``sparse_conv_ext`` from ``oracle/_ref/`` (built by
+  ``oracle/build_ref.py``).  Works wherever the prebuilt file travelled to (this container and the
+  GPU box).  ``ext_backbone_forward`` drives the two backbones through that extension with the
+  exact call sequence of conv.py:113-229 / spconv_backbone.py:134-186,241-290 (rulebook cache per
+  indice_key, indice_conv_fp32, bias, BatchNorm1d eval, residual, ReLU) using torch CPU ops.
+* ``load_reference_python()``: additionally imports the reference's *Python* files in place from
+  /root/reference (numba voxelizer, MeanVFE, spconv package, backbones).  Only possible in the build
+  container; used by tests/golden/make_golden.py to generate the committed fixtures.
+"""
+import importlib
+import importlib.machinery
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+
+from . import build_ref
+from .oracle import backbone_plan, conv_output_size, _triple
+
+REF_ROOT = build_ref.REF_ROOT
+_ext = None
+
+
+def have_ext():
+    return build_ref.built_path() is not None
+
+
+def load_ext():
+    """Import oracle/_ref/sparse_conv_ext*.so (pybind module of src/all.cc:22-71)."""
+    global _ext
+    if _ext is None:
+        path = build_ref.built_path()
+        if path is None:
+            raise FileNotFoundError("oracle/_ref/sparse_conv_ext.so missing: run `python oracle/build_ref.py` "
+                                    "in the build container")
+        import torch  # noqa: F401  (libtorch must be loaded before the extension)
+        loader = importlib.machinery.ExtensionFileLoader(build_ref.EXT_NAME, path)
+        spec = importlib.util.spec_from_loader(build_ref.EXT_NAME, loader)
+        mod = importlib.util.module_from_spec(spec)
+        loader.exec_module(mod)
+        _ext = mod
+    return _ext
+
+
+# --------------------------------------------------------------------------------------------
+# reference extension driven directly (runs on the GPU box too)
+# --------------------------------------------------------------------------------------------
+def ext_get_indice_pairs(indices, batch, in_shape, ksize, stride, pad, dil, subm):
+    """ops.py:46-94 -> sparse_conv_ext.get_indice_pairs_3d (spconv_ops.h:28)."""
+    ext = load_ext()
+    ks, st, pd, dl = _triple(ksize), _triple(stride), _triple(pad), _triple(dil)
+    in_shape = [int(s) for s in in_shape]
+    out_shape = in_shape if subm else conv_output_size(in_shape, ks, st, pd, dl)
+    outids, pairs, num = ext.get_indice_pairs_3d(indices, int(batch), out_shape, in_shape, ks, st, pd, dl,
+                                                 [0, 0, 0], int(subm), 0)
+    return outids, pairs, num, out_shape
+
+
+def ext_backbone_forward(name, params, voxel_features, voxel_coords, batch_size, sparse_shape, last_pad=0,
+                         timers=None):
+    """Eval forward of VoxelBackBone8x / VoxelResBackBone8x through the reference extension (CPU tensors).
+
+    params: {state_dict key: torch.Tensor (cpu, fp32)}.  Returns the same structure as
+    oracle.backbone_forward but with torch tensors.
+    """
+    import time
+
+    import torch
+    import torch.nn.functional as F
+
+    ext = load_ext()
+    feats = torch.as_tensor(voxel_features, dtype=torch.float32)
+    inds = torch.as_tensor(voxel_coords).int().contiguous()
+    shape = [int(s) for s in sparse_shape]
+    books = {}
+    t_rb = t_cv = 0.0
+
+    def conv(feats, inds, shape, prefix, kind, key, ksize, stride, pad):
+        nonlocal t_rb, t_cv
+        t0 = time.perf_counter()
+        if key in books:
+            outids, pairs, num, oshape = books[key]
+        else:
+            outids, pairs, num, oshape = ext_get_indice_pairs(inds, batch_size, shape, ksize, stride, pad, 1,
+                                                              kind == "subm")
+            books[key] = (outids, pairs, num, oshape)
+        t1 = time.perf_counter()
+        w = params[prefix + ".weight"]
+        out = ext.indice_conv_fp32(feats, w, pairs, num, outids.shape[0], 0, int(kind == "subm"))
+        b = params.get(prefix + ".bias")
+        if b is not None:
+            out += b
+        t_rb += t1 - t0
+        t_cv += time.perf_counter() - t1
+        return out, outids, oshape
+
+    def bn(x, prefix):
+        return F.batch_norm(x, params[prefix + ".running_mean"], params[prefix + ".running_var"],
+                            params[prefix + ".weight"], params[prefix + ".bias"], False, 0.01, 1e-3)
+
+    outs = {}
+    with torch.no_grad():
+        for stage, ops in backbone_plan(name, feats.shape[1], last_pad):
+            for op in ops:
+                if op["op"] == "conv":
+                    feats, inds, shape = conv(feats, inds, shape, op["conv"], op["kind"], op["key"], op["ksize"],
+                                              op["stride"], op["pad"])
+                    feats = torch.relu(bn(feats, op["bn"]))
+                else:
+                    p = op["prefix"]
+                    identity = feats
+                    f1, inds, shape = conv(feats, inds, shape, p + ".conv1", "subm", op["key"], 3, 1, 1)
+                    f1 = torch.relu(bn(f1, p + ".bn1"))
+                    f2, inds, shape = conv(f1, inds, shape, p + ".conv2", "subm", op["key"], 3, 1, 1)
+                    f2 = bn(f2, p + ".bn2")
+                    f2 += identity
+                    feats = torch.relu(f2)
+            tag = {"conv1": "x_conv1", "conv2": "x_conv2", "conv3": "x_conv3", "conv4": "x_conv4",
+                   "conv_out": "out"}.get(stage)
+            if tag:
+                outs[tag] = (feats, inds, list(shape))
+    outs["rulebooks"] = {k: v[:3] for k, v in books.items()}
+    if timers is not None:
+        timers["rulebook_s"] = timers.get("rulebook_s", 0.0) + t_rb
+        timers["conv_s"] = timers.get("conv_s", 0.0) + t_cv
+    return outs
+
+
+# --------------------------------------------------------------------------------------------
+# reference Python imported in place (build container only)
+# --------------------------------------------------------------------------------------------
+def have_reference_python():
+    return os.path.isdir(os.path.join(REF_ROOT, "pcdet", "ops", "spconv"))
+
+
+def _stub_pkg(name, path):
+    mod = types.ModuleType(name)
+    mod.__path__ = [path]
+    sys.modules[name] = mod
+    return mod
+
+
+def load_reference_python():
+    """Returns a namespace with the reference's VoxelGenerator, MeanVFE, spconv package and backbones.
+
+    Parent packages are registered as bare stubs whose __path__ points into /root/reference so that the
+    reference files are imported unmodified without executing pcdet/__init__.py (which needs easydict,
+    tensorboardX, skimage -- absent here).  mmcv.cnn.CONV_LAYERS (conv.py:17) is stubbed: it is a
+    registry decorator with no arithmetic.
+    """
+    if not have_reference_python():
+        raise FileNotFoundError(REF_ROOT + " is not present (only exists in the build container)")
+    if "pcdet.ops.spconv" in sys.modules and hasattr(sys.modules["pcdet.ops.spconv"], "SparseConvTensor"):
+        return _namespace()
+    ext = load_ext()
+    cnn = types.ModuleType("mmcv.cnn")
+
+    class _Registry:
+        def register_module(self, *a, **k):
+            return lambda cls: cls
+
+    cnn.CONV_LAYERS = _Registry()
+    mm = types.ModuleType("mmcv")
+    mm.cnn = cnn
+    sys.modules.setdefault("mmcv", mm)
+    sys.modules.setdefault("mmcv.cnn", cnn)
+    root = os.path.join(REF_ROOT, "pcdet")
+    _stub_pkg("pcdet", root)
+    _stub_pkg("pcdet.ops", os.path.join(root, "ops"))
+    _stub_pkg("pcdet.models", os.path.join(root, "models"))
+    _stub_pkg("pcdet.models.backbones_3d", os.path.join(root, "models", "backbones_3d"))
+    _stub_pkg("pcdet.models.backbones_3d.vfe", os.path.join(root, "models", "backbones_3d", "vfe"))
+    _stub_pkg("pcdet.datasets", os.path.join(root, "datasets"))
+    _stub_pkg("pcdet.datasets.processor", os.path.join(root, "datasets", "processor"))
+    sys.modules["pcdet.ops.spconv.sparse_conv_ext"] = ext  # ops.py:17 `from . import sparse_conv_ext`
+    sp = importlib.import_module("pcdet.ops.spconv")
+    sys.modules["pcdet.ops"].spconv = sp
+    return _namespace()
+
+
+def _namespace():
+    ns = types.SimpleNamespace()
+    ns.spconv = importlib.import_module("pcdet.ops.spconv")
+    ns.VoxelGenerator = importlib.import_module("pcdet.datasets.processor.voxel_generator").VoxelGenerator
+    ns.MeanVFE = importlib.import_module("pcdet.models.backbones_3d.vfe.mean_vfe").MeanVFE
+    bb = importlib.import_module("pcdet.models.backbones_3d.spconv_backbone")
+    ns.VoxelBackBone8x = bb.VoxelBackBone8x
+    ns.VoxelResBackBone8x = bb.VoxelResBackBone8x
+    ns.ext = load_ext()
+    return ns
+
+
+def to_numpy_params(state_dict):
+    return {k: v.detach().cpu().numpy() for k, v in state_dict.items() if v.dtype.is_floating_point}
