@@ -356,6 +356,16 @@ class BackboneEngine(object):
             outs[st.export] = t
         return outs, n
 
+    def launch_count(self):
+        """Kernels of libfv2p_b200 enqueued by one launch(): rulebook chains + one fused conv per layer."""
+        n = len(self.steps)
+        for bk in self.books:
+            if bk.subm:
+                n += 5 if self.materialize_pairs else 3  # clear, insert, probe (+ scan, compact)
+            else:
+                n += 9 if self.materialize_pairs else 7  # clear, insert, winners, scan, assign, fill, pairs (+2)
+        return n
+
     def __call__(self, voxel_features, voxel_coords, batch_size):
         a = self.launch(voxel_features, voxel_coords, batch_size)
         return self.collect(a, voxel_coords, batch_size)[0]

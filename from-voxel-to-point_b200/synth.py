@@ -108,7 +108,7 @@ def randomize_state(state_dict, seed=0):
 
     Works on any mapping name -> tensor/ndarray with the reference's key names (conv ``weight``
     [kD,kH,kW,Cin,Cout] / ``bias``, BatchNorm ``weight bias running_mean running_var``), so the
-    reference modules, this package's modules and the numpy oracle can all be loaded with the SAME
+    reference modules, this package's modules and any CPU checker can all be loaded with the SAME
     numbers without shipping multi-megabyte fixtures.  Conv init follows conv.py:106-111
     (kaiming-uniform, a=sqrt(5) -> U(-1/sqrt(fan_in), 1/sqrt(fan_in))); BatchNorm statistics follow
     SURVEY.md section 8d (gamma~U(.5,1.5), beta~N(0,.1), mean~N(0,.1), var~U(.5,1.5)).

@@ -1,0 +1,352 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the committed reference
+fixtures.  Bar: voxel coordinates, counts and rulebooks BIT-EXACT; features within 1e-4 relative
+(max|a-b|/max|b| per tensor) on the fp32 path, within 3e-2 on the bf16 path."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_err
+from oracle import oracle as O
+
+import fv2p_b200
+from fv2p_b200 import _lib, spconv, synth
+
+pytestmark = pytest.mark.gpu
+FP32_TOL = 1e-4
+BF16_TOL = 3e-2
+DEV = "cuda:0"
+
+
+def cuda(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    return t.to(dtype) if dtype is not None else t
+
+
+def test_native_library_is_loaded_and_device_is_sm100():
+    lib = _lib.load()
+    sm, major, minor = (_lib.ctypes.c_int(0) for _ in range(3))
+    st = lib.fv2p_device_check(_lib.ctypes.byref(sm), _lib.ctypes.byref(major), _lib.ctypes.byref(minor))
+    assert st == 0, _lib.last_error()
+    assert major.value == 10 and sm.value >= 100
+
+
+# ------------------------------------------------------------------------------------- voxelizer
+def test_voxelizer_matches_reference_fixtures():
+    g = load_golden("voxelize")
+    for i in range(int(g["n_cases"])):
+        vg = fv2p_b200.VoxelGenerator(g[f"c{i}_voxel_size"], g[f"c{i}_range"], int(g[f"c{i}_T"]),
+                                      int(g[f"c{i}_max_voxels"]))
+        voxels, coors, num = vg.generate(g[f"c{i}_points"])
+        assert np.array_equal(coors, g[f"c{i}_coors"]), i
+        assert np.array_equal(num, g[f"c{i}_num"]), i
+        assert np.array_equal(voxels, g[f"c{i}_voxels"]), i
+        assert rel_err(vg.last_voxel_features.cpu().numpy(), g[f"c{i}_mean"]) < 1e-6, i
+        # MeanVFE module on the padded tensor (reference batch_dict contract: counts arrive as floats)
+        bd = fv2p_b200.MeanVFE({}, voxels.shape[2])({"voxels": cuda(voxels), "voxel_num_points": cuda(num).float()})
+        assert rel_err(bd["voxel_features"].cpu().numpy(), g[f"c{i}_mean"]) < 1e-6, i
+
+
+@pytest.mark.parametrize("ds,shuffle,max_voxels", [("kitti", False, 40000), ("kitti", True, 16000),
+                                                   ("kitti", True, 5000), ("waymo", False, 90000),
+                                                   ("waymo", True, 30000)])
+def test_voxelizer_full_frames_match_oracle(ds, shuffle, max_voxels):
+    cfg = synth.DATASETS[ds]
+    pts = synth.lidar_frame(ds, seed=11, shuffle=shuffle)
+    ref = O.voxelize(pts, cfg["voxel_size"], cfg["point_cloud_range"], 5, max_voxels)
+    vg = fv2p_b200.VoxelGenerator(cfg["voxel_size"], cfg["point_cloud_range"], 5, max_voxels)
+    got = vg.generate(pts)
+    for a, b in zip(got, ref):
+        assert np.array_equal(a, b)
+    assert rel_err(vg.last_voxel_features.cpu().numpy(), O.mean_vfe(ref[0], ref[2])) < 1e-6
+
+
+def test_batch_voxelizer_ragged_batch_and_empty_frame():
+    cfg = synth.DATASETS["kitti"]
+    frames = [synth.lidar_frame("kitti", seed=s, az_steps=a, shuffle=sh)
+              for s, a, sh in ((1, 300, False), (2, 40, True), (3, 120, False))]
+    frames.insert(2, np.zeros((0, 4), np.float32))  # an empty frame in the middle
+    max_voxels = 9000
+    offs = np.concatenate([[0], np.cumsum([f.shape[0] for f in frames])]).astype(np.int32)
+    bv = fv2p_b200.BatchVoxelizer(cfg["voxel_size"], cfg["point_cloud_range"], 5, max_voxels, want_voxels=True)
+    out = bv(cuda(np.concatenate(frames)), cuda(offs), max(f.shape[0] for f in frames))
+    voff = out["voxel_offsets"].cpu().numpy()
+    assert int(out["status"].item()) == 0
+    exp_coords, exp_feat, exp_num = [], [], []
+    for b, f in enumerate(frames):
+        v, c, n = O.voxelize(f, cfg["voxel_size"], cfg["point_cloud_range"], 5, max_voxels)
+        assert voff[b + 1] - voff[b] == c.shape[0]
+        exp_coords.append(np.concatenate([np.full((c.shape[0], 1), b, np.int32), c], 1))
+        exp_feat.append(O.mean_vfe(v, n))
+        exp_num.append(n)
+    m = voff[-1]
+    assert np.array_equal(out["voxel_coords"][:m].cpu().numpy(), np.concatenate(exp_coords))
+    assert np.array_equal(out["voxel_num_points"][:m].cpu().numpy(), np.concatenate(exp_num))
+    assert rel_err(out["voxel_features"][:m].cpu().numpy(), np.concatenate(exp_feat)) < 1e-6
+
+
+def test_voxelizer_is_deterministic_and_permutation_sensitive_like_the_reference():
+    cfg = synth.DATASETS["waymo"]
+    pts = synth.lidar_frame("waymo", seed=5, az_steps=900)
+    vg = fv2p_b200.VoxelGenerator(cfg["voxel_size"], cfg["point_cloud_range"], 5, 20000)
+    a = vg.generate(pts)
+    b = vg.generate(pts)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    # the set of voxels below the cap is order dependent (first arrival), the oracle agrees on a permutation
+    perm = np.random.default_rng(0).permutation(pts.shape[0])
+    c = vg.generate(pts[perm])
+    r = O.voxelize(pts[perm], cfg["voxel_size"], cfg["point_cloud_range"], 5, 20000)
+    for x, y in zip(c, r):
+        assert np.array_equal(x, y)
+
+
+# ------------------------------------------------------------------------------------- rulebooks
+GEOMS = {"subm3": (True, 3, 1, 1), "s2p1": (False, 3, 2, 1), "s2p011": (False, 3, 2, (0, 1, 1)),
+         "down311": (False, (3, 1, 1), (2, 1, 1), 0), "s1p1": (False, 3, 1, 1), "k2s2": (False, 2, 2, 0)}
+
+
+@pytest.mark.parametrize("cset", ["rand", "shuf", "blob"])
+@pytest.mark.parametrize("geom", sorted(GEOMS))
+def test_rulebooks_match_reference_fixtures(cset, geom):
+    g = load_golden("rulebook_conv")
+    subm, ks, st, pd = GEOMS[geom]
+    ind = cuda(g[f"{cset}_indices"])
+    outids, pairs, num, nbr = spconv.ops.get_indice_pairs(ind, int(g[f"{cset}_batch"]), g["shape"].tolist(), ks, st,
+                                                          pd, 1, 0, subm, False, return_nbr=True)
+    assert np.array_equal(outids.cpu().numpy(), g[f"{cset}_{geom}_outids"])
+    assert np.array_equal(num.cpu().numpy(), g[f"{cset}_{geom}_num"])
+    assert np.array_equal(pairs.cpu().numpy(), g[f"{cset}_{geom}_pairs"])
+    # the neighbour map carries the same pairs, output-major
+    p, n, m = pairs.cpu().numpy(), num.cpu().numpy(), nbr.cpu().numpy()
+    assert (m >= 0).sum() == n.sum()
+    for k in range(p.shape[0]):
+        assert np.array_equal(m[k][p[k, 1, :n[k]]], p[k, 0, :n[k]])
+    assert np.array_equal(spconv.ops.pairs_to_nbr(pairs, num, outids.shape[0]).cpu().numpy(), m)
+
+
+@pytest.mark.parametrize("ds", ["kitti", "waymo"])
+def test_rulebooks_full_frame_chain_matches_oracle(ds):
+    """Every rulebook of the backbone, level by level, on a full-size frame (bit-exact incl. the -1 tail)."""
+    cfg = synth.DATASETS[ds]
+    pts = synth.lidar_frame(ds, seed=21)
+    _, c, _ = O.voxelize(pts, cfg["voxel_size"], cfg["point_cloud_range"], 5, cfg["max_voxels"]["test"])
+    ind = O.collate([c])
+    gs = synth.grid_size(cfg)
+    shape = [int(gs[2]) + 1, int(gs[1]), int(gs[0])]
+    chain = [(True, 3, 1, 1), (False, 3, 2, 1), (True, 3, 1, 1), (False, 3, 2, 1), (True, 3, 1, 1),
+             (False, 3, 2, (0, 1, 1)), (True, 3, 1, 1), (False, (3, 1, 1), (2, 1, 1), 0)]
+    for subm, ks, st, pd in chain:
+        got = spconv.ops.get_indice_pairs(cuda(ind), 1, shape, ks, st, pd, 1, 0, subm, False)
+        if subm:
+            ref = O.rulebook_subm(ind, 1, shape, ks, 1)
+        else:
+            ref = O.rulebook_conv(ind, 1, shape, ks, st, pd, 1)
+        for a, b in zip(got, ref[:3]):
+            assert np.array_equal(a.cpu().numpy(), b)
+        if not subm:
+            ind, shape = ref[0], ref[3]
+
+
+def test_rulebook_batch_above_int32_grid_limit():
+    """64 frames in one call: the reference's dense grid overflows int32 past 23 frames;
+    the hash path must equal the per-frame oracle with batch offsets."""
+    shape = [41, 1600, 1408]
+    base = synth.random_voxels(shape, 300, 1, seed=3)
+    frames = []
+    for b in range(64):
+        f = base.copy()
+        f[:, 0] = b
+        frames.append(f)
+    ind = np.concatenate(frames)
+    _, pairs, num = spconv.ops.get_indice_pairs(cuda(ind), 64, shape, 3, 1, 1, 1, 0, True, False)
+    _, p1, n1 = O.rulebook_subm(base, 1, shape, 3, 1)
+    assert np.array_equal(num.cpu().numpy(), n1 * 64)
+    outids, pairs, num = spconv.ops.get_indice_pairs(cuda(ind), 64, shape, 3, 2, 1, 1, 0, False, False)
+    o1, _, n1, _ = O.rulebook_conv(base, 1, shape, 3, 2, 1, 1)
+    assert np.array_equal(num.cpu().numpy(), n1 * 64)
+    assert np.array_equal(outids.cpu().numpy()[-o1.shape[0]:, 1:], o1[:, 1:])
+    assert outids.shape[0] == 64 * o1.shape[0]
+
+
+def test_rulebook_empty_and_single_voxel():
+    empty = torch.zeros((0, 4), dtype=torch.int32, device=DEV)
+    outids, pairs, num = spconv.ops.get_indice_pairs(empty, 1, [8, 8, 8], 3, 1, 1, 1, 0, True, False)
+    assert pairs.shape == (27, 2, 0) and int(num.sum()) == 0
+    outids, pairs, num = spconv.ops.get_indice_pairs(empty, 1, [8, 8, 8], 3, 2, 1, 1, 0, False, False)
+    assert outids.shape[0] == 0 and int(num.sum()) == 0
+    one = np.int32([[0, 0, 0, 0]])
+    got = spconv.ops.get_indice_pairs(cuda(one), 1, [8, 8, 8], 3, 2, 1, 1, 0, False, False)
+    ref = O.rulebook_conv(one, 1, [8, 8, 8], 3, 2, 1, 1)
+    for a, b in zip(got, ref[:3]):
+        assert np.array_equal(a.cpu().numpy(), b)
+
+
+def test_rulebook_dilated_and_even_submanifold_geometries():
+    """Non mirror-symmetric submanifold kernels take the input-side probe path."""
+    ind = synth.random_voxels([9, 20, 20], 900, 2, seed=8)
+    for ks, dil in ((3, 2), ((2, 2, 2), 1), ((1, 3, 3), 1)):
+        got = spconv.ops.get_indice_pairs(cuda(ind), 2, [9, 20, 20], ks, 1, 0, dil, 0, True, False)
+        ref = O.rulebook_subm(ind, 2, [9, 20, 20], ks, dil)
+        for a, b in zip(got, ref):
+            assert np.array_equal(a.cpu().numpy(), b), (ks, dil)
+
+
+# ------------------------------------------------------------------------------------- convolution
+@pytest.mark.parametrize("geom", sorted(GEOMS))
+@pytest.mark.parametrize("ch", [(4, 16), (16, 32), (5, 16)])
+def test_indice_conv_matches_reference_fixtures(geom, ch):
+    g = load_golden("rulebook_conv")
+    key = f"conv_{geom}_{ch[0]}_{ch[1]}"
+    out = spconv.ops.indice_conv(cuda(g[key + "_feats"]), cuda(g[key + "_w"]), cuda(g[f"blob_{geom}_pairs"]),
+                                 cuda(g[f"blob_{geom}_num"]), g[f"blob_{geom}_outids"].shape[0], False, GEOMS[geom][0])
+    assert rel_err(out.cpu().numpy(), g[key + "_out"]) < FP32_TOL
+
+
+@pytest.mark.parametrize("cin,cout", [(16, 16), (32, 64), (64, 64), (128, 128), (7, 19), (64, 128)])
+def test_conv_fused_epilogue_matches_oracle(cin, cout):
+    rng = np.random.default_rng(cin * 1000 + cout)
+    ind = synth.random_voxels([7, 24, 24], 1500, 2, seed=cin)
+    feats = rng.standard_normal((ind.shape[0], cin)).astype(np.float32)
+    w = (rng.standard_normal((27, cin, cout)) / np.sqrt(27 * cin)).astype(np.float32)
+    bias, gamma, beta, mean = (rng.standard_normal(cout).astype(np.float32) * 0.1 for _ in range(4))
+    var = rng.uniform(0.5, 1.5, cout).astype(np.float32)
+    res = rng.standard_normal((ind.shape[0], cout)).astype(np.float32)
+    _, pairs, num = O.rulebook_subm(ind, 2, [7, 24, 24], 3, 1)
+    ref = O.bias_bn_res_relu(O.indice_conv(feats, w, pairs, num, ind.shape[0], False, True), bias,
+                             (gamma + 1, beta, mean, var), res, True)
+    _, _, _, nbr = spconv.ops.get_indice_pairs(cuda(ind), 2, [7, 24, 24], 3, 1, 1, 1, 0, True, False, return_nbr=True)
+    scale = (gamma + 1) / np.sqrt(var + 1e-3)
+    shift = beta - mean * scale
+    out = spconv.ops.conv_forward(cuda(feats), cuda(w), nbr, ind.shape[0], cuda(bias), cuda(scale.astype(np.float32)),
+                                  cuda(shift.astype(np.float32)), cuda(res), True)
+    assert rel_err(out.cpu().numpy(), ref) < FP32_TOL
+
+
+def test_sparse_conv_equals_dense_conv3d():
+    """The property the reference's test_utils.py:144-193 was written for: sparse conv == F.conv3d on .dense()."""
+    torch.manual_seed(0)
+    torch.backends.cudnn.allow_tf32 = False  # the dense comparison must be true fp32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    shape = [6, 10, 9]
+    ind = synth.random_voxels(shape, 200, 2, seed=4)
+    feats = torch.randn(ind.shape[0], 8, device=DEV)
+    x = spconv.SparseConvTensor(feats, cuda(ind), shape, 2)
+    for conv in (spconv.SparseConv3d(8, 12, 3, stride=2, padding=1, bias=True),
+                 spconv.SparseConv3d(8, 12, (3, 1, 1), stride=(2, 1, 1), padding=0, bias=False),
+                 spconv.SparseConv3d(8, 12, 3, stride=1, padding=1, bias=True)):
+        conv = conv.to(DEV)
+        y = conv(x)
+        w = conv.weight.permute(4, 3, 0, 1, 2).contiguous()
+        ref = torch.nn.functional.conv3d(x.dense(), w, conv.bias, conv.stride, conv.padding)
+        dense = y.dense()
+        # a strided sparse conv only materialises outputs that have at least one active input
+        mask = (y.dense().abs().sum(1, keepdim=True) > 0) | (ref.abs().sum(1, keepdim=True) == 0)
+        assert dense.shape == ref.shape
+        assert torch.allclose(dense * mask, ref * mask, atol=1e-4, rtol=1e-4)
+    sub = spconv.SubMConv3d(8, 12, 3, bias=False, indice_key="s").to(DEV)
+    y = sub(x)
+    w = sub.weight.permute(4, 3, 0, 1, 2).contiguous()
+    ref = torch.nn.functional.conv3d(x.dense(), w, None, 1, 1)
+    active = (x.dense().abs().sum(1, keepdim=True) > 0).float()
+    assert torch.allclose(y.dense(), ref * active, atol=1e-4, rtol=1e-4)
+
+
+# ------------------------------------------------------------------------------------- backbones
+def _load_backbone(name, in_ch, grid, seed, cfg=None):
+    net = getattr(fv2p_b200, name)(dict(cfg or {}), in_ch, np.array(grid)).eval()
+    state = synth.randomize_state(net.state_dict(), seed=seed)
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in state.items()}, strict=False)
+    return net.to(DEV), state
+
+
+@pytest.mark.parametrize("ds", ["kitti", "waymo"])
+@pytest.mark.parametrize("name", ["VoxelBackBone8x", "VoxelResBackBone8x"])
+@pytest.mark.parametrize("fused", [True, False])
+def test_backbone_matches_reference_fixtures(ds, name, fused):
+    g = load_golden(f"backbone_{ds}_{name}")
+    net, _ = _load_backbone(name, g["voxel_features"].shape[1], g["grid_size"], int(g["seed"]), {"FUSED": fused})
+    bd = {"voxel_features": cuda(g["voxel_features"]), "voxel_coords": cuda(g["voxel_coords"]).float(),
+          "batch_size": int(g["batch_size"])}
+    with torch.no_grad():
+        bd = net(bd)
+    outs = dict(bd["multi_scale_3d_features"], out=bd["encoded_spconv_tensor"])
+    for k in ("x_conv1", "x_conv2", "x_conv3", "x_conv4", "out"):
+        assert np.array_equal(outs[k].indices.cpu().numpy(), g[k + "_indices"]), k
+        assert rel_err(outs[k].features.float().cpu().numpy(), g[k + "_features"]) < FP32_TOL, k
+    assert list(outs["out"].spatial_shape) == g["out_shape"].tolist()
+    idict = outs["out"].indice_dict
+    for key in [f[3:-4] for f in g.files if f.startswith("rb_") and f.endswith("_num")]:
+        outids, _, pairs, num, _ = idict[key]
+        assert np.array_equal(num.cpu().numpy(), g[f"rb_{key}_num"]), key
+        assert outids.shape[0] == int(g[f"rb_{key}_nout"]), key
+        assert pairs.shape[0] == num.shape[0] and pairs.shape[1] == 2
+
+
+@pytest.mark.parametrize("name", ["VoxelBackBone8x", "VoxelResBackBone8x"])
+def test_backbone_full_kitti_frame_vs_oracle_and_rulebooks_bit_exact(name):
+    cfg = synth.DATASETS["kitti"]
+    pts = synth.lidar_frame("kitti", seed=31)
+    v, c, n = O.voxelize(pts, cfg["voxel_size"], cfg["point_cloud_range"], 5, 40000)
+    feats, coords = O.mean_vfe(v, n), O.collate([c])
+    gs = synth.grid_size(cfg)
+    net, state = _load_backbone(name, 4, gs, 5)
+    ref = O.backbone_forward(name, state, feats, coords, 1, [int(gs[2]) + 1, int(gs[1]), int(gs[0])])
+    with torch.no_grad():
+        bd = net({"voxel_features": cuda(feats), "voxel_coords": cuda(coords), "batch_size": 1})
+    outs = dict(bd["multi_scale_3d_features"], out=bd["encoded_spconv_tensor"])
+    for k in ("x_conv1", "x_conv2", "x_conv3", "x_conv4", "out"):
+        assert np.array_equal(outs[k].indices.cpu().numpy(), ref[k][1]), k
+        assert rel_err(outs[k].features.cpu().numpy(), ref[k][0]) < FP32_TOL, k
+    for key, (outids, pairs, num) in ref["rulebooks"].items():
+        g_out, _, g_pairs, g_num, _ = outs["out"].indice_dict[key]
+        assert np.array_equal(g_out.cpu().numpy(), outids), key
+        assert np.array_equal(g_num.cpu().numpy(), num), key
+        assert np.array_equal(g_pairs.cpu().numpy(), pairs), key
+
+
+def test_hot_path_from_host_points_batch_invariance():
+    """Whole path from host buffers: frames processed in a batch equal the same frames processed alone
+    (frames are independent units -- the multi-GPU sharding relies on exactly this)."""
+    cfg = synth.DATASETS["kitti"]
+    gs = synth.grid_size(cfg)
+    net, state = _load_backbone("VoxelResBackBone8x", 4, gs, 9)
+    hp = fv2p_b200.HotPath(net, cfg["voxel_size"], cfg["point_cloud_range"], 5, 16000)
+    frames = [synth.lidar_frame("kitti", seed=40 + i, az_steps=120 + 40 * i) for i in range(3)]
+    bd, info = hp(frames, fetch="encoded")
+    enc = bd["encoded_spconv_tensor"]
+    feats_all, ind_all = enc.features.cpu().numpy().copy(), enc.indices.cpu().numpy().copy()
+    assert np.array_equal(info["encoded_indices_host"].numpy(), ind_all)
+    assert info["h2d_bytes"] > 0 and info["d2h_bytes"] > feats_all.nbytes
+    for b, f in enumerate(frames):
+        bd1, _ = hp([f])
+        e1 = bd1["encoded_spconv_tensor"]
+        sel = ind_all[:, 0] == b
+        assert np.array_equal(ind_all[sel][:, 1:], e1.indices.cpu().numpy()[:, 1:])
+        assert rel_err(feats_all[sel], e1.features.cpu().numpy()) < 1e-6
+        # and against the CPU oracle end to end
+        v, c, n = O.voxelize(f, cfg["voxel_size"], cfg["point_cloud_range"], 5, 16000)
+        ref = O.backbone_forward("VoxelResBackBone8x", state, O.mean_vfe(v, n), O.collate([c]), 1,
+                                 [int(gs[2]) + 1, int(gs[1]), int(gs[0])])
+        assert np.array_equal(e1.indices.cpu().numpy(), ref["out"][1])
+        assert rel_err(e1.features.cpu().numpy(), ref["out"][0]) < FP32_TOL
+
+
+def test_bf16_backbone_within_stated_tolerance():
+    g = load_golden("backbone_kitti_VoxelResBackBone8x")
+    net, _ = _load_backbone("VoxelResBackBone8x", 4, g["grid_size"], int(g["seed"]), {"PRECISION": "bf16"})
+    with torch.no_grad():
+        bd = net({"voxel_features": cuda(g["voxel_features"]), "voxel_coords": cuda(g["voxel_coords"]),
+                  "batch_size": int(g["batch_size"])})
+    outs = dict(bd["multi_scale_3d_features"], out=bd["encoded_spconv_tensor"])
+    for k in ("x_conv1", "x_conv2", "x_conv3", "x_conv4", "out"):
+        assert outs[k].features.dtype == torch.bfloat16
+        assert np.array_equal(outs[k].indices.cpu().numpy(), g[k + "_indices"]), k
+        assert rel_err(outs[k].features.float().cpu().numpy(), g[k + "_features"]) < BF16_TOL, k
+
+
+def test_dense_matches_reference_scatter():
+    ind = synth.random_voxels([5, 12, 11], 300, 3, seed=6)
+    feats = torch.randn(ind.shape[0], 16, device=DEV)
+    x = spconv.SparseConvTensor(feats, cuda(ind), [5, 12, 11], 3)
+    ref = spconv.scatter_nd(x.indices.long(), feats, [3, 5, 12, 11, 16]).permute(0, 4, 1, 2, 3).contiguous()
+    assert torch.equal(x.dense(), ref)
