@@ -116,6 +116,23 @@ def pairs_to_nbr(indice_pairs, indice_pair_num, num_activate_out, inverse=False)
     return nbr[:, :int(num_activate_out)]
 
 
+def pack_weight(weight_flat, mode):
+    """Packed shared-memory image of W [K,Cin,Cout] for the tensor-core modes (fv2p_pack_weight)."""
+    dev = _lib.require_device(weight_flat)
+    lib = _lib.load()
+    kvol, cin, cout = weight_flat.shape
+    nbytes = lib.fv2p_pack_weight_bytes(kvol, cin, cout, int(mode))
+    if nbytes == 0:
+        raise ValueError("tensor-core conv needs cin in {16,32,64,128,256} and cout in {16,32,64,128}")
+    w = weight_flat.detach().float().contiguous()
+    packed = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+    with torch.cuda.device(dev):
+        _lib.check(lib.fv2p_pack_weight(_lib.ptr(w), kvol, cin, cout, int(mode), _lib.ptr(packed),
+                                        _lib.stream_ptr(w.device)), "pack_weight")
+    packed.fv2p_cout = cout
+    return packed
+
+
 def conv_forward(features, weight_flat, nbr, num_activate_out, bias=None, scale=None, shift=None, residual=None,
                  relu=False, mode=None, n_out_dev=None, out=None):
     """fv2p_conv_fwd: out = act((sum_k X[nbr[k]] W[k] + bias) * scale + shift + residual)."""

@@ -222,6 +222,58 @@ def test_conv_fused_epilogue_matches_oracle(cin, cout):
     assert rel_err(out.cpu().numpy(), ref) < FP32_TOL
 
 
+@pytest.mark.parametrize("mode", ["tf32x3", "bf16"])
+@pytest.mark.parametrize("cin,cout", [(16, 16), (16, 32), (32, 32), (32, 64), (64, 64), (64, 128), (128, 128)])
+@pytest.mark.parametrize("geom", ["subm", "s2"])
+def test_tensor_core_conv_matches_oracle(mode, cin, cout, geom):
+    """tcgen05 kernels: 3xTF32 must hold the fp32 bar, bf16 its stated tolerance, fused epilogue included."""
+    rng = np.random.default_rng(cin * 7 + cout)
+    shape = [9, 40, 40]
+    ind = synth.random_voxels(shape, 2200, 2, seed=cout)
+    # clustered coordinates so that tiles have many active offsets and missing neighbours at the same time
+    ind[:, 1:] = ind[:, 1:] // np.array([2, 3, 3])
+    ind = np.unique(ind, axis=0).astype(np.int32)
+    feats = rng.standard_normal((ind.shape[0], cin)).astype(np.float32)
+    w = (rng.standard_normal((27, cin, cout)) / np.sqrt(27 * cin)).astype(np.float32)
+    bias, beta, mean = (rng.standard_normal(cout).astype(np.float32) * 0.1 for _ in range(3))
+    gamma = rng.uniform(0.5, 1.5, cout).astype(np.float32)
+    var = rng.uniform(0.5, 1.5, cout).astype(np.float32)
+    if geom == "subm":
+        outids, pairs, num = O.rulebook_subm(ind, 2, shape, 3, 1)
+        got_rb = spconv.ops.get_indice_pairs(cuda(ind), 2, shape, 3, 1, 1, 1, 0, True, False, return_nbr=True)
+    else:
+        outids, pairs, num, _ = O.rulebook_conv(ind, 2, shape, 3, 2, 1, 1)
+        got_rb = spconv.ops.get_indice_pairs(cuda(ind), 2, shape, 3, 2, 1, 1, 0, False, False, return_nbr=True)
+    n_out = outids.shape[0]
+    res = rng.standard_normal((n_out, cout)).astype(np.float32)
+    nbr = got_rb[3].contiguous()
+    scale = (gamma / np.sqrt(var + 1e-3)).astype(np.float32)
+    shift = (beta - mean * scale).astype(np.float32)
+    if mode == "bf16":
+        q = lambda a: torch.from_numpy(a).to(torch.bfloat16).float().numpy()  # noqa: E731
+        ref = O.bias_bn_res_relu(O.indice_conv(q(feats), q(w), pairs, num, n_out, False, geom == "subm"), bias,
+                                 (gamma, beta, mean, var), q(res), True)
+        packed = spconv.ops.pack_weight(cuda(w), _lib.MODE_BF16_TC)
+        out = spconv.ops.conv_forward(cuda(feats, torch.bfloat16), packed, nbr, n_out, cuda(bias), cuda(scale),
+                                      cuda(shift), cuda(res, torch.bfloat16), True, mode=_lib.MODE_BF16_TC)
+        assert out.dtype == torch.bfloat16
+        assert rel_err(out.float().cpu().numpy(), ref) < 1e-2  # one bf16 rounding of the output
+    else:
+        # float64 contraction as the truth here: the fp32 oracle's own summation error over 27*cin terms is of
+        # the same order as the bar being checked
+        acc = np.zeros((n_out, cout), np.float64)
+        for k in range(27):
+            t = num[k]
+            np.add.at(acc, pairs[k, 1, :t], feats[pairs[k, 0, :t]].astype(np.float64) @ w[k].astype(np.float64))
+        assert rel_err(O.indice_conv(feats, w, pairs, num, n_out, False, geom == "subm"), acc) < 1e-5
+        ref = O.bias_bn_res_relu(acc.astype(np.float32), bias, (gamma, beta, mean, var), res, True)
+        packed = spconv.ops.pack_weight(cuda(w), _lib.MODE_TF32X3_TC)
+        out = spconv.ops.conv_forward(cuda(feats), packed, nbr, n_out, cuda(bias), cuda(scale), cuda(shift),
+                                      cuda(res), True, mode=_lib.MODE_TF32X3_TC)
+        err = rel_err(out.cpu().numpy(), ref)
+        assert err < 1e-5, err
+
+
 def test_sparse_conv_equals_dense_conv3d():
     """The property the reference's test_utils.py:144-193 was written for: sparse conv == F.conv3d on .dense()."""
     torch.manual_seed(0)
