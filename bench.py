@@ -67,14 +67,17 @@ class ClockSampler(threading.Thread):
             for line in self.proc.stdout:
                 parts = [x.strip() for x in line.strip().split(",")]
                 if len(parts) >= 7:
-                    self.rows.append(parts)
+                    self.rows.append(parts + [time.perf_counter()])
         except Exception:
             pass
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if self.proc is not None:
             self.proc.terminate()
         self.join(timeout=3)
+        if t0 is not None:
+            inside = [r for r in self.rows if t0 <= r[-1] <= t1]
+            self.rows = inside if inside else self.rows[-3:]
         sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -156,6 +159,8 @@ def run_ours(args, wl, rank, world, device):
     import torch.distributed as dist
     from fv2p_b200 import _lib
     precision = args.precision
+    sampler = ClockSampler(torch.cuda.current_device() if device.index is None else device.index)
+    sampler.start()  # nvidia-smi takes a second to start streaming; rows are filtered to the timed region later
     net, hp, state, cfg = build_model(wl, device, precision)
     frames = make_frames(wl, rank, wl["batch"])
     flush_buf = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=device)
@@ -175,8 +180,6 @@ def run_ours(args, wl, rank, world, device):
     for _ in range(args.warmup):
         handle = hp.launch_resident(pts, off, mfp)
         hp.finish(handle)
-    sampler = ClockSampler(torch.cuda.current_device() if device.index is None else device.index)
-    sampler.start()
     barrier()
     step_ms = []
     t_wall0 = time.perf_counter()
@@ -205,7 +208,7 @@ def run_ours(args, wl, rank, world, device):
         d2h_bytes = einfo["d2h_bytes"]
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_wall0, time.perf_counter())
 
     # ---- reduce over ranks (MAX of elapsed)
     t = torch.tensor([total_ms, e2e_s * 1000.0], dtype=torch.float64, device=device)

@@ -7,18 +7,19 @@
 //   CTA tile      128 output rows x Cout, accumulator in TMEM (fp32, Cout columns, double buffered so the
 //                 epilogue of tile t overlaps the contraction of tile t+1)
 //   K loop        the kernel offsets that have at least one neighbour in the tile  x  Cin in 128-byte slices
-//   A operand     the gathered input rows: warps 4-7 issue 16-byte cp.async straight into the UMMA canonical
-//                 K-major (no-swizzle) layout; a missing neighbour is a zero-filled cp.async, so there is no
-//                 predication in the MMA and no scatter afterwards
+//   A operand     the gathered input rows: warps 4-11 issue 16-byte cp.async straight into the UMMA canonical
+//                 K-major (no-swizzle) layout and hand the stage over with cp.async.mbarrier.arrive (the
+//                 arrival fires when the copies land, the threads never wait); a missing neighbour is a
+//                 zero-filled cp.async, so there is no predication in the MMA and no scatter afterwards
 //   B operand     W[k] slices, pre-packed once per layer into the exact shared-memory image and pulled with
 //                 one TMA bulk copy (cp.async.bulk, mbarrier complete_tx) per stage
-//   MMA           one elected lane of warp 8 issues tcgen05.mma (kind::f16 for bf16, kind::tf32 for fp32),
+//   MMA           one elected lane of warp 12 issues tcgen05.mma (kind::f16 for bf16, kind::tf32 for fp32),
 //                 tcgen05.commit releases the smem stage / publishes the accumulator through mbarriers
 //   epilogue      warps 0-3 read TMEM with tcgen05.ld (one accumulator row per thread), apply
 //                 bias + folded BatchNorm + residual + ReLU and store 16-byte vectors
 //
-// fp32 path = 3xTF32: A is split in shared memory into hi = rn_tf32(A) and lo = rn_tf32(A - hi) by the thread
-// that gathered it, W is packed as hi/lo images, and each K step issues A_lo*W_hi + A_hi*W_lo + A_hi*W_hi.  The
+// fp32 path = 3xTF32: A is split in shared memory into hi = rn_tf32(A) and lo = rn_tf32(A - hi) by four
+// transform warps (13-16) between the gather and the MMA, W is packed as hi/lo images, and each K step issues A_lo*W_hi + A_hi*W_lo + A_hi*W_hi.  The
 // dropped lo*lo term and the rounding of the lo parts are O(2^-22) relative and unbiased, far inside 1e-4.
 #include "common.cuh"
 
@@ -27,11 +28,13 @@ namespace {
 
 constexpr int kTileM = 128;
 constexpr int kEpiThreads = 128;     // warps 0-3
-constexpr int kGatherThreads = 128;  // warps 4-7
-constexpr int kTcThreads = kEpiThreads + kGatherThreads + 32;
+constexpr int kGatherThreads = 256;  // warps 4-11: two per scheduler so one warp's smem/L2 latency hides behind the other
+constexpr int kGatherWarps = kGatherThreads / 32;
+constexpr int kMmaWarp = (kEpiThreads + kGatherThreads) / 32;
+constexpr int kXformThreads = 128;  // warps 13-16, fp32 (3xTF32) kernels only
+constexpr int kTcThreadsBase = kEpiThreads + kGatherThreads + 32;
 constexpr int kMaxStages = 8;
 constexpr int kSmemBudget = 212 * 1024;
-constexpr int kLookahead = 2;  // cp.async groups in flight per gather thread
 
 // ------------------------------------------------------------------------------------------ PTX
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -65,10 +68,10 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+// The mbarrier arrival is triggered when every cp.async this thread issued so far has landed (.noinc: it is one
+// of the arrivals the barrier was initialised with).  Non-blocking: the thread moves on to the next stage.
+__device__ __forceinline__ void cp_async_arrive(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -137,7 +140,8 @@ struct Cfg {
   static constexpr int kStages = kStagesRaw > kMaxStages ? kMaxStages : kStagesRaw;
   static constexpr int kSmemBytes = kStages * kStageBytes + kNbrBytes + 1024 + 1024;  // + barriers + align slack
   static constexpr int kTmemCols = 2 * N < 32 ? 32 : 2 * N;  // N in {16,32,64,128} -> power of two
-  static_assert(kStages >= kLookahead + 1, "pipeline too shallow");
+  static constexpr int kThreads = kTcThreadsBase + (kTf32 ? kXformThreads : 0);
+  static_assert(kStages >= 3, "pipeline too shallow");
 };
 
 struct Epilogue {
@@ -148,7 +152,7 @@ struct Epilogue {
 };
 
 template <bool kTf32, int N>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__((Cfg<kTf32, N>::kThreads), 1)
 conv_tc_kernel(const void *__restrict__ features, const uint8_t *__restrict__ wpacked,
                const int *__restrict__ nbr, int64_t nbr_stride, int kvol, int64_t n_out_cap,
                const int *__restrict__ n_out_dev, int cin, Epilogue ep) {
@@ -159,10 +163,11 @@ conv_tc_kernel(const void *__restrict__ features, const uint8_t *__restrict__ wp
   uint8_t *stage_base = smem;
   int *nbr_s = reinterpret_cast<int *>(smem + C::kStages * C::kStageBytes);
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C::kStages * C::kStageBytes + C::kNbrBytes);
-  // barrier layout: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2]
+  // barrier layout: full[kStages], empty[kStages], landed[kStages] (fp32 only), tmem_full[2], tmem_empty[2]
   const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * C::kStages;
-  const uint32_t bar_tfull = bar_empty + 8 * C::kStages, bar_tempty = bar_tfull + 16;
-  volatile int *stage_flags = reinterpret_cast<volatile int *>(bars + 2 * C::kStages + 4);  // [kStages]
+  const uint32_t bar_landed = bar_empty + 8 * C::kStages;
+  const uint32_t bar_tfull = bar_landed + 8 * C::kStages, bar_tempty = bar_tfull + 16;
+  volatile int *stage_flags = reinterpret_cast<volatile int *>(bars + 3 * C::kStages + 4);  // [kStages]
   volatile uint32_t *tile_mask = reinterpret_cast<volatile uint32_t *>(stage_flags + C::kStages);
   uint32_t *tmem_slot = const_cast<uint32_t *>(tile_mask) + 1;
 
@@ -177,8 +182,11 @@ conv_tc_kernel(const void *__restrict__ features, const uint8_t *__restrict__ wp
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::kStages; ++s) {
-      mbar_init(bar_full + 8 * s, kGatherThreads + 1);
+      // bf16: 256 cp.async arrivals + the expect_tx arrive of the weight copy.  fp32: the gathers land on
+      // `landed` (+1 plain arrive that publishes the stage flags), the transform warps arrive on `full`.
+      mbar_init(bar_full + 8 * s, (kTf32 ? kXformThreads : kGatherThreads) + 1);
       mbar_init(bar_empty + 8 * s, 1);
+      mbar_init(bar_landed + 8 * s, kGatherThreads + 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
@@ -186,7 +194,7 @@ conv_tc_kernel(const void *__restrict__ features, const uint8_t *__restrict__ wp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 8) {
+  if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"((uint32_t)C::kTmemCols)
                  : "memory");
@@ -197,50 +205,40 @@ conv_tc_kernel(const void *__restrict__ features, const uint8_t *__restrict__ wp
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp >= 4 && warp < 8) {
+  if (warp >= 4 && warp < kMmaWarp) {
     // =============================== gather producers ===============================
     const int tid = threadIdx.x - kEpiThreads;
     const uint8_t *feat = static_cast<const uint8_t *>(features);
     const size_t feat_row_bytes = (size_t)cin * kElem;
-    uint32_t issued = 0, arrived = 0;
-    const int cshift = __ffs(chunks) - 1;  // chunks is 2, 4 or 8
-    auto finish_stage = [&](uint32_t st_idx) {
-      const uint32_t s = st_idx % C::kStages;
-      if constexpr (kTf32) {
-        // split what THIS thread gathered: A_raw <- hi (tf32-exact), A_lo <- x - hi
-        uint8_t *a_hi = stage_base + (size_t)s * C::kStageBytes;
-        uint8_t *a_lo = a_hi + C::kABytes;
-        for (int it = 0; it < chunks; ++it) {
-          const int off = (it * kGatherThreads + tid) * 16;
-          float4 x = *reinterpret_cast<float4 *>(a_hi + off);
-          float4 h, l;
-          h.x = tf32_rn(x.x), h.y = tf32_rn(x.y), h.z = tf32_rn(x.z), h.w = tf32_rn(x.w);
-          l.x = tf32_rn(x.x - h.x), l.y = tf32_rn(x.y - h.y), l.z = tf32_rn(x.z - h.z), l.w = tf32_rn(x.w - h.w);
-          *reinterpret_cast<float4 *>(a_hi + off) = h;
-          *reinterpret_cast<float4 *>(a_lo + off) = l;
-        }
-      }
-      fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
-      mbar_arrive(bar_full + 8 * s);
-    };
+    uint32_t issued = 0;
+    // Item (it, tid) of a stage is the 16-byte unit  it*256 + tid  of the canonical layout
+    // ((row/8)*chunks + chunk)*8 + row%8.  With 256 threads the chunk of a thread is constant and only the
+    // row advances with `it`, so eight consecutive lanes write 128 contiguous bytes of shared memory (no bank
+    // conflicts) while lanes 8 apart read the next 16 bytes of the same global rows (full 32-byte sectors).
+    const int cshift = __ffs(chunks) - 1;            // chunks is 2, 4 or 8
+    const int my_chunk = (tid >> 3) & (chunks - 1);
+    const int my_row0 = ((tid >> (3 + cshift)) << 3) + (tid & 7);
+    const int rows_per_it = kGatherThreads >> cshift;  // 128, 64 or 32 rows per pass
+    const int iters = chunks >> 1;                     // kTileM * chunks / kGatherThreads
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int row0 = tile * kTileM;
       // ---- neighbour rows of this tile -> smem, and which offsets feed anything
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // everyone finished reading nbr_s of the previous tile
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // everyone finished reading nbr_s of the previous tile
       if (tid == 0) *tile_mask = 0u;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       {
-        const int row = row0 + tid;
+        const int r = tid & (kTileM - 1);
+        const int row = row0 + r;
         uint32_t mine = 0;
-        for (int k = 0; k < kvol; ++k) {
+        for (int k = tid >> 7; k < kvol; k += 2) {  // warps 4-7 take the even offsets, 8-11 the odd ones
           int src = -1;
           if (row < n_out) src = __ldg(&nbr[(size_t)k * nbr_stride + row]);
-          nbr_s[k * kTileM + tid] = src;
+          nbr_s[k * kTileM + r] = src;
           if (__ballot_sync(0xFFFFFFFFu, src >= 0)) mine |= 1u << k;
         }
         if (lane == 0 && mine) atomicOr(const_cast<uint32_t *>(tile_mask), mine);
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       uint32_t mask = *tile_mask;
       if (mask == 0u) mask = 1u;  // a tile nothing feeds still has to produce (zero) accumulators
       const uint32_t first_k = __ffs(mask) - 1;
@@ -248,6 +246,10 @@ conv_tc_kernel(const void *__restrict__ features, const uint8_t *__restrict__ wp
       while (mask) {
         const int k = __ffs(mask) - 1;
         mask &= mask - 1;
+        int src_row[4];
+#pragma unroll
+        for (int it = 0; it < 4; ++it)
+          src_row[it] = it < iters ? nbr_s[k * kTileM + it * rows_per_it + my_row0] : -1;
         for (int sl = 0; sl < slices; ++sl) {
           const uint32_t s = issued % C::kStages;
           mbar_wait(bar_empty + 8 * s, ((issued / C::kStages) & 1) ^ 1);
@@ -258,33 +260,24 @@ conv_tc_kernel(const void *__restrict__ features, const uint8_t *__restrict__ wp
             uint8_t *w_dst = a_dst + (kTf32 ? 2 : 1) * C::kABytes;
             mbar_arrive_expect_tx(bar_full + 8 * s, w_stage_bytes * (kTf32 ? 2 : 1));
             bulk_g2s(smem_u32(w_dst), wsrc, w_stage_bytes * (kTf32 ? 2 : 1), bar_full + 8 * s);
+            if constexpr (kTf32) mbar_arrive(bar_landed + 8 * s);
           }
-          const uint32_t a_u32 = smem_u32(a_dst);
-          for (int it = 0; it < chunks; ++it) {
-            const int item = it * kGatherThreads + tid;  // ((group*chunks + chunk)*8 + row_in_group)
-            const int g = item >> (cshift + 3);
-            const int c = (item >> 3) & (chunks - 1);
-            const int r = g * 8 + (item & 7);
-            const int src = nbr_s[k * kTileM + r];
-            const uint8_t *p = feat + (src >= 0 ? (size_t)src * feat_row_bytes + (size_t)sl * row_bytes + c * 16 : 0);
-            cp_async16(a_u32 + item * 16, p, src >= 0 ? 16u : 0u);
+          const uint32_t a_u32 = smem_u32(a_dst) + tid * 16;
+          const size_t col_off = (size_t)sl * row_bytes + my_chunk * 16;
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            if (it < iters) {
+              const int src = src_row[it];
+              const uint8_t *p = feat + (src >= 0 ? (size_t)src * feat_row_bytes + col_off : 0);
+              cp_async16(a_u32 + it * (kGatherThreads * 16), p, src >= 0 ? 16u : 0u);
+            }
           }
-          cp_async_commit();
+          cp_async_arrive(kTf32 ? bar_landed + 8 * s : bar_full + 8 * s);
           ++issued;
-          if (issued - arrived > kLookahead) {
-            cp_async_wait<kLookahead>();
-            finish_stage(arrived);
-            ++arrived;
-          }
         }
       }
     }
-    cp_async_wait<0>();
-    while (arrived < issued) {
-      finish_stage(arrived);
-      ++arrived;
-    }
-  } else if (warp == 8) {
+  } else if (warp == kMmaWarp) {
     // =============================== MMA issuer ===============================
     constexpr uint32_t idesc = instr_desc(N, kTf32);
     const uint32_t sbo = (uint32_t)chunks * 128u;
@@ -329,6 +322,39 @@ conv_tc_kernel(const void *__restrict__ features, const uint8_t *__restrict__ wp
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
+    }
+  } else if (warp > kMmaWarp) {
+    // =============================== fp32 split (warps 13-16, 3xTF32 kernels only) ===============================
+    // A_raw <- hi = rn_tf32(x), A_lo <- rn_tf32(x - hi).  Done by warps that have no cp.async in flight, so
+    // the proxy fence that makes the generic-proxy stores visible to the tensor core does not stall on gathers.
+    if constexpr (kTf32) {
+      const int t = threadIdx.x - (kTcThreadsBase);
+      uint32_t done = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        bool last = false;
+        while (!last) {
+          const uint32_t s = done % C::kStages;
+          mbar_wait(bar_landed + 8 * s, (done / C::kStages) & 1);
+          last = (stage_flags[s] & 2) != 0;
+          uint8_t *a_hi = stage_base + (size_t)s * C::kStageBytes;
+          uint8_t *a_lo = a_hi + C::kABytes;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            if (it < chunks) {
+              const int off = (it * kXformThreads + t) * 16;
+              float4 x = *reinterpret_cast<float4 *>(a_hi + off);
+              float4 h, l;
+              h.x = tf32_rn(x.x), h.y = tf32_rn(x.y), h.z = tf32_rn(x.z), h.w = tf32_rn(x.w);
+              l.x = tf32_rn(x.x - h.x), l.y = tf32_rn(x.y - h.y), l.z = tf32_rn(x.z - h.z), l.w = tf32_rn(x.w - h.w);
+              *reinterpret_cast<float4 *>(a_hi + off) = h;
+              *reinterpret_cast<float4 *>(a_lo + off) = l;
+            }
+          }
+          fence_proxy_async();
+          mbar_arrive(bar_full + 8 * s);
+          ++done;
+        }
+      }
     }
   } else {
     // =============================== epilogue (warps 0-3) ===============================
@@ -409,7 +435,7 @@ conv_tc_kernel(const void *__restrict__ features, const uint8_t *__restrict__ wp
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::kTmemCols)
                  : "memory");
@@ -469,7 +495,7 @@ int launch_one(const void *features, const void *weight, const int *nbr, int64_t
   int64_t tiles = (n_out_cap + kTileM - 1) / kTileM;
   int grid = (int)(tiles < sm_count() ? tiles : sm_count());
   if (grid < 1) grid = 1;
-  conv_tc_kernel<kTf32, N><<<grid, kTcThreads, C::kSmemBytes, stream>>>(
+  conv_tc_kernel<kTf32, N><<<grid, C::kThreads, C::kSmemBytes, stream>>>(
       features, static_cast<const uint8_t *>(weight), nbr, nbr_stride, kvol, n_out_cap, n_out_dev, cin, ep);
   return cuda_status(cudaGetLastError(), "conv_fwd(tc)");
 }

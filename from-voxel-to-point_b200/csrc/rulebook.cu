@@ -104,48 +104,67 @@ subm_insert_kernel(const int4 *__restrict__ indices, const int *n_dev, int64_t n
 }
 
 // Output-side probe: mat[k][i] = input row at  in = out*stride - pad + k*dil  (stride 1 here), or -1.
-// Also counts the hits per (matrix row, chunk) for the compaction.
+// Also counts the hits per (matrix row, chunk) for the compaction.  Work item = (chunk, offset): K times more
+// CTAs than a per-chunk split, and the eight probes of a thread are issued as independent loads before any
+// of them is resolved (a probe is a dependent chain of L2 accesses; serialising 27 of them per thread was the
+// single slowest kernel of the first profile).
 __global__ void __launch_bounds__(kThreads)
 subm_probe_kernel(const int4 *__restrict__ indices, const int *n_dev, int64_t n_cap, Geom g,
                   const unsigned long long *__restrict__ keys, const int *__restrict__ vals, int *mat,
                   int64_t mat_stride, int *counts, int n_chunks) {
-  __shared__ int hits[FV2P_MAX_KVOL];
   const int n = live_count(n_dev, n_cap);
   const uint32_t mask = table_slots_for(n) - 1;
-  const int lane = threadIdx.x & 31;
   const int D = g.out_shape[0], H = g.out_shape[1], W = g.out_shape[2];
-  for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
-    if (threadIdx.x < FV2P_MAX_KVOL) hits[threadIdx.x] = 0;
-    __syncthreads();
+  const int work = n_chunks * g.kvol;
+  for (int w = blockIdx.x; w < work; w += gridDim.x) {
+    const int c = w / g.kvol, k = w - c * g.kvol;
     const int base = c * kChunk;
-    if (base < n) {
-      for (int p = 0; p < kItemsPerThread; ++p) {
-        const int i = base + p * kThreads + threadIdx.x;
-        const bool live = i < n;
-        int4 o = live ? __ldg(&indices[i]) : make_int4(0, 0, 0, 0);
-        int k = 0;
-        for (int kz = 0; kz < g.ksize[0]; ++kz) {
-          const int z = o.y - g.pad[0] + kz * g.dil[0];
-          for (int ky = 0; ky < g.ksize[1]; ++ky) {
-            const int y = o.z - g.pad[1] + ky * g.dil[1];
-            for (int kx = 0; kx < g.ksize[2]; ++kx, ++k) {
-              const int x = o.w - g.pad[2] + kx * g.dil[2];
-              int found = -1;
-              if (live && z >= 0 && z < D && y >= 0 && y < H && x >= 0 && x < W) {
-                uint32_t slot = table_find(keys, mask, voxel_key(o.x, z, y, x, D, H, W));
-                if (slot != 0xFFFFFFFFu) found = __ldg(&vals[slot]);
-              }
-              if (live) mat[(size_t)k * mat_stride + i] = found;
-              unsigned bal = __ballot_sync(0xFFFFFFFFu, found >= 0);
-              if (lane == 0 && bal) atomicAdd(&hits[k], __popc(bal));
-            }
-          }
+    if (base >= n) {
+      if (threadIdx.x == 0) counts[(size_t)k * n_chunks + c] = 0;
+      continue;
+    }
+    const int kx = k % g.ksize[2], ky = (k / g.ksize[2]) % g.ksize[1], kz = k / (g.ksize[2] * g.ksize[1]);
+    const int dz = kz * g.dil[0] - g.pad[0], dy = ky * g.dil[1] - g.pad[1], dx = kx * g.dil[2] - g.pad[2];
+    unsigned long long key[kItemsPerThread], seen[kItemsPerThread];
+    uint32_t slot[kItemsPerThread];
+#pragma unroll
+    for (int p = 0; p < kItemsPerThread; ++p) {
+      const int i = base + p * kThreads + threadIdx.x;
+      key[p] = kEmptyKey;
+      seen[p] = kEmptyKey;
+      slot[p] = 0;
+      if (i < n) {
+        const int4 o = __ldg(&indices[i]);
+        const int z = o.y + dz, y = o.z + dy, x = o.w + dx;
+        if (z >= 0 && z < D && y >= 0 && y < H && x >= 0 && x < W) {
+          key[p] = voxel_key(o.x, z, y, x, D, H, W);
+          slot[p] = mix64(key[p]) & mask;
+          seen[p] = __ldg(&keys[slot[p]]);
         }
       }
     }
-    __syncthreads();
-    if (threadIdx.x < g.kvol) counts[(size_t)threadIdx.x * n_chunks + c] = hits[threadIdx.x];
-    __syncthreads();
+    int found[kItemsPerThread];
+#pragma unroll
+    for (int p = 0; p < kItemsPerThread; ++p) {
+      uint32_t s = slot[p];
+      unsigned long long sk = seen[p];
+      while (sk != key[p] && sk != kEmptyKey) {
+        s = (s + 1) & mask;
+        sk = __ldg(&keys[s]);
+      }
+      found[p] = (key[p] != kEmptyKey && sk == key[p]) ? (int)s : -1;
+    }
+#pragma unroll
+    for (int p = 0; p < kItemsPerThread; ++p)
+      if (found[p] >= 0) found[p] = __ldg(&vals[found[p]]);
+    int total = 0;
+#pragma unroll
+    for (int p = 0; p < kItemsPerThread; ++p) {
+      const int i = base + p * kThreads + threadIdx.x;
+      if (i < n) mat[(size_t)k * mat_stride + i] = found[p];
+      total += __syncthreads_count(found[p] >= 0);
+    }
+    if (threadIdx.x == 0) counts[(size_t)k * n_chunks + c] = total;
   }
 }
 
