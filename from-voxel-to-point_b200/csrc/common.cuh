@@ -32,7 +32,7 @@ int sm_count();                                    // cached per process (curren
 // Every kernel is persistent/grid-stride over a row count that lives in device memory, so launch
 // dimensions never depend on data: a few CTAs per SM, 148 SMs on B200.
 constexpr int kThreads = 256;
-constexpr int kItemsPerThread = 8;
+constexpr int kItemsPerThread = 2;
 constexpr int kChunk = kThreads * kItemsPerThread;  // rows per work item of the ordered passes
 
 inline int persistent_grid(int ctas_per_sm = 4) { return sm_count() * ctas_per_sm; }

@@ -245,8 +245,8 @@ dense_ncdhw_kernel(const float *__restrict__ features, const int4 *__restrict__ 
 }  // namespace
 
 // implemented in conv_tc.cu
-int launch_conv_tc(const void *features, const void *weight, const int *nbr, int64_t nbr_stride, int kvol,
-                   int64_t n_out_cap, const int *n_out_dev, int cin, int cout, const float *bias,
+int launch_conv_tc(const void *features, int64_t feat_rows, const void *weight, const int *nbr, int64_t nbr_stride,
+                   int kvol, int64_t n_out_cap, const int *n_out_dev, int cin, int cout, const float *bias,
                    const float *scale, const float *shift, const void *residual, int relu, int mode, void *out,
                    cudaStream_t stream);
 
@@ -254,7 +254,7 @@ int launch_conv_tc(const void *features, const void *weight, const int *nbr, int
 
 using namespace fv2p;
 
-extern "C" int fv2p_conv_fwd(const void *features, const void *weight, const int32_t *nbr, int64_t nbr_stride,
+extern "C" int fv2p_conv_fwd(const void *features, int64_t n_in_cap, const void *weight, const int32_t *nbr, int64_t nbr_stride,
                              int kvol, int64_t n_out_cap, const int32_t *n_out_dev, int cin, int cout,
                              const float *bias, const float *scale, const float *shift, const void *residual,
                              int relu, int mode, void *out, fv2p_stream_t stream_) {
@@ -280,8 +280,8 @@ extern "C" int fv2p_conv_fwd(const void *features, const void *weight, const int
                                                residual, relu, out, stream);
     case FV2P_MODE_BF16_TC:
     case FV2P_MODE_TF32X3_TC:
-      return launch_conv_tc(features, weight, nbr, nbr_stride, kvol, n_out_cap, n_out_dev, cin, cout, bias, scale,
-                            shift, residual, relu, mode, out, stream);
+      return launch_conv_tc(features, n_in_cap, weight, nbr, nbr_stride, kvol, n_out_cap, n_out_dev, cin, cout, bias,
+                            scale, shift, residual, relu, mode, out, stream);
     default:
       set_error("conv_fwd: unknown mode %d", mode);
       return FV2P_ERR_INVALID;
@@ -307,7 +307,7 @@ extern "C" int fv2p_indice_conv_fp32(const float *features, const float *filters
   int *nbr = static_cast<int *>(workspace);
   int st = fv2p_pairs_to_nbr(pairs, pair_num, kvol, pair_stride, inverse, num_act_out, nbr, num_act_out, stream_);
   if (st) return st;
-  return fv2p_conv_fwd(features, filters, nbr, num_act_out, kvol, num_act_out, nullptr, cin, cout, nullptr, nullptr,
+  return fv2p_conv_fwd(features, 0, filters, nbr, num_act_out, kvol, num_act_out, nullptr, cin, cout, nullptr, nullptr,
                        nullptr, nullptr, 0, FV2P_MODE_F32, out, stream_);
 }
 

@@ -7,32 +7,43 @@
 //   CTA tile      128 output rows x Cout, accumulator in TMEM (fp32, Cout columns, double buffered so the
 //                 epilogue of tile t overlaps the contraction of tile t+1)
 //   K loop        the kernel offsets that have at least one neighbour in the tile  x  Cin in 128-byte slices
-//   A operand     the gathered input rows: warps 4-11 issue 16-byte cp.async straight into the UMMA canonical
-//                 K-major (no-swizzle) layout and hand the stage over with cp.async.mbarrier.arrive (the
-//                 arrival fires when the copies land, the threads never wait); a missing neighbour is a
-//                 zero-filled cp.async, so there is no predication in the MMA and no scatter afterwards
-//   B operand     W[k] slices, pre-packed once per layer into the exact shared-memory image and pulled with
-//                 one TMA bulk copy (cp.async.bulk, mbarrier complete_tx) per stage
-//   MMA           one elected lane of warp 12 issues tcgen05.mma (kind::f16 for bf16, kind::tf32 for fp32),
+//   A operand     the gathered input rows in the 128B/64B/32B-swizzled K-major tile tcgen05.mma reads.  Two
+//                 interchangeable producers (profiles/r1_notes.md has the measurements):
+//                   * TMA: cp.async.bulk.tensor ... tile::gather4 pulls four arbitrary feature rows per
+//                     instruction; a missing neighbour is an out-of-range row index that the TMA zero fills;
+//                   * LSU: 16-byte cp.async (LDGSTS), eight lanes per row so that every warp instruction reads
+//                     whole 128-byte lines and, thanks to the swizzle, writes conflict-free; a missing
+//                     neighbour is a zero-fill cp.async; the stage is handed over with
+//                     cp.async.mbarrier.arrive, so the issuing warp never waits for its copies.
+//                 Each ring slot is owned by one producer warp, so the waits and arrivals of one stage overlap
+//                 the copy issue of the next ones.  Either way the MMA needs no predication
+//                 and nothing is scattered afterwards.
+//   B operand     W[k] slices, pre-packed once per layer into the exact (swizzled) shared-memory image and
+//                 pulled with one TMA bulk copy per stage
+//   MMA           one elected lane of warp 12 issues tcgen05.mma (kind::f16 for bf16, kind::tf32 for fp32);
 //                 tcgen05.commit releases the smem stage / publishes the accumulator through mbarriers
 //   epilogue      warps 0-3 read TMEM with tcgen05.ld (one accumulator row per thread), apply
 //                 bias + folded BatchNorm + residual + ReLU and store 16-byte vectors
 //
-// fp32 path = 3xTF32: A is split in shared memory into hi = rn_tf32(A) and lo = rn_tf32(A - hi) by four
-// transform warps (13-16) between the gather and the MMA, W is packed as hi/lo images, and each K step issues A_lo*W_hi + A_hi*W_lo + A_hi*W_hi.  The
-// dropped lo*lo term and the rounding of the lo parts are O(2^-22) relative and unbiased, far inside 1e-4.
+// fp32 path = 3xTF32: four transform warps (13-16) split the landed fp32 tile in place into
+// hi = rn_tf32(x) and a second tile lo = rn_tf32(x - hi); W is packed as hi/lo images, and each K step issues
+// A_lo*W_hi + A_hi*W_lo + A_hi*W_hi.  The dropped lo*lo term and the rounding of the lo parts are O(2^-22)
+// relative and unbiased.  What remains (measured 1-2e-5 at 27*128 terms) is the tensor core's truncating
+// fp32 accumulation, 5x inside the 1e-4 bar.
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace fv2p {
 namespace {
 
 constexpr int kTileM = 128;
-constexpr int kEpiThreads = 128;     // warps 0-3
-constexpr int kGatherThreads = 256;  // warps 4-11: two per scheduler so one warp's smem/L2 latency hides behind the other
-constexpr int kGatherWarps = kGatherThreads / 32;
-constexpr int kMmaWarp = (kEpiThreads + kGatherThreads) / 32;
-constexpr int kXformThreads = 128;  // warps 13-16, fp32 (3xTF32) kernels only
-constexpr int kTcThreadsBase = kEpiThreads + kGatherThreads + 32;
+constexpr int kEpiThreads = 128;   // warps 0-3
+constexpr int kProdThreads = 256;  // warps 4-11: neighbour prefetch + gather issue (each ring slot has one owner warp)
+constexpr int kProdWarps = kProdThreads / 32;
+constexpr int kMmaWarp = (kEpiThreads + kProdThreads) / 32;  // warp 12
+constexpr int kXformThreads = 128;                           // warps 13-16, fp32 (3xTF32) kernels only
+constexpr int kTcThreadsBase = kEpiThreads + kProdThreads + 32;
 constexpr int kMaxStages = 8;
 constexpr int kSmemBudget = 212 * 1024;
 
@@ -48,8 +59,21 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ int g_tc_poll = 0;  // experiment: 1 = poll with test_wait instead of the suspending try_wait
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done;
+  if (g_tc_poll) {
+    do {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(done)
+          : "r"(bar), "r"(parity)
+          : "memory");
+    } while (!done);
+    return;
+  }
   do {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -65,11 +89,20 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+// Four rows (r0..r3) x one box of columns starting at `col` -> 4 consecutive swizzled smem rows.
+__device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap *map, int col, int r0, int r1, int r2,
+                                            int r3, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(dst),
+      "l"(map), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar)
+      : "memory");
+}
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
-// The mbarrier arrival is triggered when every cp.async this thread issued so far has landed (.noinc: it is one
-// of the arrivals the barrier was initialised with).  Non-blocking: the thread moves on to the next stage.
+// The mbarrier arrival fires when every cp.async this thread issued so far has landed (.noinc: it is one of the
+// arrivals the barrier was initialised with).  Non-blocking.
 __device__ __forceinline__ void cp_async_arrive(uint32_t bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -116,12 +149,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// UMMA shared-memory descriptor, K-major, no swizzle (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
-// [0,14) start>>4, [16,30) leading byte offset>>4 (between the two 16-byte K chunks of one MMA),
-// [32,46) stride byte offset>>4 (between 8-row groups), [46,48) version=1, [61,64) layout type 0.
-__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
-  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) |
-         (1ull << 46);
+// UMMA shared-memory descriptor, K-major, swizzled (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
+// [0,14) start>>4, [16,30) leading byte offset>>4 (1 for swizzled K-major), [32,46) stride byte offset>>4
+// (distance between 8-row groups = 8 * row_bytes), [46,48) version=1, [61,64) layout: 2/4/6 = 128B/64B/32B swizzle.
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t sbo, uint32_t layout) {
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46) |
+         ((uint64_t)layout << 61);
 }
 // Instruction descriptor (InstrDescriptor): c=F32 [4,6), a/b format [7,10)/[10,13), K-major both,
 // n>>3 at [17,23), m>>4 at [24,29).
@@ -130,9 +163,14 @@ __host__ __device__ constexpr uint32_t instr_desc(int n, bool tf32) {
          ((uint32_t)(kTileM >> 4) << 24);
 }
 
+// Timing experiments only (profiles/run_layer.py --debug): 4 = no MMA, 6 = no epilogue body.  0 in production.
+__device__ int g_tc_debug = 0;
+// Host-side choice of the A-tile producer: -1 = auto (measured best per shape), 0 = LSU (cp.async), 1 = TMA gather4.
+int g_tc_gather_mode = -1;
+
 template <bool kTf32, int N>
 struct Cfg {
-  static constexpr int kABytes = kTileM * 128;                   // one 128-byte slice per row
+  static constexpr int kABytes = kTileM * 128;  // one (up to) 128-byte slice per row
   static constexpr int kWBytes = N * 128;
   static constexpr int kStageBytes = (kTf32 ? 2 : 1) * (kABytes + kWBytes);
   static constexpr int kNbrBytes = FV2P_MAX_KVOL * kTileM * 4;
@@ -153,9 +191,10 @@ struct Epilogue {
 
 template <bool kTf32, int N>
 __global__ void __launch_bounds__((Cfg<kTf32, N>::kThreads), 1)
-conv_tc_kernel(const void *__restrict__ features, const uint8_t *__restrict__ wpacked,
+conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restrict__ feat_ptr,
+               const uint8_t *__restrict__ wpacked,
                const int *__restrict__ nbr, int64_t nbr_stride, int kvol, int64_t n_out_cap,
-               const int *__restrict__ n_out_dev, int cin, Epilogue ep) {
+               const int *__restrict__ n_out_dev, int cin, int oob_row, int use_tma_arg, Epilogue ep) {
   using C = Cfg<kTf32, N>;
   constexpr int kElem = kTf32 ? 4 : 2;
   extern __shared__ uint8_t smem_raw[];
@@ -172,27 +211,33 @@ conv_tc_kernel(const void *__restrict__ features, const uint8_t *__restrict__ wp
   uint32_t *tmem_slot = const_cast<uint32_t *>(tile_mask) + 1;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int dbg = g_tc_debug;
+  const bool use_tma = use_tma_arg != 0;
   int n_out = n_out_dev ? *n_out_dev : (int)n_out_cap;
   if (n_out > n_out_cap) n_out = (int)n_out_cap;
   const int n_tiles = (n_out + kTileM - 1) / kTileM;
-  const int row_bytes = min(cin * kElem, 128);  // bytes of one row consumed per stage
-  const int chunks = row_bytes >> 4;            // 16-byte chunks per row per stage
-  const int slices = (cin * kElem) / row_bytes; // stages per kernel offset
+  const int row_bytes = min(cin * kElem, 128);   // bytes of one row consumed per stage (= TMA box width)
+  const int slices = (cin * kElem) / row_bytes;  // stages per kernel offset
+  const uint32_t a_stage_bytes = (uint32_t)kTileM * row_bytes;
   const uint32_t w_stage_bytes = (uint32_t)N * row_bytes;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::kStages; ++s) {
-      // bf16: 256 cp.async arrivals + the expect_tx arrive of the weight copy.  fp32: the gathers land on
-      // `landed` (+1 plain arrive that publishes the stage flags), the transform warps arrive on `full`.
-      mbar_init(bar_full + 8 * s, (kTf32 ? kXformThreads : kGatherThreads) + 1);
+      // bf16: the producer's expect_tx arrive; the TMA gathers and the weight copy complete the transaction.
+      // fp32: gathers land on `landed` (one expect_tx arrive), the transform warps + the weight copy on `full`.
+      // LSU gather: + the 32 cp.async arrivals of the owning warp (the fp32 `landed` barrier also gets one plain
+      // arrive that publishes the stage flags).
+      const uint32_t a_arrivals = use_tma ? 1u : 33u;
+      mbar_init(bar_full + 8 * s, kTf32 ? kXformThreads + 1 : a_arrivals);
       mbar_init(bar_empty + 8 * s, 1);
-      mbar_init(bar_landed + 8 * s, kGatherThreads + 1);
+      mbar_init(bar_landed + 8 * s, a_arrivals);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
       mbar_init(bar_tempty + 8 * a, kEpiThreads);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&feat_map) : "memory");
   }
   if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
@@ -206,38 +251,52 @@ conv_tc_kernel(const void *__restrict__ features, const uint8_t *__restrict__ wp
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp >= 4 && warp < kMmaWarp) {
-    // =============================== gather producers ===============================
+    // =============================== producers: neighbour prefetch + TMA issue ===============================
     const int tid = threadIdx.x - kEpiThreads;
-    const uint8_t *feat = static_cast<const uint8_t *>(features);
+    const int pwarp = tid >> 5;
+    const uint8_t *feat = static_cast<const uint8_t *>(feat_ptr);
     const size_t feat_row_bytes = (size_t)cin * kElem;
     uint32_t issued = 0;
-    // Item (it, tid) of a stage is the 16-byte unit  it*256 + tid  of the canonical layout
-    // ((row/8)*chunks + chunk)*8 + row%8.  With 256 threads the chunk of a thread is constant and only the
-    // row advances with `it`, so eight consecutive lanes write 128 contiguous bytes of shared memory (no bank
-    // conflicts) while lanes 8 apart read the next 16 bytes of the same global rows (full 32-byte sectors).
-    const int cshift = __ffs(chunks) - 1;            // chunks is 2, 4 or 8
-    const int my_chunk = (tid >> 3) & (chunks - 1);
-    const int my_row0 = ((tid >> (3 + cshift)) << 3) + (tid & 7);
-    const int rows_per_it = kGatherThreads >> cshift;  // 128, 64 or 32 rows per pass
-    const int iters = chunks >> 1;                     // kTileM * chunks / kGatherThreads
+    // LSU gather geometry: `lanes_per_row` = 16-byte chunks per row slice (8, 4 or 2); one warp instruction covers
+    // 32/lanes_per_row rows.  Swizzle<B,4,3>: chunk ^= (row >> (3-B)) & (chunks-1) with B = log2(chunks).
+    const int chunks = row_bytes >> 4;
+    const int cshift = __ffs(chunks) - 1;
+    const int my_chunk = lane & (chunks - 1);
+    const int my_row0 = lane >> cshift;
+    const int rows_per_instr = 32 >> cshift;
+    // The neighbour rows of a tile are prefetched into registers one tile ahead: the loads of tile t+1 are in
+    // flight while tile t's stages are being issued.  Thread t serves row t%128 for the offsets of parity t/128.
+    constexpr int kNbrRegs = FV2P_MAX_KVOL / 2;
+    int nbr_next[kNbrRegs];
+    const int pre_r = tid & (kTileM - 1);
+    const int pre_k0 = tid >> 7;
+    auto prefetch = [&](int tile) {
+      const int row = tile * kTileM + pre_r;
+#pragma unroll
+      for (int q = 0; q < kNbrRegs; ++q) {
+        const int k = pre_k0 + 2 * q;
+        nbr_next[q] = (tile < n_tiles && k < kvol && row < n_out) ? __ldg(&nbr[(size_t)k * nbr_stride + row]) : -1;
+      }
+    };
+    prefetch(blockIdx.x);
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int row0 = tile * kTileM;
-      // ---- neighbour rows of this tile -> smem, and which offsets feed anything
-      asm volatile("bar.sync 1, 256;" ::: "memory");  // everyone finished reading nbr_s of the previous tile
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // every producer warp finished reading nbr_s of the last tile
       if (tid == 0) *tile_mask = 0u;
       asm volatile("bar.sync 1, 256;" ::: "memory");
       {
-        const int r = tid & (kTileM - 1);
-        const int row = row0 + r;
         uint32_t mine = 0;
-        for (int k = tid >> 7; k < kvol; k += 2) {  // warps 4-7 take the even offsets, 8-11 the odd ones
-          int src = -1;
-          if (row < n_out) src = __ldg(&nbr[(size_t)k * nbr_stride + row]);
-          nbr_s[k * kTileM + r] = src;
-          if (__ballot_sync(0xFFFFFFFFu, src >= 0)) mine |= 1u << k;
+#pragma unroll
+        for (int q = 0; q < kNbrRegs; ++q) {
+          const int k = pre_k0 + 2 * q;
+          if (k < kvol) {
+            const int src = nbr_next[q];
+            nbr_s[k * kTileM + pre_r] = (src < 0 && use_tma) ? oob_row : src;  // TMA: out-of-range row -> zero fill
+            if (__ballot_sync(0xFFFFFFFFu, src >= 0)) mine |= 1u << k;
+          }
         }
         if (lane == 0 && mine) atomicOr(const_cast<uint32_t *>(tile_mask), mine);
       }
+      prefetch(tile + gridDim.x);
       asm volatile("bar.sync 1, 256;" ::: "memory");
       uint32_t mask = *tile_mask;
       if (mask == 0u) mask = 1u;  // a tile nothing feeds still has to produce (zero) accumulators
@@ -246,41 +305,56 @@ conv_tc_kernel(const void *__restrict__ features, const uint8_t *__restrict__ wp
       while (mask) {
         const int k = __ffs(mask) - 1;
         mask &= mask - 1;
-        int src_row[4];
-#pragma unroll
-        for (int it = 0; it < 4; ++it)
-          src_row[it] = it < iters ? nbr_s[k * kTileM + it * rows_per_it + my_row0] : -1;
-        for (int sl = 0; sl < slices; ++sl) {
+        for (int sl = 0; sl < slices; ++sl, ++issued) {
+          // A ring slot always belongs to the same producer warp, so each empty barrier is waited on by one warp
+          // in program order (the parity wait cannot alias, whatever the drift between warps); warps without a
+          // slot of their own (ring shorter than the warp count) only help with the neighbour prefetch.
           const uint32_t s = issued % C::kStages;
+          if ((int)(s % kProdWarps) != pwarp) continue;
           mbar_wait(bar_empty + 8 * s, ((issued / C::kStages) & 1) ^ 1);
-          uint8_t *a_dst = stage_base + (size_t)s * C::kStageBytes;
-          if (tid == 0) {
+          const uint32_t a_u32 = smem_u32(stage_base + (size_t)s * C::kStageBytes);
+          const uint32_t a_bar = kTf32 ? bar_landed + 8 * s : bar_full + 8 * s;
+          if (lane == 0) {
             stage_flags[s] = ((k == (int)first_k && sl == 0) ? 1 : 0) | ((k == (int)last_k && sl == slices - 1) ? 2 : 0);
-            const uint8_t *wsrc = wpacked + ((size_t)k * slices + sl) * w_stage_bytes * (kTf32 ? 2 : 1);
-            uint8_t *w_dst = a_dst + (kTf32 ? 2 : 1) * C::kABytes;
-            mbar_arrive_expect_tx(bar_full + 8 * s, w_stage_bytes * (kTf32 ? 2 : 1));
-            bulk_g2s(smem_u32(w_dst), wsrc, w_stage_bytes * (kTf32 ? 2 : 1), bar_full + 8 * s);
-            if constexpr (kTf32) mbar_arrive(bar_landed + 8 * s);
-          }
-          const uint32_t a_u32 = smem_u32(a_dst) + tid * 16;
-          const size_t col_off = (size_t)sl * row_bytes + my_chunk * 16;
-#pragma unroll
-          for (int it = 0; it < 4; ++it) {
-            if (it < iters) {
-              const int src = src_row[it];
-              const uint8_t *p = feat + (src >= 0 ? (size_t)src * feat_row_bytes + col_off : 0);
-              cp_async16(a_u32 + it * (kGatherThreads * 16), p, src >= 0 ? 16u : 0u);
+            const uint32_t wb = w_stage_bytes * (kTf32 ? 2 : 1);
+            const uint8_t *wsrc = wpacked + ((size_t)k * slices + sl) * wb;
+            const uint32_t w_u32 = a_u32 + (kTf32 ? 2 : 1) * C::kABytes;
+            const uint32_t a_tx = use_tma ? a_stage_bytes : 0u;
+            if constexpr (kTf32) {
+              if (use_tma) mbar_arrive_expect_tx(bar_landed + 8 * s, a_tx);
+              else mbar_arrive(bar_landed + 8 * s);
+              mbar_arrive_expect_tx(bar_full + 8 * s, wb);
+            } else {
+              mbar_arrive_expect_tx(bar_full + 8 * s, a_tx + wb);
             }
+            bulk_g2s(w_u32, wsrc, wb, bar_full + 8 * s);
           }
-          cp_async_arrive(kTf32 ? bar_landed + 8 * s : bar_full + 8 * s);
-          ++issued;
+          __syncwarp();
+          if (use_tma) {
+            // lane l gathers tile rows 4l..4l+3
+            const int4 rows = *reinterpret_cast<const int4 *>(&nbr_s[k * kTileM + 4 * lane]);
+            tma_gather4(a_u32 + (uint32_t)(4 * lane) * row_bytes, &feat_map, sl * (row_bytes / kElem), rows.x, rows.y,
+                        rows.z, rows.w, a_bar);
+          } else {
+            const size_t col_off = (size_t)sl * row_bytes + my_chunk * 16;
+            const int *rows_k = nbr_s + k * kTileM;
+#pragma unroll 4
+            for (int r = my_row0; r < kTileM; r += rows_per_instr) {
+              const int src = rows_k[r];
+              const uint32_t swz = (uint32_t)(my_chunk ^ ((r >> (3 - cshift)) & (chunks - 1)));
+              const uint8_t *p = feat + (src >= 0 ? (size_t)src * feat_row_bytes + col_off : 0);
+              cp_async16(a_u32 + (uint32_t)r * row_bytes + (swz << 4), p, src >= 0 ? 16u : 0u);
+            }
+            cp_async_arrive(a_bar);
+          }
         }
       }
     }
   } else if (warp == kMmaWarp) {
     // =============================== MMA issuer ===============================
     constexpr uint32_t idesc = instr_desc(N, kTf32);
-    const uint32_t sbo = (uint32_t)chunks * 128u;
+    const uint32_t sbo = 8u * (uint32_t)row_bytes;
+    const uint32_t layout = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
     const int ksteps = row_bytes >> 5;  // 32 bytes of K per MMA (16 bf16 / 8 tf32)
     uint32_t consumed = 0;
     int acc = 0;
@@ -300,12 +374,12 @@ conv_tc_kernel(const void *__restrict__ features, const uint8_t *__restrict__ wp
           const uint32_t a_addr = smem_u32(stage_base + (size_t)s * C::kStageBytes);
           const uint32_t w_addr = a_addr + (kTf32 ? 2 : 1) * C::kABytes;
           uint32_t accumulate = (flags & 1) ? 0u : 1u;
-          for (int j = 0; j < ksteps; ++j) {
-            const uint64_t a_hi = smem_desc(a_addr + j * 256, 128, sbo);
-            const uint64_t b_hi = smem_desc(w_addr + j * 256, 128, sbo);
+          for (int j = 0; j < (dbg == 4 ? 0 : ksteps); ++j) {
+            const uint64_t a_hi = smem_desc(a_addr + j * 32, sbo, layout);
+            const uint64_t b_hi = smem_desc(w_addr + j * 32, sbo, layout);
             if constexpr (kTf32) {
-              const uint64_t a_lo = smem_desc(a_addr + C::kABytes + j * 256, 128, sbo);
-              const uint64_t b_lo = smem_desc(w_addr + w_stage_bytes + j * 256, 128, sbo);
+              const uint64_t a_lo = smem_desc(a_addr + C::kABytes + j * 32, sbo, layout);
+              const uint64_t b_lo = smem_desc(w_addr + w_stage_bytes + j * 32, sbo, layout);
               tc_mma<true>(d_tmem, a_lo, b_hi, idesc, accumulate);
               tc_mma<true>(d_tmem, a_hi, b_lo, idesc, 1u);
               tc_mma<true>(d_tmem, a_hi, b_hi, idesc, 1u);
@@ -314,7 +388,7 @@ conv_tc_kernel(const void *__restrict__ features, const uint8_t *__restrict__ wp
             }
             accumulate = 1u;
           }
-          tc_commit(bar_empty + 8 * s);            // smem stage reusable once these MMAs retire
+          tc_commit(bar_empty + 8 * s);              // smem stage reusable once these MMAs retire
           if (last) tc_commit(bar_tfull + 8 * acc);  // accumulator complete
         }
         __syncwarp();
@@ -325,10 +399,12 @@ conv_tc_kernel(const void *__restrict__ features, const uint8_t *__restrict__ wp
     }
   } else if (warp > kMmaWarp) {
     // =============================== fp32 split (warps 13-16, 3xTF32 kernels only) ===============================
-    // A_raw <- hi = rn_tf32(x), A_lo <- rn_tf32(x - hi).  Done by warps that have no cp.async in flight, so
-    // the proxy fence that makes the generic-proxy stores visible to the tensor core does not stall on gathers.
+    // A_raw <- hi = rn_tf32(x), A_lo <- rn_tf32(x - hi), element-wise in place, so the swizzle is irrelevant here.
+    // These warps have no async copies in flight, so the proxy fence that makes their generic-proxy stores
+    // visible to the tensor core is cheap.
     if constexpr (kTf32) {
-      const int t = threadIdx.x - (kTcThreadsBase);
+      const int t = threadIdx.x - kTcThreadsBase;
+      const int units = (int)(a_stage_bytes >> 4) / kXformThreads;  // 16-byte units per thread: 8, 4 or 2
       uint32_t done = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         bool last = false;
@@ -340,7 +416,7 @@ conv_tc_kernel(const void *__restrict__ features, const uint8_t *__restrict__ wp
           uint8_t *a_lo = a_hi + C::kABytes;
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
-            if (it < chunks) {
+            if (it < units) {
               const int off = (it * kXformThreads + t) * 16;
               float4 x = *reinterpret_cast<float4 *>(a_hi + off);
               float4 h, l;
@@ -369,7 +445,7 @@ conv_tc_kernel(const void *__restrict__ features, const uint8_t *__restrict__ wp
       for (int c0 = 0; c0 < N; c0 += 16) {
         float v[16];
         tmem_ld16(taddr + c0, v);  // warp-collective: executed by all lanes even for rows past the end
-        if (row < n_out) {
+        if (row < n_out && dbg != 6) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             float x = v[i];
@@ -442,15 +518,23 @@ conv_tc_kernel(const void *__restrict__ features, const uint8_t *__restrict__ wp
   }
 }
 
+// Byte offset of 16-byte chunk c of row n inside a K-major tile with `row_bytes` per row and the matching
+// 128B/64B/32B swizzle (Swizzle<B,4,3>: address bits [4,4+B) ^= bits [7,7+B)).
+__host__ __device__ inline size_t swizzled_offset(int n, int c, int row_bytes) {
+  const size_t lin = (size_t)n * row_bytes + (size_t)c * 16;
+  const int bits = row_bytes == 128 ? 3 : (row_bytes == 64 ? 2 : 1);
+  const size_t x = (lin >> 7) & ((1u << bits) - 1);
+  return lin ^ (x << 4);
+}
+
 // Packs W [K,cin,cout] fp32 into per-(offset, 128-byte slice) shared-memory images of the B operand
-// (N x Kslice, K-major canonical layout: ((n/8)*chunks + chunk)*8 + n%8 sixteen-byte units).
+// (N rows x Kslice, K-major, swizzled like the A tile so one bulk copy drops it in place).
 template <bool kTf32>
 __global__ void __launch_bounds__(kThreads)
 pack_weight_kernel(const float *__restrict__ w, int kvol, int cin, int cout, uint8_t *packed) {
   constexpr int kElem = kTf32 ? 4 : 2;
   constexpr int kPerChunk = 16 / kElem;
   const int row_bytes = min(cin * kElem, 128);
-  const int chunks = row_bytes >> 4;
   const int slices = (cin * kElem) / row_bytes;
   const int per_slice = row_bytes / kElem;  // input channels per slice
   const int64_t total = (int64_t)kvol * cin * cout;
@@ -461,15 +545,15 @@ pack_weight_kernel(const float *__restrict__ w, int kvol, int cin, int cout, uin
     const int k = (int)(e / ((int64_t)cout * cin));
     const int sl = ci / per_slice, within = ci % per_slice;
     const int c = within / kPerChunk, t = within % kPerChunk;
-    const size_t unit = ((size_t)(n >> 3) * chunks + c) * 8 + (n & 7);
+    const size_t off = swizzled_offset(n, c, row_bytes);
     const float val = w[e];
     uint8_t *base = packed + ((size_t)k * slices + sl) * image * (kTf32 ? 2 : 1);
     if constexpr (kTf32) {
       const float hi = tf32_rn(val);
-      reinterpret_cast<float *>(base + unit * 16)[t] = hi;
-      reinterpret_cast<float *>(base + image + unit * 16)[t] = tf32_rn(val - hi);
+      reinterpret_cast<float *>(base + off)[t] = hi;
+      reinterpret_cast<float *>(base + image + off)[t] = tf32_rn(val - hi);
     } else {
-      reinterpret_cast<__nv_bfloat16 *>(base + unit * 16)[t] = __float2bfloat16_rn(val);
+      reinterpret_cast<__nv_bfloat16 *>(base + off)[t] = __float2bfloat16_rn(val);
     }
   }
 }
@@ -480,9 +564,51 @@ bool tc_shape_ok(int cin, int cout) {
   return n_ok && k_ok;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (the library links no libcuda).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2D map over the feature matrix [rows, cin]; box = one row slice of row_bytes; gather4 fetches four boxes.
+int make_feature_map(CUtensorMap *map, const void *features, int64_t rows, int cin, bool tf32) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    set_error("conv_fwd(tc): cuTensorMapEncodeTiled is not available from this driver");
+    return FV2P_ERR_DEVICE;
+  }
+  const int elem = tf32 ? 4 : 2;
+  const int row_bytes = cin * elem < 128 ? cin * elem : 128;
+  cuuint64_t gdim[2] = {(cuuint64_t)cin, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)cin * elem};
+  cuuint32_t box[2] = {(cuuint32_t)(row_bytes / elem), 1};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMapSwizzle sw = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                           : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  CUresult r = fn(map, tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                  const_cast<void *>(features), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("conv_fwd(tc): cuTensorMapEncodeTiled failed with %d (rows=%lld cin=%d)", (int)r, (long long)rows, cin);
+    return FV2P_ERR_INVALID;
+  }
+  return 0;
+}
+
 template <bool kTf32, int N>
-int launch_one(const void *features, const void *weight, const int *nbr, int64_t nbr_stride, int kvol,
-               int64_t n_out_cap, const int *n_out_dev, int cin, const Epilogue &ep, cudaStream_t stream) {
+int launch_one(const void *features, int64_t feat_rows, const void *weight, const int *nbr, int64_t nbr_stride,
+               int kvol, int64_t n_out_cap, const int *n_out_dev, int cin, const Epilogue &ep, cudaStream_t stream) {
   using C = Cfg<kTf32, N>;
   static bool configured = false;
   if (!configured) {
@@ -492,18 +618,25 @@ int launch_one(const void *features, const void *weight, const int *nbr, int64_t
     if (st) return st;
     configured = true;
   }
+  CUtensorMap map;
+  int st = make_feature_map(&map, features, feat_rows, cin, kTf32);
+  if (st) return st;
+  // Measured on B200 (profiles/r1_notes.md): the TMA gather wins for fp32 rows of 128 bytes and more (the LSU
+  // path also has to feed the transform warps there), the swizzled cp.async gather everywhere else.
+  const int use_tma = g_tc_gather_mode >= 0 ? g_tc_gather_mode : ((kTf32 && cin >= 32) ? 1 : 0);
   int64_t tiles = (n_out_cap + kTileM - 1) / kTileM;
   int grid = (int)(tiles < sm_count() ? tiles : sm_count());
   if (grid < 1) grid = 1;
   conv_tc_kernel<kTf32, N><<<grid, C::kThreads, C::kSmemBytes, stream>>>(
-      features, static_cast<const uint8_t *>(weight), nbr, nbr_stride, kvol, n_out_cap, n_out_dev, cin, ep);
+      map, features, static_cast<const uint8_t *>(weight), nbr, nbr_stride, kvol, n_out_cap, n_out_dev, cin,
+      (int)feat_rows, use_tma, ep);
   return cuda_status(cudaGetLastError(), "conv_fwd(tc)");
 }
 
 }  // namespace
 
-int launch_conv_tc(const void *features, const void *weight, const int *nbr, int64_t nbr_stride, int kvol,
-                   int64_t n_out_cap, const int *n_out_dev, int cin, int cout, const float *bias,
+int launch_conv_tc(const void *features, int64_t feat_rows, const void *weight, const int *nbr, int64_t nbr_stride,
+                   int kvol, int64_t n_out_cap, const int *n_out_dev, int cin, int cout, const float *bias,
                    const float *scale, const float *shift, const void *residual, int relu, int mode, void *out,
                    cudaStream_t stream) {
   if (!tc_shape_ok(cin, cout)) {
@@ -511,13 +644,17 @@ int launch_conv_tc(const void *features, const void *weight, const int *nbr, int
               cin, cout);
     return FV2P_ERR_INVALID;
   }
+  if (feat_rows < 1 || feat_rows >= (1ll << 31) - 1) {
+    set_error("conv_fwd: tensor-core modes need the input row capacity (got %lld)", (long long)feat_rows);
+    return FV2P_ERR_INVALID;
+  }
   Epilogue ep{bias, scale, shift, residual, out, relu};
   const bool tf32 = mode == FV2P_MODE_TF32X3_TC;
-#define FV2P_TC(NN)                                                                                           \
-  return tf32 ? launch_one<true, NN>(features, weight, nbr, nbr_stride, kvol, n_out_cap, n_out_dev, cin, ep,  \
-                                     stream)                                                                 \
-              : launch_one<false, NN>(features, weight, nbr, nbr_stride, kvol, n_out_cap, n_out_dev, cin, ep, \
-                                      stream)
+#define FV2P_TC(NN)                                                                                            \
+  return tf32 ? launch_one<true, NN>(features, feat_rows, weight, nbr, nbr_stride, kvol, n_out_cap, n_out_dev, \
+                                     cin, ep, stream)                                                          \
+              : launch_one<false, NN>(features, feat_rows, weight, nbr, nbr_stride, kvol, n_out_cap, n_out_dev, \
+                                      cin, ep, stream)
   switch (cout) {
     case 16: FV2P_TC(16);
     case 32: FV2P_TC(32);
@@ -530,6 +667,19 @@ int launch_conv_tc(const void *features, const void *weight, const int *nbr, int
 }  // namespace fv2p
 
 using namespace fv2p;
+
+extern "C" int fv2p_tc_gather_mode(int mode) {
+  g_tc_gather_mode = mode < 0 ? -1 : (mode ? 1 : 0);
+  return FV2P_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int fv2p_debug_poll(int v) {
+  return (int)cudaMemcpyToSymbol(g_tc_poll, &v, sizeof(int));
+}
+
+extern "C" __attribute__((visibility("default"))) int fv2p_debug_set(int v) {
+  return (int)cudaMemcpyToSymbol(g_tc_debug, &v, sizeof(int));
+}
 
 extern "C" size_t fv2p_pack_weight_bytes(int kvol, int cin, int cout, int mode) {
   if (kvol < 1 || kvol > FV2P_MAX_KVOL || !tc_shape_ok(cin, cout)) return 0;

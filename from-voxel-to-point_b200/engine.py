@@ -316,7 +316,7 @@ class BackboneEngine(object):
                 out = a["bufs"][st_.out_buf]
                 nbr = a["books"][st_.key]["nbr"]
                 w = p["packed"] if p["packed"] is not None else p["w"]
-                rc = lib.fv2p_conv_fwd(_lib.ptr(src), _lib.ptr(w), _lib.ptr(nbr), nbr.shape[1], st_.kvol,
+                rc = lib.fv2p_conv_fwd(_lib.ptr(src), src.shape[0], _lib.ptr(w), _lib.ptr(nbr), nbr.shape[1], st_.kvol,
                                        level_cap[st_.out_level], n_ptr[st_.out_level], st_.cin, st_.cout,
                                        _lib.ptr(p["bias"]), _lib.ptr(p["scale"]), _lib.ptr(p["shift"]), _lib.ptr(res),
                                        int(st_.relu), p["mode"], _lib.ptr(out), stream)

@@ -78,6 +78,36 @@ class HotPath(object):
         arena = self.engine.launch(vox["voxel_features"], vox["voxel_coords"], batch, n0_dev=n0, cap0=vox["cap"])
         return dict(vox=vox, arena=arena, batch=batch)
 
+    def launch_graph(self, frame_offsets_dev=None):
+        """Same step as launch_resident over the WHOLE staging buffer, replayed from a CUDA graph.
+
+        The step has no host synchronisation and every buffer (points staging, voxel outputs, rulebooks, feature
+        arena) has a fixed address, so it is captured once per staging capacity and replayed with one launch.
+        Row counts are read from device memory by every kernel, so the same graph serves batches with different
+        point counts up to the staging capacity.  Call upload() first; returns the handle for finish()."""
+        s = self._stage
+        if s is None:
+            raise RuntimeError("launch_graph: call upload() first")
+        off = s["dev_off"] if frame_offsets_dev is None else frame_offsets_dev
+        key = (s["dev_pts"].data_ptr(), off.data_ptr(), s["pcap"], s["batch"])
+        entry = self._graphs.get(key)
+        if entry is None:
+            cur = torch.cuda.current_stream(s["device"])
+            side = torch.cuda.Stream(device=s["device"])
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):  # warm-up: allocates arenas, packs weights, sets kernel attributes
+                for _ in range(2):
+                    handle = self.launch_resident(s["dev_pts"], off, s["pcap"])
+            cur.wait_stream(side)
+            torch.cuda.synchronize(s["device"])
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                handle = self.launch_resident(s["dev_pts"], off, s["pcap"])
+            entry = (graph, handle)
+            self._graphs[key] = entry
+        entry[0].replay()
+        return entry[1]
+
     def finish(self, handle, fetch="counts", sync=True):
         """D2H of the row counts (always) and, with fetch='encoded', of the stride-8 output features and
         indices.  Returns (outputs dict of SparseConvTensor, info dict)."""
@@ -91,12 +121,12 @@ class HotPath(object):
             stream.synchronize()
             outs, n = eng.views(arena, vox["voxel_coords"], batch)
             enc = outs["out"]
-            key = "enc_host"
             need = (enc.features.shape[0], enc.features.shape[1])
-            hb = handle.get(key)
-            if hb is None or hb[0].shape[0] < need[0]:
+            hb = getattr(self, "_enc_host", None)
+            if hb is None or hb[0].shape[0] < need[0] or hb[0].shape[1] != need[1] or hb[0].dtype != enc.features.dtype:
                 hb = (torch.empty((int(need[0] * 1.2) + 64, need[1]), dtype=enc.features.dtype).pin_memory(),
                       torch.empty((int(need[0] * 1.2) + 64, 4), dtype=torch.int32).pin_memory())
+                self._enc_host = hb  # pinned staging for the result, grow-only
             hb[0][:need[0]].copy_(enc.features, non_blocking=True)
             hb[1][:need[0]].copy_(enc.indices, non_blocking=True)
             stream.synchronize()
@@ -111,7 +141,7 @@ class HotPath(object):
 
     def __call__(self, frames, device="cuda", fetch="counts"):
         pts, off, mfp, h2d = self.upload(frames, device)
-        handle = self.launch_resident(pts, off, mfp)
+        handle = self.launch_graph() if self.use_graph else self.launch_resident(pts, off, mfp)
         outs, info = self.finish(handle, fetch)
         info["h2d_bytes"] = h2d
         batch_dict = {

@@ -152,7 +152,8 @@ def conv_forward(features, weight_flat, nbr, num_activate_out, bias=None, scale=
         out = torch.empty((n_cap, cout), dtype=out_dtype, device=features.device)
     assert nbr.stride(1) == 1 and out.is_contiguous() and features.is_contiguous()
     with torch.cuda.device(dev):
-        st = _lib.load().fv2p_conv_fwd(_lib.ptr(features), _lib.ptr(weight_flat), _lib.ptr(nbr), nbr.stride(0), kvol,
+        st = _lib.load().fv2p_conv_fwd(_lib.ptr(features), features.shape[0], _lib.ptr(weight_flat), _lib.ptr(nbr),
+                                       nbr.stride(0), kvol,
                                        n_cap, _lib.ptr(n_out_dev), cin, cout, _lib.ptr(bias), _lib.ptr(scale),
                                        _lib.ptr(shift), _lib.ptr(residual), int(relu), int(mode), _lib.ptr(out),
                                        _lib.stream_ptr(features.device))

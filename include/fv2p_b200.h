@@ -161,15 +161,21 @@ FV2P_API int fv2p_pairs_to_nbr(const int32_t *pairs, const int32_t *pair_num, in
  *     out[i,:] = act( (sum_k X[nbr[k][i],:] * W[k] + bias) * scale + shift + residual[i,:] )
  * Any of bias/scale/shift/residual may be NULL.  scale/shift are the folded eval BatchNorm:
  * scale = gamma / sqrt(var + eps), shift = beta - mean * scale.
- *   features  device [*,cin]   (fp32 or bf16 by mode)
+ *   features  device [n_in_cap,cin]   (fp32 or bf16 by mode); n_in_cap = rows the buffer holds (the tensor-core
+ *             modes describe it to the TMA unit; every neighbour index must be < n_in_cap)
  *   weight    device: FV2P_MODE_F32 / *_SIMT: [K,cin,cout] fp32 (the reference layout, flattened);
  *             tensor-core modes: the packed image written by fv2p_pack_weight
  *   n_out_cap rows of `out`/`nbr` columns; live count *n_out_dev if given
  * ------------------------------------------------------------------------------------------- */
-FV2P_API int fv2p_conv_fwd(const void *features, const void *weight, const int32_t *nbr, int64_t nbr_stride,
+FV2P_API int fv2p_conv_fwd(const void *features, int64_t n_in_cap, const void *weight, const int32_t *nbr, int64_t nbr_stride,
                   int kvol, int64_t n_out_cap, const int32_t *n_out_dev, int cin, int cout,
                   const float *bias, const float *scale, const float *shift, const void *residual,
                   int relu, int mode, void *out, fv2p_stream_t stream);
+
+/* Producer of the gathered A tile in the tensor-core kernels: -1 = auto (default: measured best per shape),
+ * 0 = LSU (swizzled cp.async), 1 = TMA (cp.async.bulk.tensor tile::gather4).  Same results either way; a tuning
+ * knob kept for measurement (profiles/r1_notes.md).  Process-wide, not stream-ordered. */
+FV2P_API int fv2p_tc_gather_mode(int mode);
 
 /* Packed weight image for the tensor-core modes (done once per layer, device to device). */
 FV2P_API size_t fv2p_pack_weight_bytes(int kvol, int cin, int cout, int mode);

@@ -1,0 +1,87 @@
+"""Profiling helper: builds the bench workload, runs two full steps, then re-launches one conv layer a few
+times so that `ncu -k regex:<kernel> -s <skip> -c <n>` can capture it.  Usage (under gpurun):
+    ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 40 -c 2 \
+        -o gpurun_out/prof python profiles/run_layer.py --precision bf16 --layer 12
+"""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--precision", default="bf16")
+ap.add_argument("--workload", default="kitti_b8")
+ap.add_argument("--layer", type=int, default=12)
+ap.add_argument("--repeat", type=int, default=3)
+ap.add_argument("--tma", type=int, default=-1)
+ap.add_argument("--poll", type=int, default=0)
+ap.add_argument("--debug", type=int, nargs="*", default=[])
+a = ap.parse_args()
+wl = bench.WORKLOADS[a.workload]
+dev = torch.device("cuda", 0)
+net, hp, state, cfg = bench.build_model(wl, dev, a.precision)
+frames = bench.make_frames(wl, 0, wl["batch"])
+pts, off, mfp, _ = hp.upload(frames, dev)
+from fv2p_b200 import _lib as _L  # noqa: E402
+_L.load().fv2p_tc_gather_mode(a.tma)
+_L.load().fv2p_debug_poll(a.poll)
+for _ in range(2):
+    h = hp.launch_resident(pts, off, mfp)
+    hp.finish(h)
+from fv2p_b200 import _lib  # noqa: E402
+eng, arena = hp.engine, h["arena"]
+prm = eng._prepare_params(dev)
+st, p = eng.steps[a.layer], prm[a.layer]
+caps = [h["vox"]["cap"]] + arena["caps"][1:]
+nbr = arena["books"][st.key]["nbr"]
+src = h["vox"]["voxel_features"] if st.in_buf < 0 else arena["bufs"][st.in_buf]
+res = arena["bufs"][st.res_buf] if st.res_buf is not None else None
+out = arena["bufs"][st.out_buf]
+w = p["packed"] if p["packed"] is not None else p["w"]
+flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+for _ in range(a.repeat):
+    flush.zero_()
+    rc = _lib.load().fv2p_conv_fwd(_lib.ptr(src), src.shape[0], _lib.ptr(w), _lib.ptr(nbr), nbr.shape[1], st.kvol, caps[st.out_level],
+                                   _lib.ctypes.c_void_p(arena["counts"].data_ptr() + 4 * st.out_level), st.cin,
+                                   st.cout, _lib.ptr(p["bias"]), _lib.ptr(p["scale"]), _lib.ptr(p["shift"]),
+                                   _lib.ptr(res), int(st.relu), p["mode"], _lib.ptr(out), _lib.stream_ptr(dev))
+    _lib.check(rc, "conv_fwd")
+torch.cuda.synchronize()
+import ctypes  # noqa: E402
+for mode in a.debug:
+    lib = _lib.load()
+    lib.fv2p_debug_set(ctypes.c_int(mode))
+    ts = []
+    for _ in range(3):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        lib.fv2p_conv_fwd(_lib.ptr(src), src.shape[0], _lib.ptr(w), _lib.ptr(nbr), nbr.shape[1], st.kvol, caps[st.out_level],
+                          _lib.ctypes.c_void_p(arena["counts"].data_ptr() + 4 * st.out_level), st.cin, st.cout,
+                          _lib.ptr(p["bias"]), _lib.ptr(p["scale"]), _lib.ptr(p["shift"]), _lib.ptr(res), int(st.relu),
+                          p["mode"], _lib.ptr(out), _lib.stream_ptr(dev))
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    print("debug mode", mode, "ms", min(ts))
+    if mode == 8:
+        buf = (ctypes.c_longlong * 64)()
+        lib.fv2p_debug_prof(buf, 1)
+        lib.fv2p_conv_fwd(_lib.ptr(src), src.shape[0], _lib.ptr(w), _lib.ptr(nbr), nbr.shape[1], st.kvol, caps[st.out_level],
+                          _lib.ctypes.c_void_p(arena["counts"].data_ptr() + 4 * st.out_level), st.cin, st.cout,
+                          _lib.ptr(p["bias"]), _lib.ptr(p["scale"]), _lib.ptr(p["shift"]), _lib.ptr(res), int(st.relu),
+                          p["mode"], _lib.ptr(out), _lib.stream_ptr(dev))
+        torch.cuda.synchronize()
+        lib.fv2p_debug_prof(buf, 0)
+        v = list(buf)
+        print("  gather: blocked_on_empty=%d cyc over %d stages, prologue=%d, loop=%d" % (v[0], v[1], v[2], v[3]))
+
+
+        print("  mma:    blocked_on_tmem_empty=%d, blocked_on_full=%d over %d stages, loop=%d" % (v[8], v[9], v[10], v[11]))
+        print("  epi:    blocked_on_tmem_full=%d, loop=%d" % (v[16], v[17]))
+    lib.fv2p_debug_set(ctypes.c_int(0))
+print("layer", a.layer, st.key, st.cin, st.cout, "mode", p["mode"], "rows", hp.finish(h)[1]["counts"])
