@@ -43,8 +43,14 @@ void launch_set_scalar(int *dst, int value, cudaStream_t stream) {
 
 // One CTA per segment: in-place exclusive scan of counts[seg][0..n_chunks), totals[seg] = sum.
 __global__ void __launch_bounds__(kThreads) scan_chunk_counts_kernel(int *counts, int64_t seg_stride,
-                                                                     int n_chunks, int *totals) {
+                                                                     int n_chunks, const int *n_dev, int *totals) {
   __shared__ int smem[kThreads / 32 + 1];
+  if (n_dev) {
+    int n = *n_dev;
+    n = n < 0 ? 0 : n;
+    const int live = live_chunks(n);
+    n_chunks = live < n_chunks ? live : n_chunks;
+  }
   int *row = counts + (size_t)blockIdx.x * seg_stride;
   int running = 0;
   for (int base = 0; base < n_chunks; base += kThreads) {
@@ -58,11 +64,11 @@ __global__ void __launch_bounds__(kThreads) scan_chunk_counts_kernel(int *counts
   if (threadIdx.x == 0 && totals) totals[blockIdx.x] = running;
 }
 
-void launch_scan_chunk_counts(int *counts, int segments, int64_t seg_stride, const int *, int64_t n_cap,
+void launch_scan_chunk_counts(int *counts, int segments, int64_t seg_stride, const int *n_dev, int64_t n_cap,
                               int *totals, cudaStream_t stream) {
   int n_chunks = (int)((n_cap + kChunk - 1) / kChunk);
   if (n_chunks < 1) n_chunks = 1;
-  scan_chunk_counts_kernel<<<segments, kThreads, 0, stream>>>(counts, seg_stride, n_chunks, totals);
+  scan_chunk_counts_kernel<<<segments, kThreads, 0, stream>>>(counts, seg_stride, n_chunks, n_dev, totals);
 }
 
 }  // namespace fv2p

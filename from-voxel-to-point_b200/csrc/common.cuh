@@ -133,7 +133,29 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int *smem, int &total
   return r;
 }
 
-// counts[segment][chunk] -> exclusive prefix in place, totals[segment] = sum.  One CTA per segment.
+// Exclusive scan of one 0/1 flag per thread (ballot + popc, two barriers); block total through `total`.
+__device__ __forceinline__ int block_flag_scan(bool flag, int *smem, int &total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned bal = __ballot_sync(0xFFFFFFFFu, flag);
+  if (lane == 0) smem[warp] = __popc(bal);
+  __syncthreads();
+  int base = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < kThreads / 32; ++w) {
+    const int c = smem[w];
+    if (w < warp) base += c;
+    tot += c;
+  }
+  total = tot;
+  __syncthreads();  // smem may be reused by the next call
+  return base + __popc(bal & ((1u << lane) - 1u));
+}
+
+// Number of kChunk-row work items that hold live rows (device-side count).
+__device__ __forceinline__ int live_chunks(int n) { return (n + kChunk - 1) / kChunk; }
+
+// counts[segment][chunk] -> exclusive prefix in place, totals[segment] = sum.  One CTA per segment.  With n_dev
+// the scan covers only the chunks that hold live rows (capacity-sized tails are never written nor read).
 void launch_scan_chunk_counts(int *counts, int segments, int64_t seg_stride, const int *n_dev,
                               int64_t n_cap, int *totals, cudaStream_t stream);
 

@@ -115,14 +115,10 @@ subm_probe_kernel(const int4 *__restrict__ indices, const int *n_dev, int64_t n_
   const int n = live_count(n_dev, n_cap);
   const uint32_t mask = table_slots_for(n) - 1;
   const int D = g.out_shape[0], H = g.out_shape[1], W = g.out_shape[2];
-  const int work = n_chunks * g.kvol;
+  const int work = live_chunks(n) * g.kvol;  // only chunks that hold live rows (capacity tails cost nothing)
   for (int w = blockIdx.x; w < work; w += gridDim.x) {
     const int c = w / g.kvol, k = w - c * g.kvol;
     const int base = c * kChunk;
-    if (base >= n) {
-      if (threadIdx.x == 0) counts[(size_t)k * n_chunks + c] = 0;
-      continue;
-    }
     const int kx = k % g.ksize[2], ky = (k / g.ksize[2]) % g.ksize[1], kz = k / (g.ksize[2] * g.ksize[1]);
     const int dz = kz * g.dil[0] - g.pad[0], dy = ky * g.dil[1] - g.pad[1], dx = kx * g.dil[2] - g.pad[2];
     unsigned long long key[kItemsPerThread], seen[kItemsPerThread];
@@ -178,7 +174,7 @@ subm_probe_in_kernel(const int4 *__restrict__ indices, const int *n_dev, int64_t
   const int n = live_count(n_dev, n_cap);
   const uint32_t mask = table_slots_for(n) - 1;
   const int D = g.out_shape[0], H = g.out_shape[1], W = g.out_shape[2];
-  for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+  for (int c = blockIdx.x; c < live_chunks(n); c += gridDim.x) {
     if (threadIdx.x < FV2P_MAX_KVOL) hits[threadIdx.x] = 0;
     __syncthreads();
     const int base = c * kChunk;
@@ -241,7 +237,7 @@ conv_winner_kernel(const int *n_dev, int64_t n_cap, int emax, const int *__restr
                    const int *__restrict__ cand_slot, uint32_t *wmask, int *counts, int n_chunks) {
   __shared__ int smem[kThreads / 32 + 1];
   const int n = live_count(n_dev, n_cap);
-  for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+  for (int c = blockIdx.x; c < live_chunks(n); c += gridDim.x) {
     const int base = c * kChunk;
     int mine = 0;
     if (base < n) {
@@ -279,7 +275,7 @@ conv_assign_kernel(const int4 *__restrict__ indices, const int *n_dev, int64_t n
     }
     *n_out_dev = total;
   }
-  for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+  for (int c = blockIdx.x; c < live_chunks(n); c += gridDim.x) {
     const int base = c * kChunk;
     if (base >= n) continue;
     int running = chunk_prefix[c];
@@ -332,7 +328,7 @@ conv_pairs_kernel(const int4 *__restrict__ indices, const int *n_dev, int64_t n_
                   int *mat, int64_t mat_stride, int *counts, int n_chunks) {
   __shared__ int hits[FV2P_MAX_KVOL];
   const int n = live_count(n_dev, n_cap);
-  for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+  for (int c = blockIdx.x; c < live_chunks(n); c += gridDim.x) {
     if (threadIdx.x < FV2P_MAX_KVOL) hits[threadIdx.x] = 0;
     __syncthreads();
     const int base = c * kChunk;
@@ -374,11 +370,12 @@ compact_pairs_kernel(const int *__restrict__ mat, int64_t mat_stride, const int 
                      int n_chunks, int *pairs, int64_t pair_stride, int *pair_num) {
   __shared__ int smem[kThreads / 32 + 1];
   const int n = live_count(n_dev, n_cap);
-  const int work = kvol * n_chunks;
+  const int lc = max(live_chunks(n), 1);  // chunk 0 always runs: it publishes pair_num even for an empty input
+  const int work = kvol * lc;
   for (int w = blockIdx.x; w < work; w += gridDim.x) {
-    const int kk = w / n_chunks, c = w - kk * n_chunks;
+    const int kk = w / lc, c = w - kk * lc;
     const int src = mirror ? kvol - 1 - kk : kk;
-    const int total = row_totals[src];
+    const int total = n > 0 ? row_totals[src] : 0;
     if (c == 0 && threadIdx.x == 0 && pair_num) pair_num[kk] = total;
     const int base = c * kChunk;
     if (base >= n || !pairs) continue;
@@ -390,7 +387,7 @@ compact_pairs_kernel(const int *__restrict__ mat, int64_t mat_stride, const int 
       const bool live = j < n;
       const int v = live ? mat[(size_t)src * mat_stride + j] : -1;
       int tot;
-      const int pos = running + block_exclusive_scan(v >= 0, smem, tot);
+      const int pos = running + block_flag_scan(v >= 0, smem, tot);
       running += tot;
       if (live) {
         if (v >= 0) {
@@ -532,6 +529,11 @@ extern "C" int fv2p_rulebook_subm(const int32_t *indices, int64_t n_cap, const i
     set_error("rulebook_subm: workspace too small (%zu < %zu)", workspace_bytes, w.bytes);
     return FV2P_ERR_WORKSPACE;
   }
+  const int *n_live = n_dev;
+  if (!n_live) {  // host-known count: publish it once so the chunk scans can bound themselves the same way
+    launch_set_scalar(w.scalars, (int)n_cap, stream);
+    n_live = w.scalars;
+  }
   bool mirror = true;
   for (int a = 0; a < 3; ++a) mirror = mirror && (g.ksize[a] % 2 == 1) && g.dil[a] == 1;
   const bool want_pairs = pairs || pair_num;
@@ -554,7 +556,7 @@ extern "C" int fv2p_rulebook_subm(const int32_t *indices, int64_t n_cap, const i
       src_mat = w.mat;
       src_stride = n_cap;
     }
-    launch_scan_chunk_counts(w.counts, g.kvol, w.n_chunks, nullptr, (int64_t)w.n_chunks * kChunk, w.row_totals,
+    launch_scan_chunk_counts(w.counts, g.kvol, w.n_chunks, n_live, (int64_t)w.n_chunks * kChunk, w.row_totals,
                              stream);
     compact_pairs_kernel<<<grid, kThreads, 0, stream>>>(src_mat, src_stride, n_dev, n_cap, g.kvol, mirror ? 1 : 0,
                                                         w.counts, w.row_totals, w.n_chunks, pairs, pair_stride,
@@ -594,12 +596,17 @@ extern "C" int fv2p_rulebook_conv(const int32_t *indices, int64_t n_cap, const i
   const bool want_pairs = pairs || pair_num;
   const int grid = persistent_grid();
   const int4 *ind4 = reinterpret_cast<const int4 *>(indices);
+  const int *n_live = n_dev;
+  if (!n_live) {
+    launch_set_scalar(w.scalars, (int)n_cap, stream);
+    n_live = w.scalars;
+  }
   table_clear_kernel<<<grid, kThreads, 0, stream>>>(w.keys, w.vals, n_dev, n_cap, g.emax, out_cap, INT_MAX);
   conv_insert_kernel<<<grid, kThreads, 0, stream>>>(ind4, n_dev, n_cap, g, out_cap, w.keys, w.vals, w.cand_slot);
   conv_winner_kernel<<<grid, kThreads, 0, stream>>>(n_dev, n_cap, g.emax, w.vals, w.cand_slot, w.wmask,
                                                     w.win_counts, w.n_chunks);
-  launch_scan_chunk_counts(w.win_counts, 1, w.n_chunks, nullptr, (int64_t)w.n_chunks * kChunk, w.row_totals + FV2P_MAX_KVOL,
-                           stream);
+  launch_scan_chunk_counts(w.win_counts, 1, w.n_chunks, n_live, (int64_t)w.n_chunks * kChunk,
+                           w.row_totals + FV2P_MAX_KVOL, stream);
   conv_assign_kernel<<<grid, kThreads, 0, stream>>>(ind4, n_dev, n_cap, g, out_cap, w.vals, w.cand_slot, w.wmask,
                                                     w.win_counts, w.row_totals + FV2P_MAX_KVOL, w.n_chunks,
                                                     reinterpret_cast<int4 *>(out_indices), n_out_dev, status_dev);
@@ -608,7 +615,7 @@ extern "C" int fv2p_rulebook_conv(const int32_t *indices, int64_t n_cap, const i
     conv_pairs_kernel<<<grid, kThreads, 0, stream>>>(ind4, n_dev, n_cap, g, w.vals, w.cand_slot, nbr, nbr_stride,
                                                      want_pairs ? w.mat : nullptr, n_cap, w.counts, w.n_chunks);
   if (want_pairs) {
-    launch_scan_chunk_counts(w.counts, g.kvol, w.n_chunks, nullptr, (int64_t)w.n_chunks * kChunk, w.row_totals,
+    launch_scan_chunk_counts(w.counts, g.kvol, w.n_chunks, n_live, (int64_t)w.n_chunks * kChunk, w.row_totals,
                              stream);
     compact_pairs_kernel<<<grid, kThreads, 0, stream>>>(w.mat, n_cap, n_dev, n_cap, g.kvol, 0, w.counts,
                                                         w.row_totals, w.n_chunks, pairs, pair_stride, pair_num);
