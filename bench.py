@@ -214,10 +214,9 @@ def run_ours(args, wl, rank, world, device):
     clocks = sampler.stop(t_wall0, time.perf_counter())
 
     # ---- reduce over ranks (MAX of elapsed)
-    t = torch.tensor([total_ms, e2e_s * 1000.0], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms = float(t[0].item()), float(t[1].item())
+    from fv2p_b200 import sharding
+    total_ms = sharding.max_over_ranks(total_ms, device)
+    e2e_ms = sharding.max_over_ranks(e2e_s * 1000.0, device)
     frames_total = wl["batch"] * args.steps * world
     value = frames_total / (total_ms / 1000.0)
     e2e_value = frames_total / (e2e_ms / 1000.0)
@@ -241,11 +240,41 @@ def run_ours(args, wl, rank, world, device):
     else:
         roof = dict(bound="hbm", achieved=round(gbs, 1), peak=pk["hbm_gbs"], unit="GB/s",
                     frac=round(gbs / pk["hbm_gbs"], 5))
-    roof.update(traffic=None, peak_source=pk["source"],
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(tpath):  # dram bytes per launch of the same kernel shape from the committed ncu --set full capture
+        traffic = json.load(open(tpath)).get("%s:%d:%d" % (precision, dom["cin"], dom["cout"]))
+    roof.update(traffic=traffic, peak_source=pk["source"],
                 kernel="conv_fwd layer %d (%s, %d->%d, N_out=%d, pairs=%d, mode=%d)" % (
                     dom["layer"], dom["key"], dom["cin"], dom["cout"], dom["n_out"], dom["pairs"], dom["mode"]),
                 kernel_ms=round(dom["ms"], 4), kernel_share_of_conv=round(dom["ms"] / conv_ms, 3),
                 algorithmic_flops=dom["flops"], algorithmic_bytes=dom["bytes"])
+    # ---- the HBM-bound stages, timed as groups with CUDA events (L2 flushed first)
+    def timed(fn):
+        best = 1e9
+        for _ in range(3):
+            flush()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return best
+    vox_ms = timed(lambda: hp.voxelizer(pts, off, mfp))
+    vox = hp.voxelizer(pts, off, mfp)
+    eng = hp.engine
+    n0 = vox["voxel_offsets"][wl["batch"]:wl["batch"] + 1]
+    geo_conv_ms = timed(lambda: eng.launch(vox["voxel_features"], vox["voxel_coords"], wl["batch"], n0_dev=n0,
+                                           cap0=vox["cap"]))
+    F = frames[0].shape[1]
+    P = int(sum(f.shape[0] for f in frames))
+    vox_bytes = P * F * 4 + counts[0] * (16 + F * 4 + 4)
+    rb_bytes = 0
+    for bk in eng.books:  # N*16 + K*2*N*4 + K*4 (+ Nout*16), plus the output-major map K*Nout*4 this design adds
+        n_in, n_o = counts[bk.in_level], counts[bk.out_level]
+        rb_bytes += n_in * 16 + bk.kvol * 2 * n_in * 4 + bk.kvol * 4 + (0 if bk.subm else n_o * 16) + bk.kvol * n_o * 4
+    rb_ms = max(geo_conv_ms - conv_ms, 1e-3)
     launches = hp.engine.launch_count() + 8
     line = {
         "metric": METRIC, "value": round(value, 2), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
@@ -262,7 +291,11 @@ def run_ours(args, wl, rank, world, device):
         "gpu_launches": launches * args.steps,
         "clocks": clocks,
         "roofline": roof,
-        "stages": {"conv_ms_sum": round(conv_ms, 4), "step_ms_median": round(statistics.median(step_ms), 4),
+        "stages": {"voxelize_ms": round(vox_ms, 4), "voxelize_gbs": round(vox_bytes / vox_ms / 1e6, 1),
+                   "voxelize_frac_of_hbm": round(vox_bytes / vox_ms / 1e6 / pk["hbm_gbs"], 4),
+                   "rulebooks_ms": round(rb_ms, 4), "rulebooks_gbs": round(rb_bytes / rb_ms / 1e6, 1),
+                   "rulebooks_frac_of_hbm": round(rb_bytes / rb_ms / 1e6 / pk["hbm_gbs"], 4),
+                   "conv_ms_sum": round(conv_ms, 4), "step_ms_median": round(statistics.median(step_ms), 4),
                    "host_wall_ms_per_step": round(wall_s * 1000 / args.steps, 3),
                    "total_gflop": round(sum(r["flops"] for r in recs) / 1e9, 3),
                    "total_compulsory_mb": round(sum(r["bytes"] for r in recs) / 1e6, 2),

@@ -12,6 +12,7 @@ from .spconv_backbone import SparseBasicBlock, VoxelBackBone8x, VoxelResBackBone
 from .voxel_generator import BatchVoxelizer, VoxelGenerator
 from .engine import BackboneEngine
 from .pipeline import HotPath
+from . import sharding
 
 # name lookup tables like pcdet/models/backbones_3d/__init__.py:6-12 and vfe/__init__.py:5-9
 BACKBONES_3D = {'VoxelBackBone8x': VoxelBackBone8x, 'VoxelResBackBone8x': VoxelResBackBone8x}
