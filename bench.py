@@ -123,7 +123,7 @@ def layer_profile(hp, handle, flush):
     level_cap = [handle["vox"]["cap"]] + caps[1:]
     counts = a["counts"]
     for i, (st, p) in enumerate(zip(eng.steps, prm)):
-        nbr = a["books"][st.key]["nbr"]
+        nbr, perm = eng.conv_operands(a, st, p)
         pairs_total = int((nbr[:, :n[st.out_level]] >= 0).sum().item())
         src = handle["vox"]["voxel_features"] if st.in_buf < 0 else a["bufs"][st.in_buf]
         res = a["bufs"][st.res_buf] if st.res_buf is not None else None
@@ -134,7 +134,7 @@ def layer_profile(hp, handle, flush):
             flush()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            rc = lib.fv2p_conv_fwd(_lib.ptr(src), src.shape[0], _lib.ptr(w), _lib.ptr(nbr), nbr.shape[1], st.kvol,
+            rc = lib.fv2p_conv_fwd(_lib.ptr(src), src.shape[0], _lib.ptr(w), _lib.ptr(nbr), nbr.shape[1], _lib.ptr(perm), st.kvol,
                                    level_cap[st.out_level],
                                    _lib.ctypes.c_void_p(counts.data_ptr() + 4 * st.out_level), st.cin, st.cout,
                                    _lib.ptr(p["bias"]), _lib.ptr(p["scale"]), _lib.ptr(p["shift"]), _lib.ptr(res),

@@ -193,8 +193,9 @@ template <bool kTf32, int N>
 __global__ void __launch_bounds__((Cfg<kTf32, N>::kThreads), 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restrict__ feat_ptr,
                const uint8_t *__restrict__ wpacked,
-               const int *__restrict__ nbr, int64_t nbr_stride, int kvol, int64_t n_out_cap,
-               const int *__restrict__ n_out_dev, int cin, int oob_row, int use_tma_arg, Epilogue ep) {
+               const int *__restrict__ nbr, int64_t nbr_stride, const int *__restrict__ row_perm, int kvol,
+               int64_t n_out_cap, const int *__restrict__ n_out_dev, int cin, int oob_row, int use_tma_arg,
+               Epilogue ep) {
   using C = Cfg<kTf32, N>;
   constexpr int kElem = kTf32 ? 4 : 2;
   extern __shared__ uint8_t smem_raw[];
@@ -271,7 +272,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
     const int pre_r = tid & (kTileM - 1);
     const int pre_k0 = tid >> 7;
     auto prefetch = [&](int tile) {
-      const int row = tile * kTileM + pre_r;
+      const int row = tile * kTileM + pre_r;  // with a row order, `nbr` is the map permuted the same way
 #pragma unroll
       for (int q = 0; q < kNbrRegs; ++q) {
         const int k = pre_k0 + 2 * q;
@@ -439,7 +440,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
-      const int row = tile * kTileM + warp * 32 + lane;
+      // sorted position -> output row (identity without a row order from fv2p_sort_rows_by_mask)
+      const int srow = tile * kTileM + warp * 32 + lane;
+      const int row = srow < n_out ? (row_perm ? __ldg(&row_perm[srow]) : srow) : n_out;
       const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * N);
 #pragma unroll 1
       for (int c0 = 0; c0 < N; c0 += 16) {
@@ -608,7 +611,7 @@ int make_feature_map(CUtensorMap *map, const void *features, int64_t rows, int c
 
 template <bool kTf32, int N>
 int launch_one(const void *features, int64_t feat_rows, const void *weight, const int *nbr, int64_t nbr_stride,
-               int kvol, int64_t n_out_cap, const int *n_out_dev, int cin, const Epilogue &ep, cudaStream_t stream) {
+               const int *row_perm, int kvol, int64_t n_out_cap, const int *n_out_dev, int cin, const Epilogue &ep, cudaStream_t stream) {
   using C = Cfg<kTf32, N>;
   static bool configured = false;
   if (!configured) {
@@ -628,7 +631,7 @@ int launch_one(const void *features, int64_t feat_rows, const void *weight, cons
   int grid = (int)(tiles < sm_count() ? tiles : sm_count());
   if (grid < 1) grid = 1;
   conv_tc_kernel<kTf32, N><<<grid, C::kThreads, C::kSmemBytes, stream>>>(
-      map, features, static_cast<const uint8_t *>(weight), nbr, nbr_stride, kvol, n_out_cap, n_out_dev, cin,
+      map, features, static_cast<const uint8_t *>(weight), nbr, nbr_stride, row_perm, kvol, n_out_cap, n_out_dev, cin,
       (int)feat_rows, use_tma, ep);
   return cuda_status(cudaGetLastError(), "conv_fwd(tc)");
 }
@@ -636,7 +639,7 @@ int launch_one(const void *features, int64_t feat_rows, const void *weight, cons
 }  // namespace
 
 int launch_conv_tc(const void *features, int64_t feat_rows, const void *weight, const int *nbr, int64_t nbr_stride,
-                   int kvol, int64_t n_out_cap, const int *n_out_dev, int cin, int cout, const float *bias,
+                   const int *row_perm, int kvol, int64_t n_out_cap, const int *n_out_dev, int cin, int cout, const float *bias,
                    const float *scale, const float *shift, const void *residual, int relu, int mode, void *out,
                    cudaStream_t stream) {
   if (!tc_shape_ok(cin, cout)) {
@@ -651,10 +654,10 @@ int launch_conv_tc(const void *features, int64_t feat_rows, const void *weight, 
   Epilogue ep{bias, scale, shift, residual, out, relu};
   const bool tf32 = mode == FV2P_MODE_TF32X3_TC;
 #define FV2P_TC(NN)                                                                                            \
-  return tf32 ? launch_one<true, NN>(features, feat_rows, weight, nbr, nbr_stride, kvol, n_out_cap, n_out_dev, \
-                                     cin, ep, stream)                                                          \
-              : launch_one<false, NN>(features, feat_rows, weight, nbr, nbr_stride, kvol, n_out_cap, n_out_dev, \
-                                      cin, ep, stream)
+  return tf32 ? launch_one<true, NN>(features, feat_rows, weight, nbr, nbr_stride, row_perm, kvol, n_out_cap,  \
+                                     n_out_dev, cin, ep, stream)                                               \
+              : launch_one<false, NN>(features, feat_rows, weight, nbr, nbr_stride, row_perm, kvol, n_out_cap, \
+                                      n_out_dev, cin, ep, stream)
   switch (cout) {
     case 16: FV2P_TC(16);
     case 32: FV2P_TC(32);

@@ -142,7 +142,7 @@ class BackboneEngine(object):
     """Runs a traced backbone.  precision: 'fp32' (fp32 storage, fp32-accurate arithmetic) or 'bf16'
     (bf16 storage, fp32 accumulation; the entry layer reads fp32 voxel features)."""
 
-    def __init__(self, net, precision="fp32", materialize_pairs=True, use_tensor_cores=True):
+    def __init__(self, net, precision="fp32", materialize_pairs=True, use_tensor_cores=True, sort_rows=True):
         traced = trace_backbone(net)
         if traced is None:
             raise NotImplementedError("backbone layout not recognised by the fused engine")
@@ -151,6 +151,7 @@ class BackboneEngine(object):
         self.precision = precision
         self.materialize_pairs = materialize_pairs
         self.use_tensor_cores = use_tensor_cores
+        self.sort_rows = sort_rows  # mask-sorted row order for the tensor-core layers (same results, fewer stages)
         self.arena = None
         self._param_key = None
         self._params = None
@@ -229,6 +230,10 @@ class BackboneEngine(object):
                      pair_num=torch.zeros((bk.kvol,), dtype=torch.int32, device=device),
                      pairs=(torch.empty((bk.kvol, 2, cin_cap), dtype=torch.int32, device=device)
                             if self.materialize_pairs else None))
+            if self.sort_rows:
+                d["perm"] = torch.empty((cout_cap,), dtype=torch.int32, device=device)
+                d["nbr_sorted"] = torch.empty((bk.kvol, cout_cap), dtype=torch.int32, device=device)
+                ws_bytes = max(ws_bytes, lib.fv2p_sort_rows_workspace_bytes(cout_cap))
             books[bk.key] = d
             ws_bytes = max(ws_bytes, lib.fv2p_rulebook_workspace_bytes(cin_cap, cout_cap, bk.kvol))
         a["books"] = books
@@ -286,6 +291,8 @@ class BackboneEngine(object):
             level_cap = [cap0] + caps[1:]
             n_ptr = [_lib.ctypes.c_void_p(counts.data_ptr() + 4 * i) for i in range(len(caps))]
             status_ptr = _lib.ctypes.c_void_p(counts.data_ptr() + 4 * len(caps))
+            tc_modes = (_lib.MODE_BF16_TC, _lib.MODE_TF32X3_TC)
+            tc_books = {st_.key for st_, p in zip(self.steps, prm) if p["mode"] in tc_modes}
             for bk in self.books:
                 d = a["books"][bk.key]
                 pairs = d["pairs"]
@@ -310,18 +317,32 @@ class BackboneEngine(object):
                                                 _lib.ptr(d["nbr"]), d["nbr"].shape[1], status_ptr, _lib.ptr(a["ws"]),
                                                 a["ws"].numel(), stream)
                 _lib.check(st, "rulebook[%s]" % bk.key)
+                if self.sort_rows and bk.key in tc_books:
+                    st = lib.fv2p_sort_rows_by_mask(_lib.ptr(d["nbr"]), d["nbr"].shape[1], bk.kvol,
+                                                    level_cap[bk.out_level], n_ptr[bk.out_level], _lib.ptr(d["perm"]),
+                                                    _lib.ptr(d["nbr_sorted"]), d["nbr_sorted"].shape[1],
+                                                    _lib.ptr(a["ws"]), a["ws"].numel(), stream)
+                    _lib.check(st, "sort_rows[%s]" % bk.key)
             for st_, p in zip(self.steps, prm):
                 src = voxel_features if st_.in_buf < 0 else a["bufs"][st_.in_buf]
                 res = a["bufs"][st_.res_buf] if st_.res_buf is not None else None
                 out = a["bufs"][st_.out_buf]
-                nbr = a["books"][st_.key]["nbr"]
+                nbr, perm = self.conv_operands(a, st_, p)
                 w = p["packed"] if p["packed"] is not None else p["w"]
-                rc = lib.fv2p_conv_fwd(_lib.ptr(src), src.shape[0], _lib.ptr(w), _lib.ptr(nbr), nbr.shape[1], st_.kvol,
+                rc = lib.fv2p_conv_fwd(_lib.ptr(src), src.shape[0], _lib.ptr(w), _lib.ptr(nbr), nbr.shape[1],
+                                       _lib.ptr(perm), st_.kvol,
                                        level_cap[st_.out_level], n_ptr[st_.out_level], st_.cin, st_.cout,
                                        _lib.ptr(p["bias"]), _lib.ptr(p["scale"]), _lib.ptr(p["shift"]), _lib.ptr(res),
                                        int(st_.relu), p["mode"], _lib.ptr(out), stream)
                 _lib.check(rc, "conv_fwd[%s]" % st_.key)
         return a
+
+    def conv_operands(self, a, step, prm):
+        """(neighbour map, row order) a conv step reads: the mask-sorted pair for the tensor-core modes."""
+        d = a["books"][step.key]
+        if self.sort_rows and prm["mode"] in (_lib.MODE_BF16_TC, _lib.MODE_TF32X3_TC):
+            return d["nbr_sorted"], d["perm"]
+        return d["nbr"], None
 
     def collect(self, a, voxel_coords, batch_size, sync=True):
         """One D2H copy of the row counts, then correctly shaped views (valid until the next launch)."""
@@ -364,6 +385,8 @@ class BackboneEngine(object):
                 n += 5 if self.materialize_pairs else 3  # clear, insert, probe (+ scan, compact)
             else:
                 n += 9 if self.materialize_pairs else 7  # clear, insert, winners, scan, assign, fill, pairs (+2)
+            if self.sort_rows:
+                n += 2 + 3 * ((bk.kvol + 8) // 9)  # mask, 3 kernels per 9-bit radix pass, permute
         return n
 
     def __call__(self, voxel_features, voxel_coords, batch_size):

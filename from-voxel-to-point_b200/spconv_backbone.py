@@ -9,7 +9,8 @@ Two execution paths, same numbers:
 
 Extra, optional model_cfg keys (absent in the reference's YAML, defaults keep its behaviour):
   PRECISION: 'fp32' (default) | 'bf16';  FUSED: True;  MATERIALIZE_PAIRS: True (fill indice_dict with the
-  reference-layout pair tensors; the fused kernels themselves only need the neighbour map).
+  reference-layout pair tensors; the fused kernels themselves only need the neighbour map);  SORT_ROWS: True
+  (process output rows in neighbour-mask order inside the tensor-core kernels; results are unchanged).
 """
 from functools import partial
 
@@ -88,7 +89,8 @@ class _BackboneBase(nn.Module):
         eng = getattr(self, '_engine', None)
         if eng is None or eng.precision != precision:
             eng = BackboneEngine(self, precision=precision,
-                                 materialize_pairs=bool(self._cfg('MATERIALIZE_PAIRS', True)))
+                                 materialize_pairs=bool(self._cfg('MATERIALIZE_PAIRS', True)),
+                                 sort_rows=bool(self._cfg('SORT_ROWS', True)))
             object.__setattr__(self, '_engine', eng)  # not a submodule, never in the state_dict
         return eng
 

@@ -165,12 +165,25 @@ FV2P_API int fv2p_pairs_to_nbr(const int32_t *pairs, const int32_t *pair_num, in
  *             modes describe it to the TMA unit; every neighbour index must be < n_in_cap)
  *   weight    device: FV2P_MODE_F32 / *_SIMT: [K,cin,cout] fp32 (the reference layout, flattened);
  *             tensor-core modes: the packed image written by fv2p_pack_weight
+ *   row_perm  NULL, or the row order from fv2p_sort_rows_by_mask (tensor-core modes only): `nbr` is then the map
+ *             permuted the same way (nbr_sorted) and sorted position t writes output row row_perm[t]; results are
+ *             identical either way
  *   n_out_cap rows of `out`/`nbr` columns; live count *n_out_dev if given
  * ------------------------------------------------------------------------------------------- */
 FV2P_API int fv2p_conv_fwd(const void *features, int64_t n_in_cap, const void *weight, const int32_t *nbr, int64_t nbr_stride,
-                  int kvol, int64_t n_out_cap, const int32_t *n_out_dev, int cin, int cout,
+                  const int32_t *row_perm, int kvol, int64_t n_out_cap, const int32_t *n_out_dev, int cin, int cout,
                   const float *bias, const float *scale, const float *shift, const void *residual,
                   int relu, int mode, void *out, fv2p_stream_t stream);
+
+/* Row order for the tensor-core conv: stable sort of the output rows by their neighbour mask (bit k = offset k has
+ * a neighbour).  perm[t] = output row at sorted position t; nbr_sorted[k][t] = nbr[k][perm[t]] (optional).  Tiles
+ * cut from this order need about half the pipeline stages (rows of a tile share their active offsets); the conv
+ * result does not change.  No reference counterpart (spconv_ops.h:308-357 works on per-offset pair lists). */
+FV2P_API size_t fv2p_sort_rows_workspace_bytes(int64_t n_cap);
+FV2P_API int fv2p_sort_rows_by_mask(const int32_t *nbr, int64_t nbr_stride, int kvol, int64_t n_cap,
+                                    const int32_t *n_dev, int32_t *perm, int32_t *nbr_sorted,
+                                    int64_t sorted_stride, void *workspace, size_t workspace_bytes,
+                                    fv2p_stream_t stream);
 
 /* Producer of the gathered A tile in the tensor-core kernels: -1 = auto (default: measured best per shape),
  * 0 = LSU (swizzled cp.async), 1 = TMA (cp.async.bulk.tensor tile::gather4).  Same results either way; a tuning

@@ -37,7 +37,7 @@ eng, arena = hp.engine, h["arena"]
 prm = eng._prepare_params(dev)
 st, p = eng.steps[a.layer], prm[a.layer]
 caps = [h["vox"]["cap"]] + arena["caps"][1:]
-nbr = arena["books"][st.key]["nbr"]
+nbr, perm = eng.conv_operands(arena, st, p)
 src = h["vox"]["voxel_features"] if st.in_buf < 0 else arena["bufs"][st.in_buf]
 res = arena["bufs"][st.res_buf] if st.res_buf is not None else None
 out = arena["bufs"][st.out_buf]
@@ -45,7 +45,7 @@ w = p["packed"] if p["packed"] is not None else p["w"]
 flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
 for _ in range(a.repeat):
     flush.zero_()
-    rc = _lib.load().fv2p_conv_fwd(_lib.ptr(src), src.shape[0], _lib.ptr(w), _lib.ptr(nbr), nbr.shape[1], st.kvol, caps[st.out_level],
+    rc = _lib.load().fv2p_conv_fwd(_lib.ptr(src), src.shape[0], _lib.ptr(w), _lib.ptr(nbr), nbr.shape[1], _lib.ptr(perm), st.kvol, caps[st.out_level],
                                    _lib.ctypes.c_void_p(arena["counts"].data_ptr() + 4 * st.out_level), st.cin,
                                    st.cout, _lib.ptr(p["bias"]), _lib.ptr(p["scale"]), _lib.ptr(p["shift"]),
                                    _lib.ptr(res), int(st.relu), p["mode"], _lib.ptr(out), _lib.stream_ptr(dev))
@@ -60,7 +60,7 @@ for mode in a.debug:
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        lib.fv2p_conv_fwd(_lib.ptr(src), src.shape[0], _lib.ptr(w), _lib.ptr(nbr), nbr.shape[1], st.kvol, caps[st.out_level],
+        lib.fv2p_conv_fwd(_lib.ptr(src), src.shape[0], _lib.ptr(w), _lib.ptr(nbr), nbr.shape[1], _lib.ptr(perm), st.kvol, caps[st.out_level],
                           _lib.ctypes.c_void_p(arena["counts"].data_ptr() + 4 * st.out_level), st.cin, st.cout,
                           _lib.ptr(p["bias"]), _lib.ptr(p["scale"]), _lib.ptr(p["shift"]), _lib.ptr(res), int(st.relu),
                           p["mode"], _lib.ptr(out), _lib.stream_ptr(dev))
@@ -71,7 +71,7 @@ for mode in a.debug:
     if mode == 8:
         buf = (ctypes.c_longlong * 64)()
         lib.fv2p_debug_prof(buf, 1)
-        lib.fv2p_conv_fwd(_lib.ptr(src), src.shape[0], _lib.ptr(w), _lib.ptr(nbr), nbr.shape[1], st.kvol, caps[st.out_level],
+        lib.fv2p_conv_fwd(_lib.ptr(src), src.shape[0], _lib.ptr(w), _lib.ptr(nbr), nbr.shape[1], _lib.ptr(perm), st.kvol, caps[st.out_level],
                           _lib.ctypes.c_void_p(arena["counts"].data_ptr() + 4 * st.out_level), st.cin, st.cout,
                           _lib.ptr(p["bias"]), _lib.ptr(p["scale"]), _lib.ptr(p["shift"]), _lib.ptr(res), int(st.relu),
                           p["mode"], _lib.ptr(out), _lib.stream_ptr(dev))

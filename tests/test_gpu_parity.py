@@ -404,3 +404,33 @@ def test_dense_matches_reference_scatter():
     x = spconv.SparseConvTensor(feats, cuda(ind), [5, 12, 11], 3)
     ref = spconv.scatter_nd(x.indices.long(), feats, [3, 5, 12, 11, 16]).permute(0, 4, 1, 2, 3).contiguous()
     assert torch.equal(x.dense(), ref)
+
+
+def test_mask_sorted_row_order_gives_identical_results():
+    """fv2p_sort_rows_by_mask only changes which rows share a tile: the conv output must be bit-identical, the
+    order a stable ascending sort of the neighbour masks."""
+    rng = np.random.default_rng(3)
+    shape = [9, 40, 40]
+    ind = synth.random_voxels(shape, 3000, 2, seed=5)
+    ind[:, 1:] = ind[:, 1:] // np.array([2, 3, 3])
+    ind = np.unique(ind, axis=0).astype(np.int32)
+    for subm, st in ((True, 1), (False, 2)):
+        outids, pairs, num, nbr = spconv.ops.get_indice_pairs(cuda(ind), 2, shape, 3, st, 1, 1, 0, subm, False,
+                                                              return_nbr=True)
+        nbr = nbr.contiguous()
+        n_out = outids.shape[0]
+        perm, nbr_sorted = spconv.ops.sort_rows_by_mask(nbr, n_out)
+        m = nbr.cpu().numpy()
+        masks = ((m >= 0).astype(np.int64) << np.arange(27)[:, None]).sum(0)
+        expect = np.argsort(masks, kind="stable")
+        assert np.array_equal(perm.cpu().numpy(), expect)
+        assert np.array_equal(nbr_sorted.cpu().numpy(), m[:, expect])
+        for mode, dt in ((_lib.MODE_TF32X3_TC, torch.float32), (_lib.MODE_BF16_TC, torch.bfloat16)):
+            feats = cuda(rng.standard_normal((ind.shape[0], 64)).astype(np.float32), dt)
+            w = cuda((rng.standard_normal((27, 64, 64)) / 40).astype(np.float32))
+            packed = spconv.ops.pack_weight(w, mode)
+            res = cuda(rng.standard_normal((n_out, 64)).astype(np.float32), dt)
+            a = spconv.ops.conv_forward(feats, packed, nbr, n_out, residual=res, relu=True, mode=mode)
+            b = spconv.ops.conv_forward(feats, packed, nbr_sorted.contiguous(), n_out, residual=res, relu=True,
+                                        mode=mode, row_perm=perm.contiguous())
+            assert torch.equal(a, b)
