@@ -142,7 +142,8 @@ class BackboneEngine(object):
     """Runs a traced backbone.  precision: 'fp32' (fp32 storage, fp32-accurate arithmetic) or 'bf16'
     (bf16 storage, fp32 accumulation; the entry layer reads fp32 voxel features)."""
 
-    def __init__(self, net, precision="fp32", materialize_pairs=True, use_tensor_cores=True, sort_rows=True):
+    def __init__(self, net, precision="fp32", materialize_pairs=True, use_tensor_cores=True, sort_rows=True,
+                 concurrent=True):
         traced = trace_backbone(net)
         if traced is None:
             raise NotImplementedError("backbone layout not recognised by the fused engine")
@@ -152,6 +153,8 @@ class BackboneEngine(object):
         self.materialize_pairs = materialize_pairs
         self.use_tensor_cores = use_tensor_cores
         self.sort_rows = sort_rows  # mask-sorted row order for the tensor-core layers (same results, fewer stages)
+        self.concurrent = concurrent  # geometry and feature pass on forked streams (joined before launch returns)
+        self._side = None
         self.arena = None
         self._param_key = None
         self._params = None
@@ -237,7 +240,8 @@ class BackboneEngine(object):
             books[bk.key] = d
             ws_bytes = max(ws_bytes, lib.fv2p_rulebook_workspace_bytes(cin_cap, cout_cap, bk.kvol))
         a["books"] = books
-        a["ws"] = torch.empty(ws_bytes + 1024, dtype=torch.uint8, device=device)
+        a["ws"] = torch.empty(ws_bytes + 1024, dtype=torch.uint8, device=device)       # strided chain
+        a["ws_sub"] = torch.empty(ws_bytes + 1024, dtype=torch.uint8, device=device)   # submanifold books + sorts
         # feature buffers with liveness-based reuse
         bufs, free, owner = {}, [], {}
         for i, st in enumerate(self.steps):
@@ -277,10 +281,16 @@ class BackboneEngine(object):
         a = self._ensure_arena(device, max(cap0, 1), int(batch_size))
         prm = self._prepare_params(device)
         lib = _lib.load()
-        stream = _lib.stream_ptr(device)
         counts = a["counts"]
         caps = a["caps"]
         with torch.cuda.device(dev):
+            main = torch.cuda.current_stream(device)
+            if self.concurrent:
+                if self._side is None or self._side[0].device != device:
+                    self._side = (torch.cuda.Stream(device=device), torch.cuda.Stream(device=device))
+                s_sub, s_conv = self._side
+            else:
+                s_sub = s_conv = main
             counts[len(caps):].zero_()
             if n0_dev is None:
                 counts[0:1].fill_(cap0)
@@ -293,48 +303,78 @@ class BackboneEngine(object):
             status_ptr = _lib.ctypes.c_void_p(counts.data_ptr() + 4 * len(caps))
             tc_modes = (_lib.MODE_BF16_TC, _lib.MODE_TF32X3_TC)
             tc_books = {st_.key for st_, p in zip(self.steps, prm) if p["mode"] in tc_modes}
+
+            # Three dependency chains, forked from and joined back into the caller's stream (so the whole thing is
+            # still one stream-ordered step, and one CUDA graph when captured):
+            #   main   the strided rulebooks, level by level (each needs the previous level's output coordinates)
+            #   s_sub  the submanifold rulebooks and every mask sort (leaves of that chain)
+            #   s_conv the feature pass, each layer waiting only for its own rulebook
+            # The geometry kernels are small and latency bound, so they hide behind the conv kernels.
+            def mark(stream):
+                ev = torch.cuda.Event()
+                ev.record(stream)
+                return ev
+
+            level_ready = {0: mark(main)}
+            book_ready = {}
             for bk in self.books:
                 d = a["books"][bk.key]
                 pairs = d["pairs"]
                 if bk.subm:
-                    st = lib.fv2p_rulebook_subm(_lib.ptr(level_ind[bk.in_level]), level_cap[bk.in_level],
-                                                n_ptr[bk.in_level], int(batch_size),
-                                                _lib.i32x3(self.level_shapes[bk.in_level]), _lib.i32x3(bk.ksize),
-                                                _lib.i32x3(bk.dil), _lib.ptr(pairs),
-                                                pairs.shape[2] if pairs is not None else 0,
-                                                _lib.ptr(d["pair_num"]) if pairs is not None else None,
-                                                _lib.ptr(d["nbr"]), d["nbr"].shape[1], _lib.ptr(a["ws"]),
-                                                a["ws"].numel(), stream)
+                    s_sub.wait_event(level_ready[bk.in_level])
+                    with torch.cuda.stream(s_sub):
+                        st = lib.fv2p_rulebook_subm(_lib.ptr(level_ind[bk.in_level]), level_cap[bk.in_level],
+                                                    n_ptr[bk.in_level], int(batch_size),
+                                                    _lib.i32x3(self.level_shapes[bk.in_level]), _lib.i32x3(bk.ksize),
+                                                    _lib.i32x3(bk.dil), _lib.ptr(pairs),
+                                                    pairs.shape[2] if pairs is not None else 0,
+                                                    _lib.ptr(d["pair_num"]) if pairs is not None else None,
+                                                    _lib.ptr(d["nbr"]), d["nbr"].shape[1], _lib.ptr(a["ws_sub"]),
+                                                    a["ws_sub"].numel(), _lib.stream_ptr(device))
                 else:
-                    st = lib.fv2p_rulebook_conv(_lib.ptr(level_ind[bk.in_level]), level_cap[bk.in_level],
-                                                n_ptr[bk.in_level], int(batch_size),
-                                                _lib.i32x3(self.level_shapes[bk.out_level]), _lib.i32x3(bk.ksize),
-                                                _lib.i32x3(bk.stride), _lib.i32x3(bk.pad), _lib.i32x3(bk.dil),
-                                                _lib.ptr(level_ind[bk.out_level]), level_cap[bk.out_level],
-                                                n_ptr[bk.out_level], _lib.ptr(pairs),
-                                                pairs.shape[2] if pairs is not None else 0,
-                                                _lib.ptr(d["pair_num"]) if pairs is not None else None,
-                                                _lib.ptr(d["nbr"]), d["nbr"].shape[1], status_ptr, _lib.ptr(a["ws"]),
-                                                a["ws"].numel(), stream)
+                    with torch.cuda.stream(main):
+                        st = lib.fv2p_rulebook_conv(_lib.ptr(level_ind[bk.in_level]), level_cap[bk.in_level],
+                                                    n_ptr[bk.in_level], int(batch_size),
+                                                    _lib.i32x3(self.level_shapes[bk.out_level]),
+                                                    _lib.i32x3(bk.ksize), _lib.i32x3(bk.stride), _lib.i32x3(bk.pad),
+                                                    _lib.i32x3(bk.dil), _lib.ptr(level_ind[bk.out_level]),
+                                                    level_cap[bk.out_level], n_ptr[bk.out_level], _lib.ptr(pairs),
+                                                    pairs.shape[2] if pairs is not None else 0,
+                                                    _lib.ptr(d["pair_num"]) if pairs is not None else None,
+                                                    _lib.ptr(d["nbr"]), d["nbr"].shape[1], status_ptr,
+                                                    _lib.ptr(a["ws"]), a["ws"].numel(), _lib.stream_ptr(device))
+                    level_ready[bk.out_level] = mark(main)
+                    s_sub.wait_event(level_ready[bk.out_level])
                 _lib.check(st, "rulebook[%s]" % bk.key)
                 if self.sort_rows and bk.key in tc_books:
-                    st = lib.fv2p_sort_rows_by_mask(_lib.ptr(d["nbr"]), d["nbr"].shape[1], bk.kvol,
-                                                    level_cap[bk.out_level], n_ptr[bk.out_level], _lib.ptr(d["perm"]),
-                                                    _lib.ptr(d["nbr_sorted"]), d["nbr_sorted"].shape[1],
-                                                    _lib.ptr(a["ws"]), a["ws"].numel(), stream)
+                    with torch.cuda.stream(s_sub):
+                        st = lib.fv2p_sort_rows_by_mask(_lib.ptr(d["nbr"]), d["nbr"].shape[1], bk.kvol,
+                                                        level_cap[bk.out_level], n_ptr[bk.out_level],
+                                                        _lib.ptr(d["perm"]), _lib.ptr(d["nbr_sorted"]),
+                                                        d["nbr_sorted"].shape[1], _lib.ptr(a["ws_sub"]),
+                                                        a["ws_sub"].numel(), _lib.stream_ptr(device))
                     _lib.check(st, "sort_rows[%s]" % bk.key)
+                book_ready[bk.key] = mark(s_sub)
+            waited = set()
             for st_, p in zip(self.steps, prm):
+                if st_.key not in waited:
+                    s_conv.wait_event(book_ready[st_.key])
+                    waited.add(st_.key)
                 src = voxel_features if st_.in_buf < 0 else a["bufs"][st_.in_buf]
                 res = a["bufs"][st_.res_buf] if st_.res_buf is not None else None
                 out = a["bufs"][st_.out_buf]
                 nbr, perm = self.conv_operands(a, st_, p)
                 w = p["packed"] if p["packed"] is not None else p["w"]
-                rc = lib.fv2p_conv_fwd(_lib.ptr(src), src.shape[0], _lib.ptr(w), _lib.ptr(nbr), nbr.shape[1],
-                                       _lib.ptr(perm), st_.kvol,
-                                       level_cap[st_.out_level], n_ptr[st_.out_level], st_.cin, st_.cout,
-                                       _lib.ptr(p["bias"]), _lib.ptr(p["scale"]), _lib.ptr(p["shift"]), _lib.ptr(res),
-                                       int(st_.relu), p["mode"], _lib.ptr(out), stream)
+                with torch.cuda.stream(s_conv):
+                    rc = lib.fv2p_conv_fwd(_lib.ptr(src), src.shape[0], _lib.ptr(w), _lib.ptr(nbr), nbr.shape[1],
+                                           _lib.ptr(perm), st_.kvol, level_cap[st_.out_level], n_ptr[st_.out_level],
+                                           st_.cin, st_.cout, _lib.ptr(p["bias"]), _lib.ptr(p["scale"]),
+                                           _lib.ptr(p["shift"]), _lib.ptr(res), int(st_.relu), p["mode"],
+                                           _lib.ptr(out), _lib.stream_ptr(device))
                 _lib.check(rc, "conv_fwd[%s]" % st_.key)
+            if self.concurrent:  # join: everything this step enqueued is ordered before what the caller does next
+                main.wait_event(mark(s_sub))
+                main.wait_event(mark(s_conv))
         return a
 
     def conv_operands(self, a, step, prm):
