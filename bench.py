@@ -159,6 +159,7 @@ def run_ours(args, wl, rank, world, device):
     import torch.distributed as dist
     from fv2p_b200 import _lib
     precision = args.precision
+    _lib.load().fv2p_tc_gather_mode({"auto": -1, "lsu": 0, "tma": 1, "regs": 2}[args.gather])
     sampler = ClockSampler(torch.cuda.current_device() if device.index is None else device.index)
     sampler.start()  # nvidia-smi takes a second to start streaming; rows are filtered to the timed region later
     net, hp, state, cfg = build_model(wl, device, precision, use_graph=not args.no_graph)
@@ -200,17 +201,26 @@ def run_ours(args, wl, rank, world, device):
     counts = info["counts"]
     total_ms = sum(step_ms)
 
-    # ---- end to end through the public API with host buffers (H2D + D2H inside the timed region)
-    for _ in range(max(1, args.warmup // 2)):
-        hp(frames, device, fetch="encoded")
+    # ---- end to end through the public API with host buffers (H2D + D2H inside the timed region):
+    # HotPath.run_stream = the pipelined form of HotPath(frames, fetch="encoded"): per step one pinned H2D of the
+    # points, one graph replay, D2H of the row counts + stride-8 features and indices; copies of step i overlap
+    # the kernels of step i+1 (double buffered).  Every step is synchronised on the host when its result lands.
+    for _ in hp.run_stream((frames for _ in range(max(2, args.warmup))), device):
+        pass
     barrier()
     t0 = time.perf_counter()
     d2h_bytes = 0
-    for _ in range(args.steps):
-        _, einfo = hp(frames, device, fetch="encoded")
-        d2h_bytes = einfo["d2h_bytes"]
+    for res in hp.run_stream((frames for _ in range(args.steps)), device):
+        d2h_bytes = res["d2h_bytes"]
+        assert res["encoded_features"].shape[0] == res["counts"][-1]
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    # the unpipelined call, for reference (one step fully serialised: upload -> kernels -> download)
+    t1 = time.perf_counter()
+    for _ in range(max(3, args.steps // 5)):
+        hp(frames, device, fetch="encoded")
+    torch.cuda.synchronize()
+    e2e_serial_ms = (time.perf_counter() - t1) * 1000.0 / max(3, args.steps // 5)
     clocks = sampler.stop(t_wall0, time.perf_counter())
 
     # ---- reduce over ranks (MAX of elapsed)
@@ -287,7 +297,8 @@ def run_ours(args, wl, rank, world, device):
                    "parallelism": "frames sharded per GPU, no collective on the data path",
                    "rows_per_level": counts, "points_per_step": int(sum(f.shape[0] for f in frames))},
         "e2e": {"value": round(e2e_value, 2), "unit": "frames/s", "h2d_bytes_per_step": int(h2d_bytes),
-                "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": round(e2e_ms / args.steps, 4)},
+                "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": round(e2e_ms / args.steps, 4),
+                "api": "HotPath.run_stream (double-buffered copies)", "serial_call_ms": round(e2e_serial_ms, 4)},
         "gpu_launches": launches * args.steps,
         "clocks": clocks,
         "roofline": roof,
@@ -383,12 +394,14 @@ def run_reference(args, wl, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="kitti_b8", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="auto", choices=["auto", "lsu", "tma", "regs"],
+                    help="A-tile producer of the tensor-core conv (fv2p_tc_gather_mode); auto = measured best per shape")
     ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

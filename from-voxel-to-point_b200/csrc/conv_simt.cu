@@ -226,6 +226,17 @@ __global__ void __launch_bounds__(kThreads) cast_bf16_f32_kernel(const __nv_bflo
     dst[i] = __bfloat162float(src[i]);
 }
 
+// Copies the live rows of a capacity-sized buffer (row_bytes multiple of 16), count read on the device.
+__global__ void __launch_bounds__(kThreads)
+copy_rows_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dst, int vec_per_row, int64_t n_cap,
+                 const int *n_dev) {
+  int n = n_dev ? *n_dev : (int)n_cap;
+  if (n > n_cap) n = (int)n_cap;
+  const int64_t total = (int64_t)n * vec_per_row;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x)
+    dst[e] = src[e];
+}
+
 // SparseConvTensor.dense(): out[b][c][z][y][x] = features[row][c]
 __global__ void __launch_bounds__(kThreads)
 dense_ncdhw_kernel(const float *__restrict__ features, const int4 *__restrict__ indices, int64_t n_cap,
@@ -323,6 +334,17 @@ extern "C" int fv2p_dense_ncdhw(const float *features, const int32_t *indices, i
                                                                 n_cap, n_dev, channels, shape3[0], shape3[1],
                                                                 shape3[2], dense);
   FV2P_LAUNCH_CHECK("dense");
+  return FV2P_OK;
+}
+
+extern "C" int fv2p_copy_rows(const void *src, void *dst, int64_t row_bytes, int64_t n_cap, const int32_t *n_dev,
+                              fv2p_stream_t stream_) {
+  FV2P_REQUIRE(row_bytes > 0 && row_bytes % 16 == 0 && n_cap >= 0, "copy_rows: row_bytes must be a multiple of 16");
+  if (n_cap == 0) return FV2P_OK;
+  FV2P_REQUIRE(src && dst, "copy_rows: null pointer argument");
+  copy_rows_kernel<<<persistent_grid(), kThreads, 0, static_cast<cudaStream_t>(stream_)>>>(
+      static_cast<const uint4 *>(src), static_cast<uint4 *>(dst), (int)(row_bytes / 16), n_cap, n_dev);
+  FV2P_LAUNCH_CHECK("copy_rows");
   return FV2P_OK;
 }
 

@@ -165,7 +165,8 @@ __host__ __device__ constexpr uint32_t instr_desc(int n, bool tf32) {
 
 // Timing experiments only (profiles/run_layer.py --debug): 4 = no MMA, 6 = no epilogue body.  0 in production.
 __device__ int g_tc_debug = 0;
-// Host-side choice of the A-tile producer: -1 = auto (measured best per shape), 0 = LSU (cp.async), 1 = TMA gather4.
+// Host-side choice of the A-tile producer: -1 = auto (measured best per shape), 0 = LSU (cp.async), 1 = TMA gather4,
+// 2 = fp32 only: LDG + hi/lo split in registers + STS (bf16 kernels treat 2 as 0).
 int g_tc_gather_mode = -1;
 
 template <bool kTf32, int N>
@@ -213,7 +214,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int dbg = g_tc_debug;
-  const bool use_tma = use_tma_arg != 0;
+  const bool use_tma = use_tma_arg == 1;
+  const bool split_regs = kTf32 && use_tma_arg == 2;  // fp32: LDG -> hi/lo split in registers -> STS (no transform warps)
   int n_out = n_out_dev ? *n_out_dev : (int)n_out_cap;
   if (n_out > n_out_cap) n_out = (int)n_out_cap;
   const int n_tiles = (n_out + kTileM - 1) / kTileM;
@@ -229,7 +231,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
       // LSU gather: + the 32 cp.async arrivals of the owning warp (the fp32 `landed` barrier also gets one plain
       // arrive that publishes the stage flags).
       const uint32_t a_arrivals = use_tma ? 1u : 33u;
-      mbar_init(bar_full + 8 * s, kTf32 ? kXformThreads + 1 : a_arrivals);
+      // fp32 register-split producer (mode 2): the two warps that own the slot + the weight copy's expect_tx
+      mbar_init(bar_full + 8 * s, split_regs ? 3u : (kTf32 ? kXformThreads + 1 : a_arrivals));
       mbar_init(bar_empty + 8 * s, 1);
       mbar_init(bar_landed + 8 * s, a_arrivals);
     }
@@ -311,24 +314,72 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
           // in program order (the parity wait cannot alias, whatever the drift between warps); warps without a
           // slot of their own (ring shorter than the warp count) only help with the neighbour prefetch.
           const uint32_t s = issued % C::kStages;
-          if ((int)(s % kProdWarps) != pwarp) continue;
+          if (split_regs ? (int)(s % (kProdWarps / 2)) != (pwarp >> 1) : (int)(s % kProdWarps) != pwarp) continue;
           mbar_wait(bar_empty + 8 * s, ((issued / C::kStages) & 1) ^ 1);
           const uint32_t a_u32 = smem_u32(stage_base + (size_t)s * C::kStageBytes);
           const uint32_t a_bar = kTf32 ? bar_landed + 8 * s : bar_full + 8 * s;
+          if constexpr (kTf32) {
+            if (split_regs) {
+              // Two warps per stage (64 rows each).  Eight 16-byte loads are put in flight per lane, then each is
+              // split into hi = rn_tf32(x) / lo = rn_tf32(x - hi) and stored to the two swizzled tiles.  A
+              // missing neighbour stores zeros without touching global memory.
+              if ((pwarp & 1) == 0 && lane == 0) {
+                stage_flags[s] = ((k == (int)first_k && sl == 0) ? 1 : 0) | ((k == (int)last_k && sl == slices - 1) ? 2 : 0);
+                const uint32_t wb = w_stage_bytes * 2;
+                mbar_arrive_expect_tx(bar_full + 8 * s, wb);
+                bulk_g2s(a_u32 + 2 * C::kABytes, wpacked + ((size_t)k * slices + sl) * wb, wb, bar_full + 8 * s);
+              }
+              uint8_t *a_hi = stage_base + (size_t)s * C::kStageBytes;
+              uint8_t *a_lo = a_hi + C::kABytes;
+              const size_t col_off = (size_t)sl * row_bytes + my_chunk * 16;
+              const int *rows_k = nbr_s + k * kTileM;
+              const int r_begin = (pwarp & 1) * (kTileM / 2) + my_row0, r_end = (pwarp & 1) * (kTileM / 2) + kTileM / 2;
+              for (int r0 = r_begin; r0 < r_end; r0 += 8 * rows_per_instr) {
+                float4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                  const int r = r0 + u * rows_per_instr;
+                  const int src = r < r_end ? rows_k[r] : -1;
+                  v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                  if (src >= 0)
+                    v[u] = __ldg(reinterpret_cast<const float4 *>(feat + (size_t)src * feat_row_bytes + col_off));
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                  const int r = r0 + u * rows_per_instr;
+                  if (r < r_end) {
+                    const uint32_t off = (uint32_t)r * row_bytes +
+                                         ((uint32_t)(my_chunk ^ ((r >> (3 - cshift)) & (chunks - 1))) << 4);
+                    float4 h, l;
+                    h.x = tf32_rn(v[u].x), h.y = tf32_rn(v[u].y), h.z = tf32_rn(v[u].z), h.w = tf32_rn(v[u].w);
+                    l.x = tf32_rn(v[u].x - h.x), l.y = tf32_rn(v[u].y - h.y), l.z = tf32_rn(v[u].z - h.z);
+                    l.w = tf32_rn(v[u].w - h.w);
+                    *reinterpret_cast<float4 *>(a_hi + off) = h;
+                    *reinterpret_cast<float4 *>(a_lo + off) = l;
+                  }
+                }
+              }
+              fence_proxy_async();  // every lane publishes its own generic-proxy stores to the tensor core
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bar_full + 8 * s);
+              continue;
+            }
+          }
           if (lane == 0) {
             stage_flags[s] = ((k == (int)first_k && sl == 0) ? 1 : 0) | ((k == (int)last_k && sl == slices - 1) ? 2 : 0);
             const uint32_t wb = w_stage_bytes * (kTf32 ? 2 : 1);
             const uint8_t *wsrc = wpacked + ((size_t)k * slices + sl) * wb;
             const uint32_t w_u32 = a_u32 + (kTf32 ? 2 : 1) * C::kABytes;
             const uint32_t a_tx = use_tma ? a_stage_bytes : 0u;
+            const uint32_t wtx = dbg == 3 ? 0u : wb;  // dbg 3: no weight copy
             if constexpr (kTf32) {
               if (use_tma) mbar_arrive_expect_tx(bar_landed + 8 * s, a_tx);
               else mbar_arrive(bar_landed + 8 * s);
-              mbar_arrive_expect_tx(bar_full + 8 * s, wb);
+              mbar_arrive_expect_tx(bar_full + 8 * s, wtx);
             } else {
-              mbar_arrive_expect_tx(bar_full + 8 * s, a_tx + wb);
+              mbar_arrive_expect_tx(bar_full + 8 * s, a_tx + wtx);
             }
-            bulk_g2s(w_u32, wsrc, wb, bar_full + 8 * s);
+            if (dbg != 3) bulk_g2s(w_u32, wsrc, wb, bar_full + 8 * s);
           }
           __syncwarp();
           if (use_tma) {
@@ -625,12 +676,15 @@ int launch_one(const void *features, int64_t feat_rows, const void *weight, cons
   int st = make_feature_map(&map, features, feat_rows, cin, kTf32);
   if (st) return st;
   // Measured on B200 (profiles/r1_notes.md): the TMA gather wins for fp32 rows of 128 bytes and more (the LSU
-  // path also has to feed the transform warps there), the swizzled cp.async gather everywhere else.
-  const int use_tma = g_tc_gather_mode >= 0 ? g_tc_gather_mode : ((kTf32 && cin >= 32) ? 1 : 0);
+  // path also has to feed the transform warps there), the swizzled cp.async gather everywhere else; the
+  // register-split producer (mode 2) never won (0.182 vs 0.172 ms on 64->64, 0.248 vs 0.221 ms on 128->128).
+  const int use_tma = g_tc_gather_mode >= 0 ? ((g_tc_gather_mode == 2 && !kTf32) ? 0 : g_tc_gather_mode)
+                                            : ((kTf32 && cin >= 32) ? 1 : 0);
   int64_t tiles = (n_out_cap + kTileM - 1) / kTileM;
   int grid = (int)(tiles < sm_count() ? tiles : sm_count());
   if (grid < 1) grid = 1;
-  conv_tc_kernel<kTf32, N><<<grid, C::kThreads, C::kSmemBytes, stream>>>(
+  const int block = (kTf32 && use_tma == 2) ? kTcThreadsBase : C::kThreads;  // no transform warps in mode 2
+  conv_tc_kernel<kTf32, N><<<grid, block, C::kSmemBytes, stream>>>(
       map, features, static_cast<const uint8_t *>(weight), nbr, nbr_stride, row_perm, kvol, n_out_cap, n_out_dev, cin,
       (int)feat_rows, use_tma, ep);
   return cuda_status(cudaGetLastError(), "conv_fwd(tc)");
@@ -672,7 +726,7 @@ int launch_conv_tc(const void *features, int64_t feat_rows, const void *weight, 
 using namespace fv2p;
 
 extern "C" int fv2p_tc_gather_mode(int mode) {
-  g_tc_gather_mode = mode < 0 ? -1 : (mode ? 1 : 0);
+  g_tc_gather_mode = mode < 0 ? -1 : (mode > 2 ? 2 : mode);
   return FV2P_OK;
 }
 

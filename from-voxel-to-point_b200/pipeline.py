@@ -5,10 +5,11 @@ numba voxelizer, collate_batch, load_data_to_gpu, MeanVFE.forward and the backbo
 pcdet/datasets/dataset.py:137-183, pcdet/models/__init__.py:15-21, detectors/detector3d_template.py:22-25).
 
     hp = HotPath(backbone, voxel_size, point_cloud_range, max_points_per_voxel, max_voxels)
-    result = hp(list_of_host_point_arrays)      # H2D of the points, all kernels, D2H of counts (+ features)
+    batch_dict, info = hp(list_of_host_point_arrays)    # H2D of the points, all kernels, D2H of counts (+ features)
+    for result in hp.run_stream(iterable_of_batches):   # same, pipelined: copies of batch i overlap batch i+1
 
-`launch_resident` / `finish` split the same step for callers that keep the points in HBM and for the
-benchmark.  Between the H2D copy and the final D2H copy nothing synchronises with the host.
+`upload` / `launch_resident` / `launch_graph` / `finish` split the step for callers that keep the points in HBM
+and for the benchmark.  Between the H2D copy and the final D2H copy nothing synchronises with the host.
 """
 import numpy as np
 import torch
@@ -29,32 +30,42 @@ class HotPath(object):
         self.engine = backbone.get_engine()
         self.voxelizer = BatchVoxelizer(voxel_size, point_cloud_range, max_points_per_voxel, max_voxels)
         self.use_graph = use_graph
-        self._stage = None
+        self._slots = {}
         self._graphs = {}
+        self._copy_stream = None
+        self._enc_host = None
 
     # ------------------------------------------------------------------ host -> device
-    def _staging(self, device, total_points, batch, f):
-        s = self._stage
+    def _slot(self, device, total_points, batch, f, index=0):
+        """Staging slot `index`: pinned host + device buffers for the points of one batch (grow-only)."""
+        s = self._slots.get(index)
         if s is None or s["pcap"] < total_points or s["batch"] != batch or s["f"] != f or s["device"] != device:
-            pcap = int(total_points * 1.1) + 1024
-            s = dict(pcap=pcap, batch=batch, f=f, device=device,
+            # all slots share one capacity so that they share the voxelizer / arena sizing (and graph shapes)
+            pcap = max([int(total_points * 1.1) + 1024] + [x["pcap"] for k, x in self._slots.items()
+                                                           if isinstance(k, int) and x["batch"] == batch and x["f"] == f])
+            s = dict(pcap=pcap, batch=batch, f=f, device=device, index=index,
                      host_pts=torch.empty((pcap, f), dtype=torch.float32).pin_memory(),
                      host_off=torch.zeros((batch + 1,), dtype=torch.int32).pin_memory(),
                      dev_pts=torch.empty((pcap, f), dtype=torch.float32, device=device),
                      dev_off=torch.zeros((batch + 1,), dtype=torch.int32, device=device))
-            self._stage = s
+            self._slots[index] = s
         return s
 
-    def upload(self, frames, device="cuda"):
+    @property
+    def _stage(self):
+        return self._slots.get(0)
+
+    def upload(self, frames, device="cuda", slot=0, stream=None):
         """frames: list of [P_b,F] float32 numpy arrays (or CPU tensors).  Packs them into pinned memory and
-        enqueues the H2D copies.  Returns (points_dev [P,F], frame_offsets_dev [B+1], max_frame_points, bytes)."""
+        enqueues the H2D copies (on `stream` if given).  Returns (points_dev [P,F], frame_offsets_dev [B+1],
+        max_frame_points, bytes)."""
         device = torch.device(device)
         if device.index is None:
             device = torch.device("cuda", torch.cuda.current_device())
         sizes = [int(fr.shape[0]) for fr in frames]
         f = int(frames[0].shape[1])
         total = int(sum(sizes))
-        s = self._staging(device, total, len(frames), f)
+        s = self._slot(device, total, len(frames), f, slot)
         off = 0
         hp = s["host_pts"].numpy()
         for fr in frames:
@@ -64,8 +75,10 @@ class HotPath(object):
             hp[off:off + arr.shape[0]] = arr
             off += arr.shape[0]
         s["host_off"].numpy()[:] = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
-        s["dev_pts"][:total].copy_(s["host_pts"][:total], non_blocking=True)
-        s["dev_off"].copy_(s["host_off"], non_blocking=True)
+        ctx = torch.cuda.stream(stream) if stream is not None else _NullCtx()
+        with ctx:
+            s["dev_pts"][:total].copy_(s["host_pts"][:total], non_blocking=True)
+            s["dev_off"].copy_(s["host_off"], non_blocking=True)
         nbytes = total * f * 4 + (len(frames) + 1) * 4
         return s["dev_pts"][:total], s["dev_off"], max(sizes) if sizes else 0, nbytes
 
@@ -78,18 +91,17 @@ class HotPath(object):
         arena = self.engine.launch(vox["voxel_features"], vox["voxel_coords"], batch, n0_dev=n0, cap0=vox["cap"])
         return dict(vox=vox, arena=arena, batch=batch)
 
-    def launch_graph(self, frame_offsets_dev=None):
-        """Same step as launch_resident over the WHOLE staging buffer, replayed from a CUDA graph.
+    def launch_graph(self, slot=0):
+        """Same step as launch_resident over the WHOLE staging buffer of `slot`, replayed from a CUDA graph.
 
         The step has no host synchronisation and every buffer (points staging, voxel outputs, rulebooks, feature
         arena) has a fixed address, so it is captured once per staging capacity and replayed with one launch.
         Row counts are read from device memory by every kernel, so the same graph serves batches with different
         point counts up to the staging capacity.  Call upload() first; returns the handle for finish()."""
-        s = self._stage
+        s = self._slots.get(slot)
         if s is None:
             raise RuntimeError("launch_graph: call upload() first")
-        off = s["dev_off"] if frame_offsets_dev is None else frame_offsets_dev
-        key = (s["dev_pts"].data_ptr(), off.data_ptr(), s["pcap"], s["batch"])
+        key = (s["dev_pts"].data_ptr(), s["dev_off"].data_ptr(), s["pcap"], s["batch"])
         entry = self._graphs.get(key)
         if entry is None:
             cur = torch.cuda.current_stream(s["device"])
@@ -97,12 +109,12 @@ class HotPath(object):
             side.wait_stream(cur)
             with torch.cuda.stream(side):  # warm-up: allocates arenas, packs weights, sets kernel attributes
                 for _ in range(2):
-                    handle = self.launch_resident(s["dev_pts"], off, s["pcap"])
+                    handle = self.launch_resident(s["dev_pts"], s["dev_off"], s["pcap"])
             cur.wait_stream(side)
             torch.cuda.synchronize(s["device"])
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                handle = self.launch_resident(s["dev_pts"], off, s["pcap"])
+                handle = self.launch_resident(s["dev_pts"], s["dev_off"], s["pcap"])
             entry = (graph, handle)
             self._graphs[key] = entry
         entry[0].replay()
@@ -121,23 +133,29 @@ class HotPath(object):
             stream.synchronize()
             outs, n = eng.views(arena, vox["voxel_coords"], batch)
             enc = outs["out"]
-            need = (enc.features.shape[0], enc.features.shape[1])
-            hb = getattr(self, "_enc_host", None)
-            if hb is None or hb[0].shape[0] < need[0] or hb[0].shape[1] != need[1] or hb[0].dtype != enc.features.dtype:
-                hb = (torch.empty((int(need[0] * 1.2) + 64, need[1]), dtype=enc.features.dtype).pin_memory(),
-                      torch.empty((int(need[0] * 1.2) + 64, 4), dtype=torch.int32).pin_memory())
-                self._enc_host = hb  # pinned staging for the result, grow-only
-            hb[0][:need[0]].copy_(enc.features, non_blocking=True)
-            hb[1][:need[0]].copy_(enc.indices, non_blocking=True)
+            rows = enc.features.shape[0]
+            hb = self._result_host(0, rows, enc.features.shape[1], enc.features.dtype)
+            hb[0][:rows].copy_(enc.features, non_blocking=True)
+            hb[1][:rows].copy_(enc.indices, non_blocking=True)
             stream.synchronize()
             d2h += enc.features.numel() * enc.features.element_size() + enc.indices.numel() * 4
-            info = dict(counts=n, d2h_bytes=d2h, encoded_features_host=hb[0][:need[0]],
-                        encoded_indices_host=hb[1][:need[0]])
+            info = dict(counts=n, d2h_bytes=d2h, encoded_features_host=hb[0][:rows], encoded_indices_host=hb[1][:rows])
             return outs, info
         if sync:
             stream.synchronize()
         outs, n = eng.views(arena, vox["voxel_coords"], batch)
         return outs, dict(counts=n, d2h_bytes=d2h)
+
+    def _result_host(self, slot, rows, cols, dtype):
+        """Pinned host staging for the stride-8 result of `slot` (grow-only)."""
+        if self._enc_host is None:
+            self._enc_host = {}
+        hb = self._enc_host.get(slot)
+        if hb is None or hb[0].shape[0] < rows or hb[0].shape[1] != cols or hb[0].dtype != dtype:
+            cap = int(rows * 1.25) + 64
+            hb = (torch.empty((cap, cols), dtype=dtype).pin_memory(), torch.empty((cap, 4), dtype=torch.int32).pin_memory())
+            self._enc_host[slot] = hb
+        return hb
 
     def __call__(self, frames, device="cuda", fetch="counts"):
         pts, off, mfp, h2d = self.upload(frames, device)
@@ -154,3 +172,87 @@ class HotPath(object):
             'multi_scale_3d_strides': {'x_conv1': 1, 'x_conv2': 2, 'x_conv3': 4, 'x_conv4': 8},
         }
         return batch_dict, info
+
+    # ------------------------------------------------------------------ pipelined throughput mode
+    def run_stream(self, batches, device="cuda", depth=2):
+        """Generator over an iterable of batches (each a list of host point arrays).  Yields, in order, one dict per
+        batch with HOST results: 'counts' (rows per level), 'encoded_features' [N,C] and 'encoded_indices' [N,4]
+        (pinned tensors, valid until `depth` further batches have been yielded), 'h2d_bytes', 'd2h_bytes'.
+
+        Same work per batch as __call__(fetch='encoded'), but double buffered: the H2D copy of batch i+1 and the
+        D2H copy of batch i run on a copy stream while the kernels of the other batch run.  The result of a step is
+        snapshotted on the device (live rows only) right after the step, so the arena can be reused at once.
+        """
+        device = torch.device(device)
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        if self._copy_stream is None or self._copy_stream.device != device:
+            self._copy_stream = torch.cuda.Stream(device=device)
+        copy, main = self._copy_stream, torch.cuda.current_stream(device)
+        lib = _lib.load()
+        out_step = [st for st in self.engine.steps if st.export == "out"][0]
+        pending = []
+        for i, frames in enumerate(batches):
+            slot = i % depth
+            pts, off, mfp, h2d = self.upload(frames, device, slot=slot, stream=copy)
+            up = torch.cuda.Event()
+            up.record(copy)
+            main.wait_event(up)
+            handle = self.launch_graph(slot) if self.use_graph else self.launch_resident(pts, off, mfp)
+            arena = handle["arena"]
+            last = len(arena["caps"]) - 1
+            src_f = arena["bufs"][out_step.out_buf]
+            src_i = arena["indices"][last]
+            snap = self._snapshot(slot, src_f, src_i, arena["counts"])
+            n_ptr = _lib.ctypes.c_void_p(arena["counts"].data_ptr() + 4 * last)
+            with torch.cuda.device(device):
+                _lib.check(lib.fv2p_copy_rows(_lib.ptr(src_f), _lib.ptr(snap["feat"]),
+                                              src_f.shape[1] * src_f.element_size(), src_f.shape[0], n_ptr,
+                                              _lib.stream_ptr(device)), "copy_rows")
+                _lib.check(lib.fv2p_copy_rows(_lib.ptr(src_i), _lib.ptr(snap["ind"]), 16, src_i.shape[0], n_ptr,
+                                              _lib.stream_ptr(device)), "copy_rows")
+                snap["counts"].copy_(arena["counts"], non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(main)
+            pending.append((slot, snap, done, h2d, src_f.shape[1], src_f.dtype))
+            if len(pending) >= depth:
+                yield self._collect(pending.pop(0), copy)
+        while pending:
+            yield self._collect(pending.pop(0), copy)
+
+    def _snapshot(self, slot, feat, ind, counts):
+        key = ("snap", slot)
+        s = self._slots.get(key)
+        if s is None or s["feat"].shape != feat.shape or s["feat"].dtype != feat.dtype:
+            s = dict(feat=torch.empty_like(feat), ind=torch.empty_like(ind), counts=torch.empty_like(counts),
+                     counts_host=torch.zeros(counts.shape, dtype=counts.dtype).pin_memory())
+            self._slots[key] = s
+        return s
+
+    def _collect(self, item, copy):
+        slot, snap, done, h2d, cols, dtype = item
+        copy.wait_event(done)
+        with torch.cuda.stream(copy):
+            snap["counts_host"].copy_(snap["counts"], non_blocking=True)
+        copy.synchronize()
+        host = snap["counts_host"].tolist()
+        n_levels = len(host) - 1
+        if host[n_levels]:
+            raise RuntimeError("fv2p_b200: capacity overflow (status %d)" % host[n_levels])
+        rows = host[n_levels - 1]
+        hb = self._result_host(("stream", slot), rows, cols, dtype)
+        with torch.cuda.stream(copy):
+            hb[0][:rows].copy_(snap["feat"][:rows], non_blocking=True)
+            hb[1][:rows].copy_(snap["ind"][:rows], non_blocking=True)
+        copy.synchronize()
+        d2h = len(host) * 4 + rows * cols * hb[0].element_size() + rows * 16
+        return dict(counts=host[:n_levels], encoded_features=hb[0][:rows], encoded_indices=hb[1][:rows],
+                    h2d_bytes=h2d, d2h_bytes=d2h)
+
+
+class _NullCtx(object):
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False

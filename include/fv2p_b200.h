@@ -186,7 +186,8 @@ FV2P_API int fv2p_sort_rows_by_mask(const int32_t *nbr, int64_t nbr_stride, int 
                                     fv2p_stream_t stream);
 
 /* Producer of the gathered A tile in the tensor-core kernels: -1 = auto (default: measured best per shape),
- * 0 = LSU (swizzled cp.async), 1 = TMA (cp.async.bulk.tensor tile::gather4).  Same results either way; a tuning
+ * 0 = LSU (swizzled cp.async), 1 = TMA (cp.async.bulk.tensor tile::gather4), 2 = fp32 kernels only: plain loads,
+ * hi/lo split in registers, shared-memory stores (no transform warps).  Same results either way; a tuning
  * knob kept for measurement (profiles/r1_notes.md).  Process-wide, not stream-ordered. */
 FV2P_API int fv2p_tc_gather_mode(int mode);
 
@@ -210,6 +211,11 @@ FV2P_API int fv2p_indice_conv_fp32(const float *features, const float *filters, 
 FV2P_API int fv2p_dense_ncdhw(const float *features, const int32_t *indices, int64_t n_cap,
                      const int32_t *n_dev, int channels, const int32_t *shape3, float *dense,
                      fv2p_stream_t stream);
+
+/* Copies the live rows (count on the device) of a capacity-sized row buffer; row_bytes must be a multiple of 16.
+ * Used to snapshot a step's result so that its D2H copy overlaps the next step. */
+FV2P_API int fv2p_copy_rows(const void *src, void *dst, int64_t row_bytes, int64_t n_cap, const int32_t *n_dev,
+                            fv2p_stream_t stream);
 
 /* dtype helpers used by the bf16 path */
 FV2P_API int fv2p_cast_f32_to_bf16(const float *src, void *dst, int64_t count, fv2p_stream_t stream);

@@ -434,3 +434,30 @@ def test_mask_sorted_row_order_gives_identical_results():
             b = spconv.ops.conv_forward(feats, packed, nbr_sorted.contiguous(), n_out, residual=res, relu=True,
                                         mode=mode, row_perm=perm.contiguous())
             assert torch.equal(a, b)
+
+
+def test_run_stream_matches_single_calls_and_graph_replay():
+    """The pipelined / CUDA-graph form of the hot path returns exactly what the plain call returns, batch after
+    batch with different point counts (the graph is captured once for the staging capacity)."""
+    cfg = synth.DATASETS["kitti"]
+    net, _ = _load_backbone("VoxelResBackBone8x", 4, synth.grid_size(cfg), 9)
+    batches = [[synth.lidar_frame("kitti", seed=70 + 3 * i + j, az_steps=100 + 30 * ((i + j) % 3)) for j in range(2)]
+               for i in range(5)]
+    ref = fv2p_b200.HotPath(net, cfg["voxel_size"], cfg["point_cloud_range"], 5, 16000)
+    expect = []
+    for b in batches:
+        bd, info = ref(b, fetch="encoded")
+        expect.append((info["counts"], info["encoded_features_host"].clone(), info["encoded_indices_host"].clone()))
+    for use_graph in (False, True):
+        hp = fv2p_b200.HotPath(net, cfg["voxel_size"], cfg["point_cloud_range"], 5, 16000, use_graph=use_graph)
+        # size the staging for the largest batch first (a graph serves anything up to its capture capacity)
+        hp.upload(max(batches, key=lambda b: sum(f.shape[0] for f in b)), slot=0)
+        hp.upload(max(batches, key=lambda b: sum(f.shape[0] for f in b)), slot=1)
+        got = []
+        for res in hp.run_stream(iter(batches)):
+            got.append((res["counts"], res["encoded_features"].clone(), res["encoded_indices"].clone()))
+        assert len(got) == len(expect)
+        for (c0, f0, i0), (c1, f1, i1) in zip(expect, got):
+            assert c0 == c1
+            assert torch.equal(i0, i1)
+            assert torch.equal(f0, f1)
