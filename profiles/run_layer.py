@@ -68,20 +68,5 @@ for mode in a.debug:
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
     print("debug mode", mode, "ms", min(ts))
-    if mode == 8:
-        buf = (ctypes.c_longlong * 64)()
-        lib.fv2p_debug_prof(buf, 1)
-        lib.fv2p_conv_fwd(_lib.ptr(src), src.shape[0], _lib.ptr(w), _lib.ptr(nbr), nbr.shape[1], _lib.ptr(perm), st.kvol, caps[st.out_level],
-                          _lib.ctypes.c_void_p(arena["counts"].data_ptr() + 4 * st.out_level), st.cin, st.cout,
-                          _lib.ptr(p["bias"]), _lib.ptr(p["scale"]), _lib.ptr(p["shift"]), _lib.ptr(res), int(st.relu),
-                          p["mode"], _lib.ptr(out), _lib.stream_ptr(dev))
-        torch.cuda.synchronize()
-        lib.fv2p_debug_prof(buf, 0)
-        v = list(buf)
-        print("  gather: blocked_on_empty=%d cyc over %d stages, prologue=%d, loop=%d" % (v[0], v[1], v[2], v[3]))
-
-
-        print("  mma:    blocked_on_tmem_empty=%d, blocked_on_full=%d over %d stages, loop=%d" % (v[8], v[9], v[10], v[11]))
-        print("  epi:    blocked_on_tmem_full=%d, loop=%d" % (v[16], v[17]))
     lib.fv2p_debug_set(ctypes.c_int(0))
 print("layer", a.layer, st.key, st.cin, st.cout, "mode", p["mode"], "rows", hp.finish(h)[1]["counts"])
