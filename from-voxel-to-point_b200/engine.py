@@ -156,6 +156,7 @@ class BackboneEngine(object):
         self.concurrent = concurrent  # geometry and feature pass on forked streams (joined before launch returns)
         self._side = None
         self.arena = None
+        self.arena_gen = 0
         self._param_key = None
         self._params = None
         # liveness of feature buffers: last step reading each one (exports live forever)
@@ -262,6 +263,7 @@ class BackboneEngine(object):
             bufs[st.out_buf] = free[pick][0]
         a["bufs"] = bufs
         self.arena = a
+        self.arena_gen += 1  # captured CUDA graphs hold arena addresses: a new arena invalidates them
         return a
 
     # ------------------------------------------------------------------ run

@@ -103,6 +103,8 @@ class HotPath(object):
             raise RuntimeError("launch_graph: call upload() first")
         key = (s["dev_pts"].data_ptr(), s["dev_off"].data_ptr(), s["pcap"], s["batch"])
         entry = self._graphs.get(key)
+        if entry is not None and entry[2] != (self.engine.arena_gen, self.voxelizer.gen, self.engine._param_key):
+            entry = None  # buffers or parameters behind the captured addresses changed: capture again
         if entry is None:
             cur = torch.cuda.current_stream(s["device"])
             side = torch.cuda.Stream(device=s["device"])
@@ -115,7 +117,7 @@ class HotPath(object):
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 handle = self.launch_resident(s["dev_pts"], s["dev_off"], s["pcap"])
-            entry = (graph, handle)
+            entry = (graph, handle, (self.engine.arena_gen, self.voxelizer.gen, self.engine._param_key))
             self._graphs[key] = entry
         entry[0].replay()
         return entry[1]

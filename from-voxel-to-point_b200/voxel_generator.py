@@ -97,6 +97,7 @@ class BatchVoxelizer(object):
         self.vg = VoxelGenerator(voxel_size, point_cloud_range, max_num_points, max_voxels)
         self.want_voxels = want_voxels
         self._bufs = None
+        self.gen = 0  # bumped whenever the output buffers are reallocated (captured graphs hold their addresses)
 
     def _ensure(self, device, total_points, batch, f):
         t = int(self.vg._max_num_points)
@@ -117,6 +118,7 @@ class BatchVoxelizer(object):
                      ws=torch.empty(lib.fv2p_voxelize_workspace_bytes(pcap, batch, pcap, t, cap) + 1024,
                                     dtype=torch.uint8, device=device))
             self._bufs = b
+            self.gen += 1
         return b
 
     def __call__(self, points, frame_offsets, max_frame_points=None):
