@@ -6,15 +6,13 @@ from .. import _lib
 
 
 def scatter_nd(indices, updates, shape):
-    """Reference helper (structure.py:5-18); kept for callers that import it."""
-    ret = torch.zeros(*shape, dtype=updates.dtype, device=updates.device)
-    ndim = indices.shape[-1]
-    output_shape = list(indices.shape[:-1]) + shape[indices.shape[-1]:]
-    flatted_indices = indices.view(-1, ndim)
-    slices = [flatted_indices[:, i] for i in range(ndim)]
-    slices += [Ellipsis]
-    ret[slices] = updates.view(*output_shape)
-    return ret
+    """Dense tensor of ``shape`` with ``updates`` written at ``indices`` (reference helper, structure.py:5-18;
+    kept for callers that import it)."""
+    lead = indices.shape[-1]
+    coords = indices.reshape(-1, lead).long()
+    dense = updates.new_zeros(tuple(shape))
+    dense[tuple(coords.unbind(1))] = updates.reshape(coords.shape[0], *shape[lead:])
+    return dense
 
 
 class SparseConvTensor(object):

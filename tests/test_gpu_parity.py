@@ -461,3 +461,70 @@ def test_run_stream_matches_single_calls_and_graph_replay():
             assert c0 == c1
             assert torch.equal(i0, i1)
             assert torch.equal(f0, f1)
+
+
+def test_engine_options_do_not_change_results():
+    """MATERIALIZE_PAIRS / SORT_ROWS only change what is materialised and how rows are grouped into tiles."""
+    g = load_golden("backbone_kitti_VoxelResBackBone8x")
+    outs = []
+    for cfg in ({}, {"MATERIALIZE_PAIRS": False}, {"SORT_ROWS": False}):
+        net, _ = _load_backbone("VoxelResBackBone8x", 4, g["grid_size"], int(g["seed"]), cfg)
+        with torch.no_grad():
+            bd = net({"voxel_features": cuda(g["voxel_features"]), "voxel_coords": cuda(g["voxel_coords"]),
+                      "batch_size": int(g["batch_size"])})
+        enc = bd["encoded_spconv_tensor"]
+        outs.append((enc.features.clone(), enc.indices.clone(), len(enc.indice_dict)))
+    assert outs[0][2] == 9 and outs[1][2] == 0  # pair tensors are only there when asked for
+    for o in outs[1:]:
+        assert torch.equal(o[1], outs[0][1])
+        assert torch.equal(o[0], outs[0][0])
+
+
+def test_hot_path_32_frames_and_an_empty_frame():
+    """One call over 32 frames (the reference's int32 dense grid stops at 23) with an empty frame in
+    the middle equals the frames run one by one."""
+    cfg = synth.DATASETS["kitti"]
+    net, _ = _load_backbone("VoxelBackBone8x", 4, synth.grid_size(cfg), 4)
+    hp = fv2p_b200.HotPath(net, cfg["voxel_size"], cfg["point_cloud_range"], 5, 16000)
+    frames = [synth.lidar_frame("kitti", seed=200 + i, az_steps=30 + (i % 5) * 6) for i in range(32)]
+    frames[7] = np.zeros((0, 4), np.float32)
+    bd, info = hp(frames)
+    enc = bd["encoded_spconv_tensor"]
+    ind, feat = enc.indices.cpu().numpy().copy(), enc.features.cpu().numpy().copy()
+    assert not (ind[:, 0] == 7).any() and ind[:, 0].max() == 31
+    assert np.all(np.diff(ind[:, 0]) >= 0)  # rows stay batch-contiguous (consumers rely on it, SURVEY A.3)
+    for b in (0, 6, 8, 31):
+        bd1, _ = hp([frames[b]])
+        e1 = bd1["encoded_spconv_tensor"]
+        sel = ind[:, 0] == b
+        assert np.array_equal(ind[sel][:, 1:], e1.indices.cpu().numpy()[:, 1:])
+        assert rel_err(feat[sel], e1.features.cpu().numpy()) < 1e-6
+
+
+def test_module_path_trains():
+    """Training mode uses the plain module graph; the conv backward (a torch-index composition, not on the hot
+    path) must agree with autograd through the equivalent dense conv3d."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(1)
+    shape = [5, 8, 7]
+    ind = synth.random_voxels(shape, 120, 1, seed=2)
+    conv = spconv.SubMConv3d(6, 10, 3, bias=True, indice_key="t").to(DEV)
+    feats = torch.randn(ind.shape[0], 6, device=DEV, requires_grad=True)
+    x = spconv.SparseConvTensor(feats, cuda(ind), shape, 1)
+    y = conv(x)
+    loss = (y.features ** 2).sum()
+    loss.backward()
+    gw, gb, gx = conv.weight.grad.clone(), conv.bias.grad.clone(), feats.grad.clone()
+    # dense reference
+    w = conv.weight.detach().clone().requires_grad_(True)
+    b = conv.bias.detach().clone().requires_grad_(True)
+    f2 = feats.detach().clone().requires_grad_(True)
+    dense = spconv.scatter_nd(cuda(ind).long(), f2, [1] + shape + [6]).permute(0, 4, 1, 2, 3)
+    out = torch.nn.functional.conv3d(dense, w.permute(4, 3, 0, 1, 2), b, 1, 1)
+    idx = cuda(ind).long()
+    picked = out[idx[:, 0], :, idx[:, 1], idx[:, 2], idx[:, 3]]
+    ((picked ** 2).sum()).backward()
+    assert torch.allclose(gw, w.grad, atol=1e-3, rtol=1e-3)
+    assert torch.allclose(gb, b.grad, atol=1e-3, rtol=1e-3)
+    assert torch.allclose(gx, f2.grad, atol=1e-3, rtol=1e-3)
