@@ -115,33 +115,22 @@ def layer_profile(hp, handle, flush):
     from fv2p_b200 import _lib
     eng, a = hp.engine, handle["arena"]
     outs, n = eng.views(a, handle["vox"]["voxel_coords"], handle["batch"])
-    lib = _lib.load()
     prm = eng._prepare_params(a["device"])
-    stream = _lib.stream_ptr(a["device"])
     recs = []
-    caps = a["caps"]
-    level_cap = [handle["vox"]["cap"]] + caps[1:]
-    counts = a["counts"]
     for i, (st, p) in enumerate(zip(eng.steps, prm)):
-        nbr, perm = eng.conv_operands(a, st, p)
+        nbr = eng.conv_operands(a, st, p)[0]
         pairs_total = int((nbr[:, :n[st.out_level]] >= 0).sum().item())
         src = handle["vox"]["voxel_features"] if st.in_buf < 0 else a["bufs"][st.in_buf]
         res = a["bufs"][st.res_buf] if st.res_buf is not None else None
         out = a["bufs"][st.out_buf]
-        w = p["packed"] if p["packed"] is not None else p["w"]
         times = []
         for _ in range(3):
             flush()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            rc = lib.fv2p_conv_fwd(_lib.ptr(src), src.shape[0], _lib.ptr(w), _lib.ptr(nbr), nbr.shape[1], _lib.ptr(perm), st.kvol,
-                                   level_cap[st.out_level],
-                                   _lib.ctypes.c_void_p(counts.data_ptr() + 4 * st.out_level), st.cin, st.cout,
-                                   _lib.ptr(p["bias"]), _lib.ptr(p["scale"]), _lib.ptr(p["shift"]), _lib.ptr(res),
-                                   int(st.relu), p["mode"], _lib.ptr(out), stream)
+            eng.run_conv_step(a, i, p, handle["vox"]["voxel_features"], handle["vox"]["cap"])
             e1.record()
             torch.cuda.synchronize()
-            _lib.check(rc, "conv_fwd")
             times.append(e0.elapsed_time(e1))
         e_in = 4 if src.dtype == torch.float32 else 2
         e_out = 4 if out.dtype == torch.float32 else 2
@@ -159,7 +148,7 @@ def run_ours(args, wl, rank, world, device):
     import torch.distributed as dist
     from fv2p_b200 import _lib
     precision = args.precision
-    _lib.load().fv2p_tc_gather_mode({"auto": -1, "lsu": 0, "tma": 1, "regs": 2}[args.gather])
+    _lib.load().fv2p_tc_gather_mode({"auto": -1, "lsu": 0, "tma": 1}[args.gather])
     sampler = ClockSampler(torch.cuda.current_device() if device.index is None else device.index)
     sampler.start()  # nvidia-smi takes a second to start streaming; rows are filtered to the timed region later
     net, hp, state, cfg = build_model(wl, device, precision, use_graph=not args.no_graph)
@@ -400,7 +389,7 @@ def main():
     ap.add_argument("--workload", default="kitti_b8", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--gather", default="auto", choices=["auto", "lsu", "tma", "regs"],
+    ap.add_argument("--gather", default="auto", choices=["auto", "lsu", "tma"],
                     help="A-tile producer of the tensor-core conv (fv2p_tc_gather_mode); auto = measured best per shape")
     ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()

@@ -39,10 +39,11 @@ PROTOTYPES = {
                                           _c_int, _c_int, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp,
                                           _c_sz, _c_vp]),
     "fv2p_pairs_to_nbr": (_c_int, [_c_vp, _c_vp, _c_int, _c_i64, _c_int, _c_i64, _c_vp, _c_i64, _c_vp]),
-    "fv2p_conv_fwd": (_c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_i64, _c_vp, _c_int, _c_i64, _c_vp, _c_int, _c_int, _c_vp, _c_vp,
-                               _c_vp, _c_vp, _c_int, _c_int, _c_vp, _c_vp]),
+    "fv2p_conv_fwd": (_c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_int, _c_i64, _c_vp, _c_int,
+                               _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_vp, _c_vp]),
     "fv2p_sort_rows_workspace_bytes": (_c_sz, [_c_i64]),
-    "fv2p_sort_rows_by_mask": (_c_int, [_c_vp, _c_i64, _c_int, _c_i64, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_sz, _c_vp]),
+    "fv2p_sort_rows_by_mask": (_c_int, [_c_vp, _c_i64, _c_int, _c_i64, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp, _c_sz,
+                                        _c_vp]),
     "fv2p_tc_gather_mode": (_c_int, [_c_int]),
     "fv2p_pack_weight_bytes": (_c_sz, [_c_int, _c_int, _c_int, _c_int]),
     "fv2p_pack_weight": (_c_int, [_c_vp, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp]),

@@ -257,18 +257,19 @@ dense_ncdhw_kernel(const float *__restrict__ features, const int4 *__restrict__ 
 
 // implemented in conv_tc.cu
 int launch_conv_tc(const void *features, int64_t feat_rows, const void *weight, const int *nbr, int64_t nbr_stride,
-                   const int *row_perm, int kvol, int64_t n_out_cap, const int *n_out_dev, int cin, int cout, const float *bias,
-                   const float *scale, const float *shift, const void *residual, int relu, int mode, void *out,
-                   cudaStream_t stream);
+                   const int *row_perm, const int *tile_order, int *sched, int kvol, int64_t n_out_cap,
+                   const int *n_out_dev, int cin, int cout, const float *bias, const float *scale, const float *shift,
+                   const void *residual, int relu, int mode, void *out, cudaStream_t stream);
 
 }  // namespace fv2p
 
 using namespace fv2p;
 
 extern "C" int fv2p_conv_fwd(const void *features, int64_t n_in_cap, const void *weight, const int32_t *nbr, int64_t nbr_stride,
-                             const int32_t *row_perm, int kvol, int64_t n_out_cap, const int32_t *n_out_dev, int cin, int cout,
-                             const float *bias, const float *scale, const float *shift, const void *residual,
-                             int relu, int mode, void *out, fv2p_stream_t stream_) {
+                             const int32_t *row_perm, const int32_t *tile_order, int32_t *sched, int kvol,
+                             int64_t n_out_cap, const int32_t *n_out_dev, int cin, int cout, const float *bias,
+                             const float *scale, const float *shift, const void *residual, int relu, int mode,
+                             void *out, fv2p_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   FV2P_REQUIRE(kvol >= 1 && kvol <= FV2P_MAX_KVOL, "conv_fwd: kernel volume %d out of range", kvol);
   FV2P_REQUIRE(cin >= 1 && cout >= 1 && cin <= 4096 && cout <= 4096, "conv_fwd: bad channel counts");
@@ -276,8 +277,9 @@ extern "C" int fv2p_conv_fwd(const void *features, int64_t n_in_cap, const void 
   FV2P_REQUIRE((scale == nullptr) == (shift == nullptr), "conv_fwd: scale and shift come together");
   if (n_out_cap == 0) return FV2P_OK;
   FV2P_REQUIRE(features && weight && nbr && out, "conv_fwd: null pointer argument");
-  FV2P_REQUIRE(!row_perm || mode == FV2P_MODE_BF16_TC || mode == FV2P_MODE_TF32X3_TC,
-               "conv_fwd: a row order (row_perm) is only used by the tensor-core modes");
+  FV2P_REQUIRE((!row_perm && !tile_order && !sched) || mode == FV2P_MODE_BF16_TC || mode == FV2P_MODE_TF32X3_TC,
+               "conv_fwd: row_perm / tile_order / sched are only used by the tensor-core modes");
+  FV2P_REQUIRE(!tile_order || row_perm, "conv_fwd: tile_order comes with the row order it was computed for");
   switch (mode) {
     case FV2P_MODE_F32:
       return launch_simt<float, float>(features, static_cast<const float *>(weight), nbr, nbr_stride, kvol,
@@ -293,8 +295,8 @@ extern "C" int fv2p_conv_fwd(const void *features, int64_t n_in_cap, const void 
                                                residual, relu, out, stream);
     case FV2P_MODE_BF16_TC:
     case FV2P_MODE_TF32X3_TC:
-      return launch_conv_tc(features, n_in_cap, weight, nbr, nbr_stride, row_perm, kvol, n_out_cap, n_out_dev, cin,
-                            cout, bias, scale, shift, residual, relu, mode, out, stream);
+      return launch_conv_tc(features, n_in_cap, weight, nbr, nbr_stride, row_perm, tile_order, sched, kvol, n_out_cap,
+                            n_out_dev, cin, cout, bias, scale, shift, residual, relu, mode, out, stream);
     default:
       set_error("conv_fwd: unknown mode %d", mode);
       return FV2P_ERR_INVALID;
@@ -320,7 +322,7 @@ extern "C" int fv2p_indice_conv_fp32(const float *features, const float *filters
   int *nbr = static_cast<int *>(workspace);
   int st = fv2p_pairs_to_nbr(pairs, pair_num, kvol, pair_stride, inverse, num_act_out, nbr, num_act_out, stream_);
   if (st) return st;
-  return fv2p_conv_fwd(features, 0, filters, nbr, num_act_out, nullptr, kvol, num_act_out, nullptr, cin, cout, nullptr,
+  return fv2p_conv_fwd(features, 0, filters, nbr, num_act_out, nullptr, nullptr, nullptr, kvol, num_act_out, nullptr, cin, cout, nullptr,
                        nullptr, nullptr, nullptr, 0, FV2P_MODE_F32, out, stream_);
 }
 

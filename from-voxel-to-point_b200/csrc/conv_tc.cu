@@ -24,6 +24,12 @@
 //                 tcgen05.commit releases the smem stage / publishes the accumulator through mbarriers
 //   epilogue      warps 0-3 read TMEM with tcgen05.ld (one accumulator row per thread), apply
 //                 bias + folded BatchNorm + residual + ReLU and store 16-byte vectors
+//   tiles         handed out from an atomic counter in the order fv2p_sort_rows_by_mask computed (most active
+//                 offsets first = longest-processing-time-first list scheduling): with mask-sorted rows a tile
+//                 takes 1..27 offsets, and dealing tiles round-robin left the busiest CTA with 1.3-2.2x the mean
+//                 work (KITTI: 180 stages against a mean of 81 on the 128->128 layers).  The producers fetch the
+//                 tile ids (one tile ahead of the neighbour prefetch, so the atomic's latency is hidden), publish
+//                 them through a small shared ring for the epilogue, and end the stream with a sentinel stage.
 //
 // fp32 path = 3xTF32: four transform warps (13-16) split the landed fp32 tile in place into
 // hi = rn_tf32(x) and a second tile lo = rn_tf32(x - hi); W is packed as hi/lo images, and each K step issues
@@ -46,6 +52,8 @@ constexpr int kXformThreads = 128;                           // warps 13-16, fp3
 constexpr int kTcThreadsBase = kEpiThreads + kProdThreads + 32;
 constexpr int kMaxStages = 8;
 constexpr int kSmemBudget = 212 * 1024;
+constexpr int kTileRing = 16;  // > kMaxStages + 2: how far the producers can run ahead of the epilogue, in tiles
+constexpr int kFlagFirst = 1, kFlagLast = 2, kFlagStop = 4;
 
 // ------------------------------------------------------------------------------------------ PTX
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -165,8 +173,7 @@ __host__ __device__ constexpr uint32_t instr_desc(int n, bool tf32) {
 
 // Timing experiments only (profiles/run_layer.py --debug): 4 = no MMA, 6 = no epilogue body.  0 in production.
 __device__ int g_tc_debug = 0;
-// Host-side choice of the A-tile producer: -1 = auto (measured best per shape), 0 = LSU (cp.async), 1 = TMA gather4,
-// 2 = fp32 only: LDG + hi/lo split in registers + STS (bf16 kernels treat 2 as 0).
+// Host-side choice of the A-tile producer: -1 = auto (measured best per shape), 0 = LSU (cp.async), 1 = TMA gather4.
 int g_tc_gather_mode = -1;
 
 template <bool kTf32, int N>
@@ -194,9 +201,9 @@ template <bool kTf32, int N>
 __global__ void __launch_bounds__((Cfg<kTf32, N>::kThreads), 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restrict__ feat_ptr,
                const uint8_t *__restrict__ wpacked,
-               const int *__restrict__ nbr, int64_t nbr_stride, const int *__restrict__ row_perm, int kvol,
-               int64_t n_out_cap, const int *__restrict__ n_out_dev, int cin, int oob_row, int use_tma_arg,
-               Epilogue ep) {
+               const int *__restrict__ nbr, int64_t nbr_stride, const int *__restrict__ row_perm,
+               const int *__restrict__ tile_order, int *sched, int kvol, int64_t n_out_cap,
+               const int *__restrict__ n_out_dev, int cin, int oob_row, int use_tma_arg, Epilogue ep) {
   using C = Cfg<kTf32, N>;
   constexpr int kElem = kTf32 ? 4 : 2;
   extern __shared__ uint8_t smem_raw[];
@@ -211,11 +218,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
   volatile int *stage_flags = reinterpret_cast<volatile int *>(bars + 3 * C::kStages + 4);  // [kStages]
   volatile uint32_t *tile_mask = reinterpret_cast<volatile uint32_t *>(stage_flags + C::kStages);
   uint32_t *tmem_slot = const_cast<uint32_t *>(tile_mask) + 1;
+  volatile int *next_tile_s = reinterpret_cast<volatile int *>(tmem_slot + 1);  // producers' broadcast slot
+  volatile int *tile_ring = next_tile_s + 1;                                     // [kTileRing] tile id per sequence no.
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int dbg = g_tc_debug;
   const bool use_tma = use_tma_arg == 1;
-  const bool split_regs = kTf32 && use_tma_arg == 2;  // fp32: LDG -> hi/lo split in registers -> STS (no transform warps)
   int n_out = n_out_dev ? *n_out_dev : (int)n_out_cap;
   if (n_out > n_out_cap) n_out = (int)n_out_cap;
   const int n_tiles = (n_out + kTileM - 1) / kTileM;
@@ -231,8 +239,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
       // LSU gather: + the 32 cp.async arrivals of the owning warp (the fp32 `landed` barrier also gets one plain
       // arrive that publishes the stage flags).
       const uint32_t a_arrivals = use_tma ? 1u : 33u;
-      // fp32 register-split producer (mode 2): the two warps that own the slot + the weight copy's expect_tx
-      mbar_init(bar_full + 8 * s, split_regs ? 3u : (kTf32 ? kXformThreads + 1 : a_arrivals));
+      mbar_init(bar_full + 8 * s, kTf32 ? kXformThreads + 1 : a_arrivals);
       mbar_init(bar_empty + 8 * s, 1);
       mbar_init(bar_landed + 8 * s, a_arrivals);
     }
@@ -255,7 +262,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp >= 4 && warp < kMmaWarp) {
-    // =============================== producers: neighbour prefetch + TMA issue ===============================
+    // =============================== producers: tile fetch + neighbour prefetch + gather issue ===============
     const int tid = threadIdx.x - kEpiThreads;
     const int pwarp = tid >> 5;
     const uint8_t *feat = static_cast<const uint8_t *>(feat_ptr);
@@ -268,6 +275,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
     const int my_chunk = lane & (chunks - 1);
     const int my_row0 = lane >> cshift;
     const int rows_per_instr = 32 >> cshift;
+    // Next tile of this CTA, -1 when the work is used up: from the shared counter in `tile_order` (heaviest first),
+    // or round-robin when the caller gave no scheduler scratch.
+    int static_next = blockIdx.x;
+    auto fetch_tile = [&]() -> int {
+      int i;
+      if (sched) {
+        i = atomicAdd(&sched[0], 1);
+      } else {
+        i = static_next;
+        static_next += gridDim.x;
+      }
+      if (i >= n_tiles) return -1;
+      return tile_order ? __ldg(&tile_order[i]) : i;
+    };
     // The neighbour rows of a tile are prefetched into registers one tile ahead: the loads of tile t+1 are in
     // flight while tile t's stages are being issued.  Thread t serves row t%128 for the offsets of parity t/128.
     constexpr int kNbrRegs = FV2P_MAX_KVOL / 2;
@@ -279,14 +300,46 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
 #pragma unroll
       for (int q = 0; q < kNbrRegs; ++q) {
         const int k = pre_k0 + 2 * q;
-        nbr_next[q] = (tile < n_tiles && k < kvol && row < n_out) ? __ldg(&nbr[(size_t)k * nbr_stride + row]) : -1;
+        nbr_next[q] = (tile >= 0 && k < kvol && row < n_out) ? __ldg(&nbr[(size_t)k * nbr_stride + row]) : -1;
       }
     };
-    prefetch(blockIdx.x);
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      asm volatile("bar.sync 1, 256;" ::: "memory");  // every producer warp finished reading nbr_s of the last tile
-      if (tid == 0) *tile_mask = 0u;
+    int pending = -1;  // thread 0: the tile after the next one, fetched while the current tile's stages are issued
+    if (tid == 0) {
+      *next_tile_s = fetch_tile();
+      pending = fetch_tile();
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    int tile = *next_tile_s;
+    prefetch(tile);
+    for (uint32_t seq = 0;; ++seq) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // every producer warp finished reading nbr_s / next_tile_s
+      if (tid == 0) {
+        *tile_mask = 0u;
+        tile_ring[seq % kTileRing] = tile;
+        *next_tile_s = pending;
+      }
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (tile < 0) {
+        // Sentinel stage: same arrivals as a real stage, no copies; tells the other roles to stop.
+        const uint32_t s = issued % C::kStages;
+        if ((int)(s % kProdWarps) == pwarp) {
+          mbar_wait(bar_empty + 8 * s, ((issued / C::kStages) & 1) ^ 1);
+          const uint32_t a_bar = kTf32 ? bar_landed + 8 * s : bar_full + 8 * s;
+          if (lane == 0) {
+            stage_flags[s] = kFlagStop;
+            if constexpr (kTf32) {
+              if (use_tma) mbar_arrive_expect_tx(bar_landed + 8 * s, 0u);
+              else mbar_arrive(bar_landed + 8 * s);
+              mbar_arrive_expect_tx(bar_full + 8 * s, 0u);
+            } else {
+              mbar_arrive_expect_tx(bar_full + 8 * s, 0u);
+            }
+          }
+          __syncwarp();
+          if (!use_tma) cp_async_arrive(a_bar);
+        }
+        break;
+      }
       {
         uint32_t mine = 0;
 #pragma unroll
@@ -300,8 +353,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
         }
         if (lane == 0 && mine) atomicOr(const_cast<uint32_t *>(tile_mask), mine);
       }
-      prefetch(tile + gridDim.x);
+      const int tile_after = *next_tile_s;
+      prefetch(tile_after);
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (tid == 0) pending = fetch_tile();  // consumed one iteration from now
       uint32_t mask = *tile_mask;
       if (mask == 0u) mask = 1u;  // a tile nothing feeds still has to produce (zero) accumulators
       const uint32_t first_k = __ffs(mask) - 1;
@@ -314,59 +369,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
           // in program order (the parity wait cannot alias, whatever the drift between warps); warps without a
           // slot of their own (ring shorter than the warp count) only help with the neighbour prefetch.
           const uint32_t s = issued % C::kStages;
-          if (split_regs ? (int)(s % (kProdWarps / 2)) != (pwarp >> 1) : (int)(s % kProdWarps) != pwarp) continue;
+          if ((int)(s % kProdWarps) != pwarp) continue;
           mbar_wait(bar_empty + 8 * s, ((issued / C::kStages) & 1) ^ 1);
           const uint32_t a_u32 = smem_u32(stage_base + (size_t)s * C::kStageBytes);
           const uint32_t a_bar = kTf32 ? bar_landed + 8 * s : bar_full + 8 * s;
-          if constexpr (kTf32) {
-            if (split_regs) {
-              // Two warps per stage (64 rows each).  Eight 16-byte loads are put in flight per lane, then each is
-              // split into hi = rn_tf32(x) / lo = rn_tf32(x - hi) and stored to the two swizzled tiles.  A
-              // missing neighbour stores zeros without touching global memory.
-              if ((pwarp & 1) == 0 && lane == 0) {
-                stage_flags[s] = ((k == (int)first_k && sl == 0) ? 1 : 0) | ((k == (int)last_k && sl == slices - 1) ? 2 : 0);
-                const uint32_t wb = w_stage_bytes * 2;
-                mbar_arrive_expect_tx(bar_full + 8 * s, wb);
-                bulk_g2s(a_u32 + 2 * C::kABytes, wpacked + ((size_t)k * slices + sl) * wb, wb, bar_full + 8 * s);
-              }
-              uint8_t *a_hi = stage_base + (size_t)s * C::kStageBytes;
-              uint8_t *a_lo = a_hi + C::kABytes;
-              const size_t col_off = (size_t)sl * row_bytes + my_chunk * 16;
-              const int *rows_k = nbr_s + k * kTileM;
-              const int r_begin = (pwarp & 1) * (kTileM / 2) + my_row0, r_end = (pwarp & 1) * (kTileM / 2) + kTileM / 2;
-              for (int r0 = r_begin; r0 < r_end; r0 += 8 * rows_per_instr) {
-                float4 v[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                  const int r = r0 + u * rows_per_instr;
-                  const int src = r < r_end ? rows_k[r] : -1;
-                  v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                  if (src >= 0)
-                    v[u] = __ldg(reinterpret_cast<const float4 *>(feat + (size_t)src * feat_row_bytes + col_off));
-                }
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                  const int r = r0 + u * rows_per_instr;
-                  if (r < r_end) {
-                    const uint32_t off = (uint32_t)r * row_bytes +
-                                         ((uint32_t)(my_chunk ^ ((r >> (3 - cshift)) & (chunks - 1))) << 4);
-                    float4 h, l;
-                    h.x = tf32_rn(v[u].x), h.y = tf32_rn(v[u].y), h.z = tf32_rn(v[u].z), h.w = tf32_rn(v[u].w);
-                    l.x = tf32_rn(v[u].x - h.x), l.y = tf32_rn(v[u].y - h.y), l.z = tf32_rn(v[u].z - h.z);
-                    l.w = tf32_rn(v[u].w - h.w);
-                    *reinterpret_cast<float4 *>(a_hi + off) = h;
-                    *reinterpret_cast<float4 *>(a_lo + off) = l;
-                  }
-                }
-              }
-              fence_proxy_async();  // every lane publishes its own generic-proxy stores to the tensor core
-              __syncwarp();
-              if (lane == 0) mbar_arrive(bar_full + 8 * s);
-              continue;
-            }
-          }
           if (lane == 0) {
-            stage_flags[s] = ((k == (int)first_k && sl == 0) ? 1 : 0) | ((k == (int)last_k && sl == slices - 1) ? 2 : 0);
+            stage_flags[s] = ((k == (int)first_k && sl == 0) ? kFlagFirst : 0) |
+                             ((k == (int)last_k && sl == slices - 1) ? kFlagLast : 0);
             const uint32_t wb = w_stage_bytes * (kTf32 ? 2 : 1);
             const uint8_t *wsrc = wpacked + ((size_t)k * slices + sl) * wb;
             const uint32_t w_u32 = a_u32 + (kTf32 ? 2 : 1) * C::kABytes;
@@ -424,6 +433,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
           }
         }
       }
+      tile = tile_after;
     }
   } else if (warp == kMmaWarp) {
     // =============================== MMA issuer ===============================
@@ -442,48 +452,50 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
     uint64_t a_desc = a_desc0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+    for (;;) {
+      mbar_wait(bar_full + 8 * s, phase);
+      const int flags = stage_flags[s];
+      if (flags & (kFlagFirst | kFlagStop)) mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);  // accumulator drained
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * N);
-      bool last = false;
-      while (!last) {
-        mbar_wait(bar_full + 8 * s, phase);
-        tc_fence_after();
-        const int flags = stage_flags[s];
-        last = (flags & 2) != 0;
-        if (lane == 0) {
-          const uint64_t b_desc = a_desc + kWOff;
-          uint32_t accumulate = (flags & 1) ? 0u : 1u;
-          if (dbg != 4) {
+      if (flags & kFlagStop) {
+        if (lane == 0) mbar_arrive(bar_tfull + 8 * acc);  // wakes the epilogue, which finds the sentinel tile id
+        break;
+      }
+      const bool last = (flags & kFlagLast) != 0;
+      if (lane == 0) {
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * N);
+        const uint64_t b_desc = a_desc + kWOff;
+        uint32_t accumulate = (flags & kFlagFirst) ? 0u : 1u;
+        if (dbg != 4) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (j < ksteps) {
-                const uint64_t adv = (uint64_t)(2 * j);  // 32 bytes of K
-                if constexpr (kTf32) {
-                  tc_mma<true>(d_tmem, a_desc + kALoOff + adv, b_desc + adv, idesc, accumulate);
-                  tc_mma<true>(d_tmem, a_desc + adv, b_desc + w_lo_off + adv, idesc, 1u);
-                  tc_mma<true>(d_tmem, a_desc + adv, b_desc + adv, idesc, 1u);
-                } else {
-                  tc_mma<false>(d_tmem, a_desc + adv, b_desc + adv, idesc, accumulate);
-                }
-                accumulate = 1u;
+          for (int j = 0; j < 4; ++j) {
+            if (j < ksteps) {
+              const uint64_t adv = (uint64_t)(2 * j);  // 32 bytes of K
+              if constexpr (kTf32) {
+                tc_mma<true>(d_tmem, a_desc + kALoOff + adv, b_desc + adv, idesc, accumulate);
+                tc_mma<true>(d_tmem, a_desc + adv, b_desc + w_lo_off + adv, idesc, 1u);
+                tc_mma<true>(d_tmem, a_desc + adv, b_desc + adv, idesc, 1u);
+              } else {
+                tc_mma<false>(d_tmem, a_desc + adv, b_desc + adv, idesc, accumulate);
               }
+              accumulate = 1u;
             }
           }
-          tc_commit(bar_empty + 8 * s);              // smem stage reusable once these MMAs retire
-          if (last) tc_commit(bar_tfull + 8 * acc);  // accumulator complete
         }
-        __syncwarp();
-        a_desc += kStageStep;
-        if (++s == (uint32_t)C::kStages) {
-          s = 0;
-          phase ^= 1;
-          a_desc = a_desc0;
-        }
+        tc_commit(bar_empty + 8 * s);              // smem stage reusable once these MMAs retire
+        if (last) tc_commit(bar_tfull + 8 * acc);  // accumulator complete
       }
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
+      __syncwarp();
+      if (last) {
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+      a_desc += kStageStep;
+      if (++s == (uint32_t)C::kStages) {
+        s = 0;
+        phase ^= 1;
+        a_desc = a_desc0;
+      }
     }
   } else if (warp > kMmaWarp) {
     // =============================== fp32 split (warps 13-16, 3xTF32 kernels only) ===============================
@@ -493,13 +505,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
     if constexpr (kTf32) {
       const int t = threadIdx.x - kTcThreadsBase;
       const int units = (int)(a_stage_bytes >> 4) / kXformThreads;  // 16-byte units per thread: 8, 4 or 2
-      uint32_t done = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        bool last = false;
-        while (!last) {
-          const uint32_t s = done % C::kStages;
-          mbar_wait(bar_landed + 8 * s, (done / C::kStages) & 1);
-          last = (stage_flags[s] & 2) != 0;
+      for (uint32_t done = 0;; ++done) {
+        const uint32_t s = done % C::kStages;
+        mbar_wait(bar_landed + 8 * s, (done / C::kStages) & 1);
+        const bool stop = (stage_flags[s] & kFlagStop) != 0;
+        if (!stop) {
           uint8_t *a_hi = stage_base + (size_t)s * C::kStageBytes;
           uint8_t *a_lo = a_hi + C::kABytes;
 #pragma unroll
@@ -515,18 +525,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
             }
           }
           fence_proxy_async();
-          mbar_arrive(bar_full + 8 * s);
-          ++done;
         }
+        mbar_arrive(bar_full + 8 * s);
+        if (stop) break;
       }
     }
   } else {
     // =============================== epilogue (warps 0-3) ===============================
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (uint32_t seq = 0;; ++seq) {
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
+      const int tile = tile_ring[seq % kTileRing];
+      if (tile < 0) break;
       // sorted position -> output row (identity without a row order from fv2p_sort_rows_by_mask)
       const int srow = tile * kTileM + warp * 32 + lane;
       const int row = srow < n_out ? (row_perm ? __ldg(&row_perm[srow]) : srow) : n_out;
@@ -601,6 +613,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
   }
   tc_fence_before();
   __syncthreads();
+  if (sched && threadIdx.x == 0) {
+    // the last CTA to leave re-arms the scheduler words for the next launch that uses them
+    __threadfence();
+    if (atomicAdd(&sched[1], 1) == (int)gridDim.x - 1) {
+      sched[0] = 0;
+      sched[1] = 0;
+    }
+  }
   if (warp == kMmaWarp) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::kTmemCols)
@@ -698,7 +718,8 @@ int make_feature_map(CUtensorMap *map, const void *features, int64_t rows, int c
 
 template <bool kTf32, int N>
 int launch_one(const void *features, int64_t feat_rows, const void *weight, const int *nbr, int64_t nbr_stride,
-               const int *row_perm, int kvol, int64_t n_out_cap, const int *n_out_dev, int cin, const Epilogue &ep, cudaStream_t stream) {
+               const int *row_perm, const int *tile_order, int *sched, int kvol, int64_t n_out_cap,
+               const int *n_out_dev, int cin, const Epilogue &ep, cudaStream_t stream) {
   using C = Cfg<kTf32, N>;
   static bool configured = false;
   if (!configured) {
@@ -712,26 +733,25 @@ int launch_one(const void *features, int64_t feat_rows, const void *weight, cons
   int st = make_feature_map(&map, features, feat_rows, cin, kTf32);
   if (st) return st;
   // Measured on B200 (profiles/r1_notes.md): the TMA gather wins for fp32 rows of 128 bytes and more (the LSU
-  // path also has to feed the transform warps there), the swizzled cp.async gather everywhere else; the
-  // register-split producer (mode 2) never won (0.182 vs 0.172 ms on 64->64, 0.248 vs 0.221 ms on 128->128).
-  const int use_tma = g_tc_gather_mode >= 0 ? ((g_tc_gather_mode == 2 && !kTf32) ? 0 : g_tc_gather_mode)
-                                            : ((kTf32 && cin >= 32) ? 1 : 0);
+  // path also has to feed the transform warps there), the swizzled cp.async gather everywhere else.  (A third
+  // producer, LDG + hi/lo split in registers + STS without transform warps, never won and was removed:
+  // 0.182 vs 0.172 ms on 64->64, 0.248 vs 0.221 ms on 128->128.)
+  const int use_tma = g_tc_gather_mode >= 0 ? g_tc_gather_mode : ((kTf32 && cin >= 32) ? 1 : 0);
   int64_t tiles = (n_out_cap + kTileM - 1) / kTileM;
   int grid = (int)(tiles < sm_count() ? tiles : sm_count());
   if (grid < 1) grid = 1;
-  const int block = (kTf32 && use_tma == 2) ? kTcThreadsBase : C::kThreads;  // no transform warps in mode 2
-  conv_tc_kernel<kTf32, N><<<grid, block, C::kSmemBytes, stream>>>(
-      map, features, static_cast<const uint8_t *>(weight), nbr, nbr_stride, row_perm, kvol, n_out_cap, n_out_dev, cin,
-      (int)feat_rows, use_tma, ep);
+  conv_tc_kernel<kTf32, N><<<grid, C::kThreads, C::kSmemBytes, stream>>>(
+      map, features, static_cast<const uint8_t *>(weight), nbr, nbr_stride, row_perm, tile_order, sched, kvol,
+      n_out_cap, n_out_dev, cin, (int)feat_rows, use_tma, ep);
   return cuda_status(cudaGetLastError(), "conv_fwd(tc)");
 }
 
 }  // namespace
 
 int launch_conv_tc(const void *features, int64_t feat_rows, const void *weight, const int *nbr, int64_t nbr_stride,
-                   const int *row_perm, int kvol, int64_t n_out_cap, const int *n_out_dev, int cin, int cout, const float *bias,
-                   const float *scale, const float *shift, const void *residual, int relu, int mode, void *out,
-                   cudaStream_t stream) {
+                   const int *row_perm, const int *tile_order, int *sched, int kvol, int64_t n_out_cap,
+                   const int *n_out_dev, int cin, int cout, const float *bias, const float *scale, const float *shift,
+                   const void *residual, int relu, int mode, void *out, cudaStream_t stream) {
   if (!tc_shape_ok(cin, cout)) {
     set_error("conv_fwd: tensor-core modes need cin in {16,32,64,128,256} and cout in {16,32,64,128} (got %d->%d)",
               cin, cout);
@@ -744,10 +764,10 @@ int launch_conv_tc(const void *features, int64_t feat_rows, const void *weight, 
   Epilogue ep{bias, scale, shift, residual, out, relu};
   const bool tf32 = mode == FV2P_MODE_TF32X3_TC;
 #define FV2P_TC(NN)                                                                                            \
-  return tf32 ? launch_one<true, NN>(features, feat_rows, weight, nbr, nbr_stride, row_perm, kvol, n_out_cap,  \
-                                     n_out_dev, cin, ep, stream)                                               \
-              : launch_one<false, NN>(features, feat_rows, weight, nbr, nbr_stride, row_perm, kvol, n_out_cap, \
-                                      n_out_dev, cin, ep, stream)
+  return tf32 ? launch_one<true, NN>(features, feat_rows, weight, nbr, nbr_stride, row_perm, tile_order, sched,  \
+                                     kvol, n_out_cap, n_out_dev, cin, ep, stream)                                \
+              : launch_one<false, NN>(features, feat_rows, weight, nbr, nbr_stride, row_perm, tile_order, sched, \
+                                      kvol, n_out_cap, n_out_dev, cin, ep, stream)
   switch (cout) {
     case 16: FV2P_TC(16);
     case 32: FV2P_TC(32);
@@ -762,7 +782,7 @@ int launch_conv_tc(const void *features, int64_t feat_rows, const void *weight, 
 using namespace fv2p;
 
 extern "C" int fv2p_tc_gather_mode(int mode) {
-  g_tc_gather_mode = mode < 0 ? -1 : (mode > 2 ? 2 : mode);
+  g_tc_gather_mode = mode < 0 ? -1 : (mode > 1 ? 1 : mode);
   return FV2P_OK;
 }
 

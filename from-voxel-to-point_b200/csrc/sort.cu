@@ -122,9 +122,76 @@ permute_nbr_kernel(const int *__restrict__ nbr, int64_t nbr_stride, int kvol, co
   }
 }
 
+// Tile weights for the conv's tile scheduler: weight[t] = number of offsets that have a neighbour in sorted rows
+// [128 t, 128 t + 128) = pipeline stages (per 128-byte slice) the conv spends on the tile.  One warp per tile.
+constexpr int kConvTile = 128;
+
+__global__ void __launch_bounds__(kThreads)
+tile_weight_kernel(const uint32_t *__restrict__ keys_sorted, const int *n_dev, int64_t n_cap, int *weights) {
+  const int n = live_n(n_dev, n_cap);
+  const int n_tiles = (n + kConvTile - 1) / kConvTile;
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < n_tiles; t += warps) {
+    uint32_t m = 0;
+#pragma unroll
+    for (int q = 0; q < kConvTile / 32; ++q) {
+      const int i = t * kConvTile + q * 32 + lane;
+      if (i < n) m |= keys_sorted[i];
+    }
+    m = __reduce_or_sync(0xFFFFFFFFu, m);
+    if (lane == 0) weights[t] = __popc(m);
+  }
+}
+
+// tile_order = the tiles by descending weight (counting sort over the 33 possible weights, one CTA).  The conv hands
+// tiles to its CTAs in this order from an atomic counter, i.e. longest-processing-time-first list scheduling.
+// Ties are placed in tile order (per-warp ballots under a block-ordered cursor), so the order is deterministic.
+__global__ void __launch_bounds__(1024)
+tile_rank_kernel(const int *__restrict__ weights, const int *n_dev, int64_t n_cap, int *tile_order) {
+  __shared__ int hist[33], base[33];
+  __shared__ int warp_cnt[32][33];
+  const int n = live_n(n_dev, n_cap);
+  const int n_tiles = (n + kConvTile - 1) / kConvTile;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x < 33) hist[threadIdx.x] = 0;
+  __syncthreads();
+  for (int t = threadIdx.x; t < n_tiles; t += blockDim.x) atomicAdd(&hist[weights[t]], 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int w = 32; w >= 0; --w) {
+      base[w] = run;
+      run += hist[w];
+    }
+  }
+  __syncthreads();
+  for (int t0 = 0; t0 < n_tiles; t0 += blockDim.x) {
+    const int t = t0 + threadIdx.x;
+    const int w = t < n_tiles ? weights[t] : -1;
+    const unsigned peers = __match_any_sync(0xFFFFFFFFu, w);
+    for (int b = lane; b < 33; b += 32) warp_cnt[warp][b] = 0;
+    __syncwarp();
+    if (w >= 0 && lane == __ffs(peers) - 1) warp_cnt[warp][w] = __popc(peers);
+    __syncthreads();
+    if (w >= 0) {
+      int before = 0;
+      for (int q = 0; q < warp; ++q) before += warp_cnt[q][w];
+      tile_order[base[w] + before + __popc(peers & ((1u << lane) - 1u))] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x < 33) {
+      int add = 0;
+      for (int q = 0; q < 32; ++q) add += warp_cnt[q][threadIdx.x];
+      base[threadIdx.x] += add;
+    }
+    __syncthreads();
+  }
+}
+
 struct SortWorkspace {
   uint32_t *keys_a, *keys_b;
-  int *vals_b, *counts, *totals;
+  int *vals_b, *counts, *totals, *weights;
   int n_chunks;
   size_t bytes;
 };
@@ -140,6 +207,7 @@ SortWorkspace carve(void *ws, int64_t n_cap) {
   w.vals_b = c.take<int>(n);
   w.counts = c.take<int>((size_t)kBins * w.n_chunks);
   w.totals = c.take<int>(kBins);
+  w.weights = c.take<int>(n / kConvTile + 1);
   w.bytes = c.used + 256;
   return w;
 }
@@ -156,7 +224,8 @@ extern "C" size_t fv2p_sort_rows_workspace_bytes(int64_t n_cap) {
 
 extern "C" int fv2p_sort_rows_by_mask(const int32_t *nbr, int64_t nbr_stride, int kvol, int64_t n_cap,
                                       const int32_t *n_dev, int32_t *perm, int32_t *nbr_sorted,
-                                      int64_t sorted_stride, void *workspace, size_t workspace_bytes,
+                                      int64_t sorted_stride, int32_t *tile_order, void *workspace,
+                                      size_t workspace_bytes,
                                       fv2p_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   FV2P_REQUIRE(kvol >= 1 && kvol <= FV2P_MAX_KVOL, "sort_rows: kernel volume %d out of range", kvol);
@@ -193,6 +262,10 @@ extern "C" int fv2p_sort_rows_by_mask(const int32_t *nbr, int64_t nbr_stride, in
   if (nbr_sorted)
     permute_nbr_kernel<<<grid, kThreads, 0, stream>>>(nbr, nbr_stride, kvol, perm, n_dev, n_cap, nbr_sorted,
                                                       sorted_stride);
+  if (tile_order) {  // k_src holds the sorted masks
+    tile_weight_kernel<<<grid, kThreads, 0, stream>>>(k_src, n_dev, n_cap, w.weights);
+    tile_rank_kernel<<<1, 1024, 0, stream>>>(w.weights, n_dev, n_cap, tile_order);
+  }
   FV2P_LAUNCH_CHECK("sort_rows_by_mask");
   return FV2P_OK;
 }

@@ -142,6 +142,8 @@ class BackboneEngine(object):
     """Runs a traced backbone.  precision: 'fp32' (fp32 storage, fp32-accurate arithmetic) or 'bf16'
     (bf16 storage, fp32 accumulation; the entry layer reads fp32 voxel features)."""
 
+    SIDE_STREAMS = 4
+
     def __init__(self, net, precision="fp32", materialize_pairs=True, use_tensor_cores=True, sort_rows=True,
                  concurrent=True):
         traced = trace_backbone(net)
@@ -237,12 +239,17 @@ class BackboneEngine(object):
             if self.sort_rows:
                 d["perm"] = torch.empty((cout_cap,), dtype=torch.int32, device=device)
                 d["nbr_sorted"] = torch.empty((bk.kvol, cout_cap), dtype=torch.int32, device=device)
+                d["tile_order"] = torch.empty((cout_cap // 128 + 1,), dtype=torch.int32, device=device)
                 ws_bytes = max(ws_bytes, lib.fv2p_sort_rows_workspace_bytes(cout_cap))
             books[bk.key] = d
             ws_bytes = max(ws_bytes, lib.fv2p_rulebook_workspace_bytes(cin_cap, cout_cap, bk.kvol))
         a["books"] = books
+        # two scheduler words per conv step (tile counter, CTAs done); zero between launches, the kernel re-arms them
+        a["sched"] = torch.zeros((len(self.steps), 2), dtype=torch.int32, device=device)
         a["ws"] = torch.empty(ws_bytes + 1024, dtype=torch.uint8, device=device)       # strided chain
-        a["ws_sub"] = torch.empty(ws_bytes + 1024, dtype=torch.uint8, device=device)   # submanifold books + sorts
+        # submanifold books + mask sorts: one workspace per side stream
+        a["ws_side"] = [torch.empty(ws_bytes + 1024, dtype=torch.uint8, device=device)
+                        for _ in range(self.SIDE_STREAMS)]
         # feature buffers with liveness-based reuse
         bufs, free, owner = {}, [], {}
         for i, st in enumerate(self.steps):
@@ -289,10 +296,10 @@ class BackboneEngine(object):
             main = torch.cuda.current_stream(device)
             if self.concurrent:
                 if self._side is None or self._side[0].device != device:
-                    self._side = (torch.cuda.Stream(device=device), torch.cuda.Stream(device=device))
-                s_sub, s_conv = self._side
+                    self._side = [torch.cuda.Stream(device=device) for _ in range(self.SIDE_STREAMS + 1)]
+                side, s_conv = self._side[:-1], self._side[-1]
             else:
-                s_sub = s_conv = main
+                side, s_conv = [main], main
             counts[len(caps):].zero_()
             if n0_dev is None:
                 counts[0:1].fill_(cap0)
@@ -306,11 +313,13 @@ class BackboneEngine(object):
             tc_modes = (_lib.MODE_BF16_TC, _lib.MODE_TF32X3_TC)
             tc_books = {st_.key for st_, p in zip(self.steps, prm) if p["mode"] in tc_modes}
 
-            # Three dependency chains, forked from and joined back into the caller's stream (so the whole thing is
-            # still one stream-ordered step, and one CUDA graph when captured):
+            # Dependency chains, forked from and joined back into the caller's stream (so the whole thing is still one
+            # stream-ordered step, and one CUDA graph when captured):
             #   main   the strided rulebooks, level by level (each needs the previous level's output coordinates)
-            #   s_sub  the submanifold rulebooks and every mask sort (leaves of that chain)
-            #   s_conv the feature pass, each layer waiting only for its own rulebook
+            #   side   the submanifold rulebooks and every mask sort: leaves of that chain, independent of each
+            #          other, dealt round-robin to SIDE_STREAMS streams (each with its own workspace)
+            #   s_conv the feature pass, each layer waiting only for what it reads (the sorted set for the
+            #          tensor-core kernels, the plain neighbour map otherwise)
             # The geometry kernels are small and latency bound, so they hide behind the conv kernels.
             def mark(stream):
                 ev = torch.cuda.Event()
@@ -318,21 +327,24 @@ class BackboneEngine(object):
                 return ev
 
             level_ready = {0: mark(main)}
-            book_ready = {}
-            for bk in self.books:
+            book_built, book_sorted = {}, {}
+            for j, bk in enumerate(self.books):
                 d = a["books"][bk.key]
                 pairs = d["pairs"]
+                s_side = side[j % len(side)]
+                ws_side = a["ws_side"][j % len(side)]
                 if bk.subm:
-                    s_sub.wait_event(level_ready[bk.in_level])
-                    with torch.cuda.stream(s_sub):
+                    s_side.wait_event(level_ready[bk.in_level])
+                    with torch.cuda.stream(s_side):
                         st = lib.fv2p_rulebook_subm(_lib.ptr(level_ind[bk.in_level]), level_cap[bk.in_level],
                                                     n_ptr[bk.in_level], int(batch_size),
                                                     _lib.i32x3(self.level_shapes[bk.in_level]), _lib.i32x3(bk.ksize),
                                                     _lib.i32x3(bk.dil), _lib.ptr(pairs),
                                                     pairs.shape[2] if pairs is not None else 0,
                                                     _lib.ptr(d["pair_num"]) if pairs is not None else None,
-                                                    _lib.ptr(d["nbr"]), d["nbr"].shape[1], _lib.ptr(a["ws_sub"]),
-                                                    a["ws_sub"].numel(), _lib.stream_ptr(device))
+                                                    _lib.ptr(d["nbr"]), d["nbr"].shape[1], _lib.ptr(ws_side),
+                                                    ws_side.numel(), _lib.stream_ptr(device))
+                    book_built[bk.key] = mark(s_side)
                 else:
                     with torch.cuda.stream(main):
                         st = lib.fv2p_rulebook_conv(_lib.ptr(level_ind[bk.in_level]), level_cap[bk.in_level],
@@ -345,46 +357,55 @@ class BackboneEngine(object):
                                                     _lib.ptr(d["pair_num"]) if pairs is not None else None,
                                                     _lib.ptr(d["nbr"]), d["nbr"].shape[1], status_ptr,
                                                     _lib.ptr(a["ws"]), a["ws"].numel(), _lib.stream_ptr(device))
-                    level_ready[bk.out_level] = mark(main)
-                    s_sub.wait_event(level_ready[bk.out_level])
+                    level_ready[bk.out_level] = book_built[bk.key] = mark(main)
+                    s_side.wait_event(book_built[bk.key])
                 _lib.check(st, "rulebook[%s]" % bk.key)
                 if self.sort_rows and bk.key in tc_books:
-                    with torch.cuda.stream(s_sub):
+                    with torch.cuda.stream(s_side):
                         st = lib.fv2p_sort_rows_by_mask(_lib.ptr(d["nbr"]), d["nbr"].shape[1], bk.kvol,
                                                         level_cap[bk.out_level], n_ptr[bk.out_level],
                                                         _lib.ptr(d["perm"]), _lib.ptr(d["nbr_sorted"]),
-                                                        d["nbr_sorted"].shape[1], _lib.ptr(a["ws_sub"]),
-                                                        a["ws_sub"].numel(), _lib.stream_ptr(device))
+                                                        d["nbr_sorted"].shape[1], _lib.ptr(d["tile_order"]),
+                                                        _lib.ptr(ws_side), ws_side.numel(), _lib.stream_ptr(device))
                     _lib.check(st, "sort_rows[%s]" % bk.key)
-                book_ready[bk.key] = mark(s_sub)
+                    book_sorted[bk.key] = mark(s_side)
             waited = set()
-            for st_, p in zip(self.steps, prm):
-                if st_.key not in waited:
-                    s_conv.wait_event(book_ready[st_.key])
-                    waited.add(st_.key)
-                src = voxel_features if st_.in_buf < 0 else a["bufs"][st_.in_buf]
-                res = a["bufs"][st_.res_buf] if st_.res_buf is not None else None
-                out = a["bufs"][st_.out_buf]
-                nbr, perm = self.conv_operands(a, st_, p)
-                w = p["packed"] if p["packed"] is not None else p["w"]
+            for i, (st_, p) in enumerate(zip(self.steps, prm)):
+                needs = book_sorted if self.conv_operands(a, st_, p)[1] is not None else book_built
+                if (st_.key, id(needs)) not in waited:
+                    s_conv.wait_event(needs[st_.key])
+                    waited.add((st_.key, id(needs)))
                 with torch.cuda.stream(s_conv):
-                    rc = lib.fv2p_conv_fwd(_lib.ptr(src), src.shape[0], _lib.ptr(w), _lib.ptr(nbr), nbr.shape[1],
-                                           _lib.ptr(perm), st_.kvol, level_cap[st_.out_level], n_ptr[st_.out_level],
-                                           st_.cin, st_.cout, _lib.ptr(p["bias"]), _lib.ptr(p["scale"]),
-                                           _lib.ptr(p["shift"]), _lib.ptr(res), int(st_.relu), p["mode"],
-                                           _lib.ptr(out), _lib.stream_ptr(device))
-                _lib.check(rc, "conv_fwd[%s]" % st_.key)
+                    self.run_conv_step(a, i, p, voxel_features, cap0)
             if self.concurrent:  # join: everything this step enqueued is ordered before what the caller does next
-                main.wait_event(mark(s_sub))
-                main.wait_event(mark(s_conv))
+                for s_ in side + [s_conv]:
+                    main.wait_event(mark(s_))
         return a
 
     def conv_operands(self, a, step, prm):
-        """(neighbour map, row order) a conv step reads: the mask-sorted pair for the tensor-core modes."""
+        """(neighbour map, row order, tile order) a conv step reads: the mask-sorted set for the tensor-core modes."""
         d = a["books"][step.key]
         if self.sort_rows and prm["mode"] in (_lib.MODE_BF16_TC, _lib.MODE_TF32X3_TC):
-            return d["nbr_sorted"], d["perm"]
-        return d["nbr"], None
+            return d["nbr_sorted"], d["perm"], d["tile_order"]
+        return d["nbr"], None, None
+
+    def run_conv_step(self, a, i, prm, voxel_features, cap0):
+        """Enqueues conv step ``i`` (fv2p_conv_fwd) on the current stream; its rulebook must already be enqueued."""
+        st_ = self.steps[i]
+        src = voxel_features if st_.in_buf < 0 else a["bufs"][st_.in_buf]
+        res = a["bufs"][st_.res_buf] if st_.res_buf is not None else None
+        out = a["bufs"][st_.out_buf]
+        nbr, perm, order = self.conv_operands(a, st_, prm)
+        w = prm["packed"] if prm["packed"] is not None else prm["w"]
+        tc = prm["mode"] in (_lib.MODE_BF16_TC, _lib.MODE_TF32X3_TC)
+        cap = cap0 if st_.out_level == 0 else a["caps"][st_.out_level]
+        rc = _lib.load().fv2p_conv_fwd(
+            _lib.ptr(src), src.shape[0], _lib.ptr(w), _lib.ptr(nbr), nbr.shape[1], _lib.ptr(perm), _lib.ptr(order),
+            _lib.ptr(a["sched"][i]) if tc else None, st_.kvol, cap,
+            _lib.ctypes.c_void_p(a["counts"].data_ptr() + 4 * st_.out_level), st_.cin, st_.cout,
+            _lib.ptr(prm["bias"]), _lib.ptr(prm["scale"]), _lib.ptr(prm["shift"]), _lib.ptr(res), int(st_.relu),
+            prm["mode"], _lib.ptr(out), _lib.stream_ptr(a["device"]))
+        _lib.check(rc, "conv_fwd[%s]" % st_.key)
 
     def collect(self, a, voxel_coords, batch_size, sync=True):
         """One D2H copy of the row counts, then correctly shaped views (valid until the next launch)."""

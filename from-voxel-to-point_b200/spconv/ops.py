@@ -133,27 +133,34 @@ def pack_weight(weight_flat, mode):
     return packed
 
 
-def sort_rows_by_mask(nbr, num_activate_out=None):
-    """fv2p_sort_rows_by_mask: (perm [Nout], nbr_sorted [K,Nout]) for the tensor-core conv modes."""
+def sort_rows_by_mask(nbr, num_activate_out=None, return_tile_order=False):
+    """fv2p_sort_rows_by_mask: (perm [Nout], nbr_sorted [K,Nout]) for the tensor-core conv modes, plus the
+    128-row tiles by descending number of active offsets (``tile_order``) if asked for."""
     dev = _lib.require_device(nbr)
     kvol = nbr.shape[0]
     n = int(nbr.shape[1] if num_activate_out is None else num_activate_out)
     assert nbr.stride(1) == 1
     perm = torch.empty((max(n, 1),), dtype=torch.int32, device=nbr.device)
     nbr_sorted = torch.empty((kvol, max(n, 1)), dtype=torch.int32, device=nbr.device)
+    order = torch.empty(((n + 127) // 128 + 1,), dtype=torch.int32, device=nbr.device) if return_tile_order else None
     lib = _lib.load()
     ws = _lib.Workspace.get(nbr.device, lib.fv2p_sort_rows_workspace_bytes(n), "sort")
     with torch.cuda.device(dev):
         st = lib.fv2p_sort_rows_by_mask(_lib.ptr(nbr), nbr.stride(0), kvol, n, None, _lib.ptr(perm),
-                                        _lib.ptr(nbr_sorted), nbr_sorted.stride(0), _lib.ptr(ws), ws.numel(),
-                                        _lib.stream_ptr(nbr.device))
+                                        _lib.ptr(nbr_sorted), nbr_sorted.stride(0), _lib.ptr(order), _lib.ptr(ws),
+                                        ws.numel(), _lib.stream_ptr(nbr.device))
     _lib.check(st, "sort_rows_by_mask")
+    if return_tile_order:
+        return perm[:n], nbr_sorted[:, :n], order[:(n + 127) // 128]
     return perm[:n], nbr_sorted[:, :n]
 
 
 def conv_forward(features, weight_flat, nbr, num_activate_out, bias=None, scale=None, shift=None, residual=None,
-                 relu=False, mode=None, n_out_dev=None, out=None, row_perm=None):
-    """fv2p_conv_fwd: out = act((sum_k X[nbr[k]] W[k] + bias) * scale + shift + residual)."""
+                 relu=False, mode=None, n_out_dev=None, out=None, row_perm=None, tile_order=None, dynamic=True):
+    """fv2p_conv_fwd: out = act((sum_k X[nbr[k]] W[k] + bias) * scale + shift + residual).
+
+    ``row_perm`` / ``tile_order`` come from sort_rows_by_mask (tensor-core modes); ``dynamic`` hands the tiles to the
+    CTAs from an atomic counter (two zeroed scheduler words per call) instead of round-robin."""
     dev = _lib.require_device(features)
     if mode is None:
         mode = _lib.MODE_F32 if features.dtype == torch.float32 else _lib.MODE_BF16_SIMT
@@ -169,10 +176,12 @@ def conv_forward(features, weight_flat, nbr, num_activate_out, bias=None, scale=
     if out is None:
         out = torch.empty((n_cap, cout), dtype=out_dtype, device=features.device)
     assert nbr.stride(1) == 1 and out.is_contiguous() and features.is_contiguous()
+    tc = mode in (_lib.MODE_BF16_TC, _lib.MODE_TF32X3_TC)
+    sched = torch.zeros((2,), dtype=torch.int32, device=features.device) if (tc and dynamic) else None
     with torch.cuda.device(dev):
         st = _lib.load().fv2p_conv_fwd(_lib.ptr(features), features.shape[0], _lib.ptr(weight_flat), _lib.ptr(nbr),
-                                       nbr.stride(0), _lib.ptr(row_perm), kvol,
-                                       n_cap, _lib.ptr(n_out_dev), cin, cout, _lib.ptr(bias), _lib.ptr(scale),
+                                       nbr.stride(0), _lib.ptr(row_perm), _lib.ptr(tile_order), _lib.ptr(sched),
+                                       kvol, n_cap, _lib.ptr(n_out_dev), cin, cout, _lib.ptr(bias), _lib.ptr(scale),
                                        _lib.ptr(shift), _lib.ptr(residual), int(relu), int(mode), _lib.ptr(out),
                                        _lib.stream_ptr(features.device))
     _lib.check(st, "conv_fwd")

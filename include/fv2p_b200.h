@@ -168,12 +168,17 @@ FV2P_API int fv2p_pairs_to_nbr(const int32_t *pairs, const int32_t *pair_num, in
  *   row_perm  NULL, or the row order from fv2p_sort_rows_by_mask (tensor-core modes only): `nbr` is then the map
  *             permuted the same way (nbr_sorted) and sorted position t writes output row row_perm[t]; results are
  *             identical either way
+ *   tile_order NULL, or fv2p_sort_rows_by_mask's tile list (needs row_perm): the order in which the 128-row tiles are
+ *             handed out (most active offsets first)
+ *   sched     NULL (tiles dealt round-robin to the CTAs), or two device int32 words, zero on entry, that the
+ *             tensor-core kernel uses as its tile counter and leaves zeroed again; one pair per launch that may be
+ *             in flight at the same time
  *   n_out_cap rows of `out`/`nbr` columns; live count *n_out_dev if given
  * ------------------------------------------------------------------------------------------- */
 FV2P_API int fv2p_conv_fwd(const void *features, int64_t n_in_cap, const void *weight, const int32_t *nbr, int64_t nbr_stride,
-                  const int32_t *row_perm, int kvol, int64_t n_out_cap, const int32_t *n_out_dev, int cin, int cout,
-                  const float *bias, const float *scale, const float *shift, const void *residual,
-                  int relu, int mode, void *out, fv2p_stream_t stream);
+                  const int32_t *row_perm, const int32_t *tile_order, int32_t *sched, int kvol, int64_t n_out_cap,
+                  const int32_t *n_out_dev, int cin, int cout, const float *bias, const float *scale,
+                  const float *shift, const void *residual, int relu, int mode, void *out, fv2p_stream_t stream);
 
 /* Row order for the tensor-core conv: stable sort of the output rows by their neighbour mask (bit k = offset k has
  * a neighbour).  perm[t] = output row at sorted position t; nbr_sorted[k][t] = nbr[k][perm[t]] (optional).  Tiles
@@ -182,12 +187,11 @@ FV2P_API int fv2p_conv_fwd(const void *features, int64_t n_in_cap, const void *w
 FV2P_API size_t fv2p_sort_rows_workspace_bytes(int64_t n_cap);
 FV2P_API int fv2p_sort_rows_by_mask(const int32_t *nbr, int64_t nbr_stride, int kvol, int64_t n_cap,
                                     const int32_t *n_dev, int32_t *perm, int32_t *nbr_sorted,
-                                    int64_t sorted_stride, void *workspace, size_t workspace_bytes,
-                                    fv2p_stream_t stream);
+                                    int64_t sorted_stride, int32_t *tile_order, void *workspace,
+                                    size_t workspace_bytes, fv2p_stream_t stream);
 
 /* Producer of the gathered A tile in the tensor-core kernels: -1 = auto (default: measured best per shape),
- * 0 = LSU (swizzled cp.async), 1 = TMA (cp.async.bulk.tensor tile::gather4), 2 = fp32 kernels only: plain loads,
- * hi/lo split in registers, shared-memory stores (no transform warps).  Same results either way; a tuning
+ * 0 = LSU (swizzled cp.async), 1 = TMA (cp.async.bulk.tensor tile::gather4).  Same results either way; a tuning
  * knob kept for measurement (profiles/r1_notes.md).  Process-wide, not stream-ordered. */
 FV2P_API int fv2p_tc_gather_mode(int mode);
 

@@ -36,20 +36,11 @@ from fv2p_b200 import _lib  # noqa: E402
 eng, arena = hp.engine, h["arena"]
 prm = eng._prepare_params(dev)
 st, p = eng.steps[a.layer], prm[a.layer]
-caps = [h["vox"]["cap"]] + arena["caps"][1:]
-nbr, perm = eng.conv_operands(arena, st, p)
-src = h["vox"]["voxel_features"] if st.in_buf < 0 else arena["bufs"][st.in_buf]
-res = arena["bufs"][st.res_buf] if st.res_buf is not None else None
-out = arena["bufs"][st.out_buf]
-w = p["packed"] if p["packed"] is not None else p["w"]
+vf, cap0 = h["vox"]["voxel_features"], h["vox"]["cap"]
 flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
 for _ in range(a.repeat):
     flush.zero_()
-    rc = _lib.load().fv2p_conv_fwd(_lib.ptr(src), src.shape[0], _lib.ptr(w), _lib.ptr(nbr), nbr.shape[1], _lib.ptr(perm), st.kvol, caps[st.out_level],
-                                   _lib.ctypes.c_void_p(arena["counts"].data_ptr() + 4 * st.out_level), st.cin,
-                                   st.cout, _lib.ptr(p["bias"]), _lib.ptr(p["scale"]), _lib.ptr(p["shift"]),
-                                   _lib.ptr(res), int(st.relu), p["mode"], _lib.ptr(out), _lib.stream_ptr(dev))
-    _lib.check(rc, "conv_fwd")
+    eng.run_conv_step(arena, a.layer, p, vf, cap0)
 torch.cuda.synchronize()
 import ctypes  # noqa: E402
 for mode in a.debug:
@@ -60,10 +51,7 @@ for mode in a.debug:
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        lib.fv2p_conv_fwd(_lib.ptr(src), src.shape[0], _lib.ptr(w), _lib.ptr(nbr), nbr.shape[1], _lib.ptr(perm), st.kvol, caps[st.out_level],
-                          _lib.ctypes.c_void_p(arena["counts"].data_ptr() + 4 * st.out_level), st.cin, st.cout,
-                          _lib.ptr(p["bias"]), _lib.ptr(p["scale"]), _lib.ptr(p["shift"]), _lib.ptr(res), int(st.relu),
-                          p["mode"], _lib.ptr(out), _lib.stream_ptr(dev))
+        eng.run_conv_step(arena, a.layer, p, vf, cap0)
         e1.record()
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))

@@ -419,21 +419,28 @@ def test_mask_sorted_row_order_gives_identical_results():
                                                               return_nbr=True)
         nbr = nbr.contiguous()
         n_out = outids.shape[0]
-        perm, nbr_sorted = spconv.ops.sort_rows_by_mask(nbr, n_out)
+        perm, nbr_sorted, order = spconv.ops.sort_rows_by_mask(nbr, n_out, return_tile_order=True)
         m = nbr.cpu().numpy()
         masks = ((m >= 0).astype(np.int64) << np.arange(27)[:, None]).sum(0)
         expect = np.argsort(masks, kind="stable")
         assert np.array_equal(perm.cpu().numpy(), expect)
         assert np.array_equal(nbr_sorted.cpu().numpy(), m[:, expect])
+        # tile list: every 128-row tile once, by descending number of active offsets, ties in tile order
+        sm = masks[expect]
+        weight = np.array([bin(int(np.bitwise_or.reduce(sm[t:t + 128]))).count("1") for t in range(0, n_out, 128)])
+        assert np.array_equal(order.cpu().numpy(), np.argsort(-weight, kind="stable"))
         for mode, dt in ((_lib.MODE_TF32X3_TC, torch.float32), (_lib.MODE_BF16_TC, torch.bfloat16)):
             feats = cuda(rng.standard_normal((ind.shape[0], 64)).astype(np.float32), dt)
             w = cuda((rng.standard_normal((27, 64, 64)) / 40).astype(np.float32))
             packed = spconv.ops.pack_weight(w, mode)
             res = cuda(rng.standard_normal((n_out, 64)).astype(np.float32), dt)
             a = spconv.ops.conv_forward(feats, packed, nbr, n_out, residual=res, relu=True, mode=mode)
-            b = spconv.ops.conv_forward(feats, packed, nbr_sorted.contiguous(), n_out, residual=res, relu=True,
-                                        mode=mode, row_perm=perm.contiguous())
-            assert torch.equal(a, b)
+            for kw in (dict(), dict(tile_order=order.contiguous()), dict(dynamic=False)):
+                b = spconv.ops.conv_forward(feats, packed, nbr_sorted.contiguous(), n_out, residual=res, relu=True,
+                                            mode=mode, row_perm=perm.contiguous(), **kw)
+                assert torch.equal(a, b)
+            c = spconv.ops.conv_forward(feats, packed, nbr, n_out, residual=res, relu=True, mode=mode, dynamic=False)
+            assert torch.equal(a, c)
 
 
 def test_run_stream_matches_single_calls_and_graph_replay():
