@@ -171,8 +171,17 @@ __host__ __device__ constexpr uint32_t instr_desc(int n, bool tf32) {
          ((uint32_t)(kTileM >> 4) << 24);
 }
 
-// Timing experiments only (profiles/run_layer.py --debug): 4 = no MMA, 6 = no epilogue body.  0 in production.
+// Timing experiments only (profiles/run_layer.py --debug): 3 = no weight copy, 4 = no MMA, 6 = no epilogue body,
+// 7 = CTA 0 stamps %globaltimer at entry/exit into g_tc_stamps (profiles/timeline.py).  0 in production.
 __device__ int g_tc_debug = 0;
+constexpr int kStampSlots = 256;
+__device__ unsigned long long g_tc_stamps[kStampSlots][2];
+__device__ unsigned int g_tc_stamp_n = 0;
+__device__ __forceinline__ unsigned long long global_timer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 // Host-side choice of the A-tile producer: -1 = auto (measured best per shape), 0 = LSU (cp.async), 1 = TMA gather4.
 int g_tc_gather_mode = -1;
 
@@ -223,6 +232,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int dbg = g_tc_debug;
+  unsigned int stamp_slot = 0;
+  if (dbg == 7 && blockIdx.x == 0 && threadIdx.x == 0) {
+    stamp_slot = atomicAdd(&g_tc_stamp_n, 1u) % kStampSlots;
+    g_tc_stamps[stamp_slot][0] = global_timer();
+  }
   const bool use_tma = use_tma_arg == 1;
   int n_out = n_out_dev ? *n_out_dev : (int)n_out_cap;
   if (n_out > n_out_cap) n_out = (int)n_out_cap;
@@ -275,17 +289,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
     const int my_chunk = lane & (chunks - 1);
     const int my_row0 = lane >> cshift;
     const int rows_per_instr = 32 >> cshift;
-    // Next tile of this CTA, -1 when the work is used up: from the shared counter in `tile_order` (heaviest first),
-    // or round-robin when the caller gave no scheduler scratch.
-    int static_next = blockIdx.x;
+    // Next tile of this CTA (thread 0 only), -1 when the work is used up; positions index `tile_order` (heaviest
+    // first).  The ids are needed one to two tiles ahead of their use, and claiming that early from a shared
+    // counter lets the first CTAs grab several of the heaviest tiles each when there are only 1-2 tiles per CTA
+    // (measured: 3 x 108 stages on some CTAs, none on others, on the 206-tile layers).  So the first two rounds are
+    // dealt statically in snake order - position b, then 2G-1-b: the CTA with the lightest first tile gets the
+    // heaviest second one - and only the rest comes from the counter (round-robin without scheduler scratch).
+    int fetches = 0;
     auto fetch_tile = [&]() -> int {
+      const int G = (int)gridDim.x, b = (int)blockIdx.x;
       int i;
-      if (sched) {
-        i = atomicAdd(&sched[0], 1);
-      } else {
-        i = static_next;
-        static_next += gridDim.x;
-      }
+      if (fetches == 0) i = b;
+      else if (fetches == 1) i = 2 * G - 1 - b;
+      else if (sched) i = 2 * G + atomicAdd(&sched[0], 1);
+      else i = fetches * G + b;
+      ++fetches;
       if (i >= n_tiles) return -1;
       return tile_order ? __ldg(&tile_order[i]) : i;
     };
@@ -613,6 +631,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
   }
   tc_fence_before();
   __syncthreads();
+  if (dbg == 7 && blockIdx.x == 0 && threadIdx.x == 0) g_tc_stamps[stamp_slot][1] = global_timer();
   if (sched && threadIdx.x == 0) {
     // the last CTA to leave re-arms the scheduler words for the next launch that uses them
     __threadfence();
@@ -788,6 +807,16 @@ extern "C" int fv2p_tc_gather_mode(int mode) {
 
 extern "C" __attribute__((visibility("default"))) int fv2p_debug_poll(int v) {
   return (int)cudaMemcpyToSymbol(g_tc_poll, &v, sizeof(int));
+}
+
+// copies the stamp table to `out` ([256][2] u64), returns the number of stamps taken and resets the counter
+extern "C" __attribute__((visibility("default"))) int fv2p_debug_stamps(unsigned long long *out) {
+  unsigned int n = 0, zero = 0;
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(&n, g_tc_stamp_n, sizeof(n));
+  cudaMemcpyFromSymbol(out, g_tc_stamps, sizeof(unsigned long long) * kStampSlots * 2);
+  cudaMemcpyToSymbol(g_tc_stamp_n, &zero, sizeof(zero));
+  return (int)n;
 }
 
 extern "C" __attribute__((visibility("default"))) int fv2p_debug_set(int v) {
