@@ -114,6 +114,19 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32
 __device__ __forceinline__ void cp_async_arrive(uint32_t bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
+// One lane of the (converged) warp; ptxas keeps what the elected thread computes in uniform registers, which is what
+// the tcgen05 / bulk-copy instructions take (a `lane == 0` branch makes it wrap each of them in an ELECT loop).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred = 0, laneid = 0;
+  asm volatile(
+      "{\n\t.reg .b32 %%rx;\n\t.reg .pred %%px;\n\t"
+      "elect.sync %%rx|%%px, %2;\n\t"
+      "@%%px mov.s32 %1, 1;\n\t"
+      "mov.s32 %0, %%rx;\n\t}"
+      : "+r"(laneid), "+r"(pred)
+      : "r"(0xFFFFFFFFu));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -466,22 +479,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
     constexpr uint64_t kWOff = (uint64_t)(((kTf32 ? 2 : 1) * C::kABytes) >> 4);
     constexpr uint64_t kALoOff = (uint64_t)(C::kABytes >> 4);
     const uint64_t w_lo_off = (uint64_t)(w_stage_bytes >> 4);
-    uint32_t s = 0, phase = 0;
-    uint64_t a_desc = a_desc0;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (;;) {
-      mbar_wait(bar_full + 8 * s, phase);
-      const int flags = stage_flags[s];
-      if (flags & (kFlagFirst | kFlagStop)) mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);  // accumulator drained
-      tc_fence_after();
-      if (flags & kFlagStop) {
-        if (lane == 0) mbar_arrive(bar_tfull + 8 * acc);  // wakes the epilogue, which finds the sentinel tile id
-        break;
-      }
-      const bool last = (flags & kFlagLast) != 0;
-      if (lane == 0) {
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * N);
+    // One elected thread runs the whole loop on its own (waits included).  Re-electing per stage with the warp
+    // waiting and re-synchronising around the issue costs ~300 cycles per stage and ~50 per tcgen05.mma
+    // (profiles/micro/mma_issue_bench.cu: 4 MMAs + commit per stage take 760 cycles that way, 280 this way).
+    if (elect_one_sync()) {
+      uint32_t s = 0, phase = 0;
+      uint64_t a_desc = a_desc0;
+      uint32_t acc = 0, acc_phase = 0;
+      for (;;) {
+        mbar_wait(bar_full + 8 * s, phase);
+        const int flags = stage_flags[s];
+        if (flags & (kFlagFirst | kFlagStop)) mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);  // accumulator drained
+        tc_fence_after();
+        if (flags & kFlagStop) {
+          mbar_arrive(bar_tfull + 8 * acc);  // wakes the epilogue, which finds the sentinel tile id
+          break;
+        }
+        const uint32_t d_tmem = tmem_base + acc * (uint32_t)N;
         const uint64_t b_desc = a_desc + kWOff;
         uint32_t accumulate = (flags & kFlagFirst) ? 0u : 1u;
         if (dbg != 4) {
@@ -500,21 +514,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
             }
           }
         }
-        tc_commit(bar_empty + 8 * s);              // smem stage reusable once these MMAs retire
-        if (last) tc_commit(bar_tfull + 8 * acc);  // accumulator complete
-      }
-      __syncwarp();
-      if (last) {
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
-      }
-      a_desc += kStageStep;
-      if (++s == (uint32_t)C::kStages) {
-        s = 0;
-        phase ^= 1;
-        a_desc = a_desc0;
+        tc_commit(bar_empty + 8 * s);  // smem stage reusable once these MMAs retire
+        if (flags & kFlagLast) {
+          tc_commit(bar_tfull + 8 * acc);  // accumulator complete
+          acc ^= 1u;
+          if (acc == 0u) acc_phase ^= 1u;
+        }
+        a_desc += kStageStep;
+        if (++s == (uint32_t)C::kStages) {
+          s = 0;
+          phase ^= 1;
+          a_desc = a_desc0;
+        }
       }
     }
+    __syncwarp();
   } else if (warp > kMmaWarp) {
     // =============================== fp32 split (warps 13-16, 3xTF32 kernels only) ===============================
     // A_raw <- hi = rn_tf32(x), A_lo <- rn_tf32(x - hi), element-wise in place, so the swizzle is irrelevant here.
@@ -641,6 +655,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
     }
   }
   if (warp == kMmaWarp) {
+    __syncwarp();
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::kTmemCols)
                  : "memory");
