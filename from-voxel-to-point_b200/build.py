@@ -33,7 +33,7 @@ def build(force=False, verbose=False):
     os.makedirs(LIB_DIR, exist_ok=True)
     objs = []
     procs = []
-    flags = [f for f in FLAGS if not f.startswith("--use_fast_math")]
+    flags = [f for f in FLAGS if not f.startswith("--use_fast_math")] + os.environ.get("FV2P_EXTRA_NVCC_FLAGS", "").split()
     for src in SOURCES:
         obj = os.path.join(LIB_DIR, src.replace(".cu", ".o"))
         objs.append(obj)

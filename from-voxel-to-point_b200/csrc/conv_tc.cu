@@ -31,11 +31,15 @@
 //                 tile ids (one tile ahead of the neighbour prefetch, so the atomic's latency is hidden), publish
 //                 them through a small shared ring for the epilogue, and end the stream with a sentinel stage.
 //
-// fp32 path = 3xTF32: four transform warps (13-16) split the landed fp32 tile in place into
-// hi = rn_tf32(x) and a second tile lo = rn_tf32(x - hi); W is packed as hi/lo images, and each K step issues
-// A_lo*W_hi + A_hi*W_lo + A_hi*W_hi.  The dropped lo*lo term and the rounding of the lo parts are O(2^-22)
-// relative and unbiased.  What remains (measured 1-2e-5 at 27*128 terms) is the tensor core's truncating
-// fp32 accumulation, 5x inside the 1e-4 bar.
+// fp32 path = 3xTF32 with the A operand in tensor memory: the gathered fp32 tile lands in shared memory, four
+// transform warps (13-16, one per TMEM lane quadrant, one row per thread) split it into hi = rn_tf32(x) and
+// lo = rn_tf32(x - hi) and write both with tcgen05.st into a TMEM ring; W is packed as hi/lo shared-memory images, and
+// each K step issues A_lo*W_hi + A_hi*W_lo + A_hi*W_hi with A read from TMEM (tcgen05.mma [d], [a], b-desc).
+// Shared memory then only carries the raw tile once and the W slices: with both operands in shared memory the
+// kernel was bound by that pipe (16 KB landed + 48 KB split traffic + 12 x 8 KB operand reads per stage
+// ~ 1500 cycles at 128 B/cycle, against 768 cycles of tensor work at N=128).  The dropped lo*lo term and the
+// rounding of the lo parts are O(2^-22) relative and unbiased.  What remains (measured 1-2e-5 at 27*128 terms) is
+// the tensor core's truncating fp32 accumulation, 5x inside the 1e-4 bar.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -150,12 +154,35 @@ __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_
         : "memory");
   }
 }
+// A operand from tensor memory (lane = tile row, one 32-bit column per tf32 element), B from shared memory
+__device__ __forceinline__ void tc_mma_ts_tf32(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 16 consecutive 32-bit columns of this thread's TMEM lane (the warp covers its 32-lane quadrant)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t *r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
 // Round-to-nearest fp32 -> tf32 (kept in an fp32 container).  Truncation instead would bias every product the
 // same way and the bias grows linearly with the 27*Cin-term reduction; rounding keeps the split unbiased.
 __device__ __forceinline__ float tf32_rn(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
+}
+// The same rounding (nearest, ties away from zero, on the sign-magnitude bit pattern) with integer ALU instructions:
+// cvt runs on the quarter-rate conversion pipe, and the transform warps do two per element - 8192 per 16 KB stage,
+// ~512 cycles of that pipe alone.
+__device__ __forceinline__ float tf32_rn_alu(float x) {
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 // 16 consecutive fp32 accumulator columns of this thread's TMEM lane
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
@@ -190,6 +217,20 @@ __device__ int g_tc_debug = 0;
 constexpr int kStampSlots = 256;
 __device__ unsigned long long g_tc_stamps[kStampSlots][2];
 __device__ unsigned int g_tc_stamp_n = 0;
+#ifdef FV2P_TC_TIMERS
+// Role timers (profiling builds only: FV2P_EXTRA_NVCC_FLAGS=-DFV2P_TC_TIMERS python build.py --force).
+// Per CTA: 0 total, 1 stages, 2 tiles, 3 producer-warp-0 wait(empty), 4 producer-warp-0 issue, 5 producer tile
+// prologue, 6 MMA wait(full), 7 MMA wait(tmem empty), 8 MMA issue, 9 epilogue wait, 10 epilogue work,
+// 11 transform wait, 12 transform work.
+__device__ unsigned long long g_tc_timers[160][16];
+#define TC_T0() const long long tc_t0_ = clock64()
+#define TC_ACC(var) var += clock64() - tc_t0_
+#define TC_TIMER_DECL(var) long long var = 0
+#else
+#define TC_T0()
+#define TC_ACC(var)
+#define TC_TIMER_DECL(var)
+#endif
 __device__ __forceinline__ unsigned long long global_timer() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -202,12 +243,17 @@ template <bool kTf32, int N>
 struct Cfg {
   static constexpr int kABytes = kTileM * 128;  // one (up to) 128-byte slice per row
   static constexpr int kWBytes = N * 128;
-  static constexpr int kStageBytes = (kTf32 ? 2 : 1) * (kABytes + kWBytes);
+  // bf16: A tile + W slice.  fp32: the raw fp32 A tile + W_hi + W_lo; the split A operand lives in TMEM
+  // (kAColsPerStage columns per ring slot: hi in the first 32, lo in the next 32).
+  static constexpr int kStageBytes = kABytes + (kTf32 ? 2 : 1) * kWBytes;
   static constexpr int kNbrBytes = FV2P_MAX_KVOL * kTileM * 4;
-  static constexpr int kStagesRaw = (kSmemBudget - kNbrBytes - 1024) / kStageBytes;
+  static constexpr int kAColsPerStage = 64;
+  static constexpr int kStagesSmem = (kSmemBudget - kNbrBytes - 1024) / kStageBytes;
+  static constexpr int kStagesTmem = kTf32 ? (512 - 2 * N) / kAColsPerStage : kMaxStages;
+  static constexpr int kStagesRaw = kStagesSmem < kStagesTmem ? kStagesSmem : kStagesTmem;
   static constexpr int kStages = kStagesRaw > kMaxStages ? kMaxStages : kStagesRaw;
   static constexpr int kSmemBytes = kStages * kStageBytes + kNbrBytes + 1024 + 1024;  // + barriers + align slack
-  static constexpr int kTmemCols = 2 * N < 32 ? 32 : 2 * N;  // N in {16,32,64,128} -> power of two
+  static constexpr int kTmemCols = kTf32 ? 512 : (2 * N < 32 ? 32 : 2 * N);  // power of two
   static constexpr int kThreads = kTcThreadsBase + (kTf32 ? kXformThreads : 0);
   static_assert(kStages >= 3, "pipeline too shallow");
 };
@@ -245,6 +291,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int dbg = g_tc_debug;
+#ifdef FV2P_TC_TIMERS
+  const long long tc_cta_t0 = clock64();
+#endif
   unsigned int stamp_slot = 0;
   if (dbg == 7 && blockIdx.x == 0 && threadIdx.x == 0) {
     stamp_slot = atomicAdd(&g_tc_stamp_n, 1u) % kStampSlots;
@@ -334,6 +383,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
         nbr_next[q] = (tile >= 0 && k < kvol && row < n_out) ? __ldg(&nbr[(size_t)k * nbr_stride + row]) : -1;
       }
     };
+    TC_TIMER_DECL(tm_pwait);
+    TC_TIMER_DECL(tm_pissue);
+    TC_TIMER_DECL(tm_ppro);
+    TC_TIMER_DECL(tm_tiles);
     int pending = -1;  // thread 0: the tile after the next one, fetched while the current tile's stages are issued
     if (tid == 0) {
       *next_tile_s = fetch_tile();
@@ -343,6 +396,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
     int tile = *next_tile_s;
     prefetch(tile);
     for (uint32_t seq = 0;; ++seq) {
+#ifdef FV2P_TC_TIMERS
+      const long long tc_pro0 = clock64();
+      tm_tiles += 1;
+#endif
       asm volatile("bar.sync 1, 256;" ::: "memory");  // every producer warp finished reading nbr_s / next_tile_s
       if (tid == 0) {
         *tile_mask = 0u;
@@ -388,6 +445,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
       prefetch(tile_after);
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (tid == 0) pending = fetch_tile();  // consumed one iteration from now
+#ifdef FV2P_TC_TIMERS
+      tm_ppro += clock64() - tc_pro0;
+#endif
       uint32_t mask = *tile_mask;
       if (mask == 0u) mask = 1u;  // a tile nothing feeds still has to produce (zero) accumulators
       const uint32_t first_k = __ffs(mask) - 1;
@@ -401,7 +461,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
           // slot of their own (ring shorter than the warp count) only help with the neighbour prefetch.
           const uint32_t s = issued % C::kStages;
           if ((int)(s % kProdWarps) != pwarp) continue;
-          mbar_wait(bar_empty + 8 * s, ((issued / C::kStages) & 1) ^ 1);
+          {
+            TC_T0();
+            mbar_wait(bar_empty + 8 * s, ((issued / C::kStages) & 1) ^ 1);
+            TC_ACC(tm_pwait);
+          }
+          TC_T0();
           const uint32_t a_u32 = smem_u32(stage_base + (size_t)s * C::kStageBytes);
           const uint32_t a_bar = kTf32 ? bar_landed + 8 * s : bar_full + 8 * s;
           if (lane == 0) {
@@ -409,7 +474,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
                              ((k == (int)last_k && sl == slices - 1) ? kFlagLast : 0);
             const uint32_t wb = w_stage_bytes * (kTf32 ? 2 : 1);
             const uint8_t *wsrc = wpacked + ((size_t)k * slices + sl) * wb;
-            const uint32_t w_u32 = a_u32 + (kTf32 ? 2 : 1) * C::kABytes;
+            const uint32_t w_u32 = a_u32 + C::kABytes;
             const uint32_t a_tx = use_tma ? a_stage_bytes : 0u;
             const uint32_t wtx = dbg == 3 ? 0u : wb;  // dbg 3: no weight copy
             if constexpr (kTf32) {
@@ -442,6 +507,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
                            src_base + (src >= 0 ? (size_t)src * feat_row_bytes : 0), src >= 0 ? 16u : 0u);
               }
               cp_async_arrive(a_bar);
+              TC_ACC(tm_pissue);
               continue;
             }
             const int rpg = kTileM >> (5 - cshift);  // rows per lane group: 32, 16 or 8
@@ -462,10 +528,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
             }
             cp_async_arrive(a_bar);
           }
+          TC_ACC(tm_pissue);
         }
       }
       tile = tile_after;
     }
+#ifdef FV2P_TC_TIMERS
+    if (tid == 0) {
+      g_tc_timers[blockIdx.x][1] = issued;
+      g_tc_timers[blockIdx.x][2] = tm_tiles;
+      g_tc_timers[blockIdx.x][3] = tm_pwait;
+      g_tc_timers[blockIdx.x][4] = tm_pissue;
+      g_tc_timers[blockIdx.x][5] = tm_ppro;
+    }
+#endif
   } else if (warp == kMmaWarp) {
     // =============================== MMA issuer ===============================
     constexpr uint32_t idesc = instr_desc(N, kTf32);
@@ -476,9 +552,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
     // descriptor of slot 0 plus a constant in the 16-byte start-address field (no carry: smem is < 256 KB).
     const uint64_t a_desc0 = smem_desc(smem_u32(stage_base), sbo, layout);
     constexpr uint64_t kStageStep = (uint64_t)(C::kStageBytes >> 4);
-    constexpr uint64_t kWOff = (uint64_t)(((kTf32 ? 2 : 1) * C::kABytes) >> 4);
-    constexpr uint64_t kALoOff = (uint64_t)(C::kABytes >> 4);
+    constexpr uint64_t kWOff = (uint64_t)(C::kABytes >> 4);
     const uint64_t w_lo_off = (uint64_t)(w_stage_bytes >> 4);
+    const uint32_t a_tmem0 = tmem_base + 2u * (uint32_t)N;  // fp32: TMEM ring of split A tiles behind the accumulators
     // One elected thread runs the whole loop on its own (waits included).  Re-electing per stage with the warp
     // waiting and re-synchronising around the issue costs ~300 cycles per stage and ~50 per tcgen05.mma
     // (profiles/micro/mma_issue_bench.cu: 4 MMAs + commit per stage take 760 cycles that way, 280 this way).
@@ -486,13 +562,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
       uint32_t s = 0, phase = 0;
       uint64_t a_desc = a_desc0;
       uint32_t acc = 0, acc_phase = 0;
+      TC_TIMER_DECL(tm_mfull);
+      TC_TIMER_DECL(tm_mtmem);
+      TC_TIMER_DECL(tm_missue);
       for (;;) {
-        mbar_wait(bar_full + 8 * s, phase);
+        {
+          TC_T0();
+          mbar_wait(bar_full + 8 * s, phase);
+          TC_ACC(tm_mfull);
+        }
         const int flags = stage_flags[s];
-        if (flags & (kFlagFirst | kFlagStop)) mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);  // accumulator drained
+        {
+          TC_T0();
+          if (flags & (kFlagFirst | kFlagStop)) mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);  // accumulator drained
+          TC_ACC(tm_mtmem);
+        }
+        TC_T0();
         tc_fence_after();
         if (flags & kFlagStop) {
           mbar_arrive(bar_tfull + 8 * acc);  // wakes the epilogue, which finds the sentinel tile id
+#ifdef FV2P_TC_TIMERS
+          g_tc_timers[blockIdx.x][6] = tm_mfull;
+          g_tc_timers[blockIdx.x][7] = tm_mtmem;
+          g_tc_timers[blockIdx.x][8] = tm_missue;
+#endif
           break;
         }
         const uint32_t d_tmem = tmem_base + acc * (uint32_t)N;
@@ -504,9 +597,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
             if (j < ksteps) {
               const uint64_t adv = (uint64_t)(2 * j);  // 32 bytes of K
               if constexpr (kTf32) {
-                tc_mma<true>(d_tmem, a_desc + kALoOff + adv, b_desc + adv, idesc, accumulate);
-                tc_mma<true>(d_tmem, a_desc + adv, b_desc + w_lo_off + adv, idesc, 1u);
-                tc_mma<true>(d_tmem, a_desc + adv, b_desc + adv, idesc, 1u);
+                const uint32_t a_hi = a_tmem0 + s * (uint32_t)C::kAColsPerStage + 8u * (uint32_t)j;  // 8 tf32 of K
+                tc_mma_ts_tf32(d_tmem, a_hi + 32u, b_desc + adv, idesc, accumulate);
+                tc_mma_ts_tf32(d_tmem, a_hi, b_desc + w_lo_off + adv, idesc, 1u);
+                tc_mma_ts_tf32(d_tmem, a_hi, b_desc + adv, idesc, 1u);
               } else {
                 tc_mma<false>(d_tmem, a_desc + adv, b_desc + adv, idesc, accumulate);
               }
@@ -526,51 +620,98 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
           phase ^= 1;
           a_desc = a_desc0;
         }
+        TC_ACC(tm_missue);
       }
     }
     __syncwarp();
   } else if (warp > kMmaWarp) {
     // =============================== fp32 split (warps 13-16, 3xTF32 kernels only) ===============================
-    // A_raw <- hi = rn_tf32(x), A_lo <- rn_tf32(x - hi), element-wise in place, so the swizzle is irrelevant here.
-    // These warps have no async copies in flight, so the proxy fence that makes their generic-proxy stores
-    // visible to the tensor core is cheap.
+    // Thread = tile row (the warp's TMEM lane quadrant is warp % 4): reads its landed fp32 row slice from the
+    // swizzled tile, splits it and stores hi / lo to the stage's TMEM columns.
     if constexpr (kTf32) {
       const int t = threadIdx.x - kTcThreadsBase;
-      const int units = (int)(a_stage_bytes >> 4) / kXformThreads;  // 16-byte units per thread: 8, 4 or 2
+      const int quad = warp & 3;
+      const int r = quad * 32 + lane;
+      const int chunks = row_bytes >> 4;  // 16-byte chunks per row slice: 8, 4 (cin = 16) -- 4 tf32 each
+      const int cshift = __ffs(chunks) - 1;
+      const uint32_t swz_row = (uint32_t)((r >> (3 - cshift)) & (chunks - 1));
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + 2u * (uint32_t)N;
+      TC_TIMER_DECL(tm_xwait);
+      TC_TIMER_DECL(tm_xwork);
       for (uint32_t done = 0;; ++done) {
         const uint32_t s = done % C::kStages;
-        mbar_wait(bar_landed + 8 * s, (done / C::kStages) & 1);
+        {
+          TC_T0();
+          mbar_wait(bar_landed + 8 * s, (done / C::kStages) & 1);
+          TC_ACC(tm_xwait);
+        }
+        TC_T0();
         const bool stop = (stage_flags[s] & kFlagStop) != 0;
         if (!stop) {
-          uint8_t *a_hi = stage_base + (size_t)s * C::kStageBytes;
-          uint8_t *a_lo = a_hi + C::kABytes;
+          const uint8_t *row = stage_base + (size_t)s * C::kStageBytes + (size_t)r * row_bytes;
+          const uint32_t a_cols = lane_addr + s * (uint32_t)C::kAColsPerStage;
 #pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            if (it < units) {
-              const int off = (it * kXformThreads + t) * 16;
-              float4 x = *reinterpret_cast<float4 *>(a_hi + off);
-              float4 h, l;
-              h.x = tf32_rn(x.x), h.y = tf32_rn(x.y), h.z = tf32_rn(x.z), h.w = tf32_rn(x.w);
-              l.x = tf32_rn(x.x - h.x), l.y = tf32_rn(x.y - h.y), l.z = tf32_rn(x.z - h.z), l.w = tf32_rn(x.w - h.w);
-              *reinterpret_cast<float4 *>(a_hi + off) = h;
-              *reinterpret_cast<float4 *>(a_lo + off) = l;
+          for (int half = 0; half < 2; ++half) {
+            if (half * 4 < chunks) {
+              float4 x[4];
+#pragma unroll
+              for (int c = 0; c < 4; ++c)
+                x[c] = *reinterpret_cast<const float4 *>(row + (((uint32_t)(half * 4 + c) ^ swz_row) << 4));
+              uint32_t hi[16], lo[16];
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const float v[4] = {x[c].x, x[c].y, x[c].z, x[c].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float h = tf32_rn_alu(v[e]);
+                  hi[4 * c + e] = __float_as_uint(h);
+                  lo[4 * c + e] = __float_as_uint(tf32_rn_alu(v[e] - h));
+                }
+              }
+              tmem_st16(a_cols + 16u * half, hi);
+              tmem_st16(a_cols + 32u + 16u * half, lo);
             }
           }
-          fence_proxy_async();
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          tc_fence_before();
         }
         mbar_arrive(bar_full + 8 * s);
+        TC_ACC(tm_xwork);
         if (stop) break;
       }
+#ifdef FV2P_TC_TIMERS
+      if (t == 0) {
+        g_tc_timers[blockIdx.x][11] = tm_xwait;
+        g_tc_timers[blockIdx.x][12] = tm_xwork;
+      }
+#else
+      (void)t;
+#endif
     }
   } else {
     // =============================== epilogue (warps 0-3) ===============================
     int acc = 0;
     uint32_t acc_phase = 0;
+    TC_TIMER_DECL(tm_ewait);
+    TC_TIMER_DECL(tm_ework);
     for (uint32_t seq = 0;; ++seq) {
-      mbar_wait(bar_tfull + 8 * acc, acc_phase);
+      {
+        TC_T0();
+        mbar_wait(bar_tfull + 8 * acc, acc_phase);
+        TC_ACC(tm_ewait);
+      }
+      TC_T0();
       tc_fence_after();
       const int tile = tile_ring[seq % kTileRing];
-      if (tile < 0) break;
+      if (tile < 0) {
+#ifdef FV2P_TC_TIMERS
+        if (threadIdx.x == 0) {
+          g_tc_timers[blockIdx.x][9] = tm_ewait;
+          g_tc_timers[blockIdx.x][10] = tm_ework;
+        }
+#endif
+        break;
+      }
       // sorted position -> output row (identity without a row order from fv2p_sort_rows_by_mask)
       const int srow = tile * kTileM + warp * 32 + lane;
       const int row = srow < n_out ? (row_perm ? __ldg(&row_perm[srow]) : srow) : n_out;
@@ -641,11 +782,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
       mbar_arrive(bar_tempty + 8 * acc);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
+      TC_ACC(tm_ework);
     }
   }
   tc_fence_before();
   __syncthreads();
   if (dbg == 7 && blockIdx.x == 0 && threadIdx.x == 0) g_tc_stamps[stamp_slot][1] = global_timer();
+#ifdef FV2P_TC_TIMERS
+  if (threadIdx.x == 0) g_tc_timers[blockIdx.x][0] = clock64() - tc_cta_t0;
+#endif
   if (sched && threadIdx.x == 0) {
     // the last CTA to leave re-arms the scheduler words for the next launch that uses them
     __threadfence();
@@ -833,6 +978,13 @@ extern "C" __attribute__((visibility("default"))) int fv2p_debug_stamps(unsigned
   cudaMemcpyToSymbol(g_tc_stamp_n, &zero, sizeof(zero));
   return (int)n;
 }
+
+#ifdef FV2P_TC_TIMERS
+extern "C" __attribute__((visibility("default"))) int fv2p_debug_timers(unsigned long long *out) {
+  cudaDeviceSynchronize();
+  return (int)cudaMemcpyFromSymbol(out, g_tc_timers, sizeof(unsigned long long) * 160 * 16);
+}
+#endif
 
 extern "C" __attribute__((visibility("default"))) int fv2p_debug_set(int v) {
   return (int)cudaMemcpyToSymbol(g_tc_debug, &v, sizeof(int));

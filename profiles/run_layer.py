@@ -57,4 +57,18 @@ for mode in a.debug:
         ts.append(e0.elapsed_time(e1))
     print("debug mode", mode, "ms", min(ts))
     lib.fv2p_debug_set(ctypes.c_int(0))
+if hasattr(_lib.load(), "fv2p_debug_timers"):
+    import numpy as np  # noqa: E402
+    buf = (ctypes.c_ulonglong * (160 * 16))()
+    eng.run_conv_step(arena, a.layer, p, vf, cap0)
+    _lib.load().fv2p_debug_timers(buf)
+    t = np.array(list(buf), dtype=np.float64).reshape(160, 16)[:148]
+    names = ["total", "stages", "tiles", "prod wait(empty)", "prod issue", "prod tile prologue", "mma wait(full)",
+             "mma wait(tmem)", "mma issue", "epi wait", "epi work", "xform wait", "xform work"]
+    busiest = int(np.argmax(t[:, 0]))
+    print("role timers (cycles): mean over CTAs | busiest CTA %d" % busiest)
+    for i, nm in enumerate(names):
+        print("  %-20s %12.0f %12.0f" % (nm, t[:, i].mean(), t[busiest, i]))
+    print("  cycles per stage (busiest CTA): %.0f; producer warp 0 handled 1/%d of the stages" %
+          (t[busiest, 0] / max(t[busiest, 1], 1), 8))
 print("layer", a.layer, st.key, st.cin, st.cout, "mode", p["mode"], "rows", hp.finish(h)[1]["counts"])
