@@ -52,10 +52,13 @@ constexpr int kEpiThreads = 128;   // warps 0-3
 constexpr int kProdThreads = 256;  // warps 4-11: neighbour prefetch + gather issue (each ring slot has one owner warp)
 constexpr int kProdWarps = kProdThreads / 32;
 constexpr int kMmaWarp = (kEpiThreads + kProdThreads) / 32;  // warp 12
-constexpr int kXformThreads = 128;                           // warps 13-16, fp32 (3xTF32) kernels only
-constexpr int kTcThreadsBase = kEpiThreads + kProdThreads + 32;
+constexpr int kSchedWarp = kMmaWarp + 1;                     // warp 13: tile scheduler + neighbour-map loader
+constexpr int kXformThreads = 128;                           // warps 14-17, fp32 (3xTF32) kernels only
+constexpr int kTcThreadsBase = kEpiThreads + kProdThreads + 64;
 constexpr int kMaxStages = 8;
-constexpr int kSmemBudget = 212 * 1024;
+constexpr int kSmemLimit = 232448;                 // 227 KB of dynamic shared memory per CTA
+constexpr int kSmemMisc = 2048;                    // barriers and small rings + 1024-byte alignment slack
+constexpr int kNbrBufInts = FV2P_MAX_KVOL * 128;   // one tile of the neighbour map: [offset][128 rows]
 constexpr int kTileRing = 16;  // > kMaxStages + 2: how far the producers can run ahead of the epilogue, in tiles
 constexpr int kFlagFirst = 1, kFlagLast = 2, kFlagStop = 4;
 
@@ -246,13 +249,15 @@ struct Cfg {
   // bf16: A tile + W slice.  fp32: the raw fp32 A tile + W_hi + W_lo; the split A operand lives in TMEM
   // (kAColsPerStage columns per ring slot: hi in the first 32, lo in the next 32).
   static constexpr int kStageBytes = kABytes + (kTf32 ? 2 : 1) * kWBytes;
-  static constexpr int kNbrBytes = FV2P_MAX_KVOL * kTileM * 4;
+  // The scheduler warp streams neighbour-map tiles into a ring of kNbrBufs buffers ahead of the producers.
+  static constexpr int kNbrBufs = N == 128 ? 2 : (N == 64 ? 3 : 4);
+  static constexpr int kNbrBytes = kNbrBufs * kNbrBufInts * 4;
   static constexpr int kAColsPerStage = 64;
-  static constexpr int kStagesSmem = (kSmemBudget - kNbrBytes - 1024) / kStageBytes;
+  static constexpr int kStagesSmem = (kSmemLimit - kSmemMisc - kNbrBytes) / kStageBytes;
   static constexpr int kStagesTmem = kTf32 ? (512 - 2 * N) / kAColsPerStage : kMaxStages;
   static constexpr int kStagesRaw = kStagesSmem < kStagesTmem ? kStagesSmem : kStagesTmem;
   static constexpr int kStages = kStagesRaw > kMaxStages ? kMaxStages : kStagesRaw;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kNbrBytes + 1024 + 1024;  // + barriers + align slack
+  static constexpr int kSmemBytes = kStages * kStageBytes + kNbrBytes + kSmemMisc;
   static constexpr int kTmemCols = kTf32 ? 512 : (2 * N < 32 ? 32 : 2 * N);  // power of two
   static constexpr int kThreads = kTcThreadsBase + (kTf32 ? kXformThreads : 0);
   static_assert(kStages >= 3, "pipeline too shallow");
@@ -279,15 +284,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
   uint8_t *stage_base = smem;
   int *nbr_s = reinterpret_cast<int *>(smem + C::kStages * C::kStageBytes);
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C::kStages * C::kStageBytes + C::kNbrBytes);
-  // barrier layout: full[kStages], empty[kStages], landed[kStages] (fp32 only), tmem_full[2], tmem_empty[2]
+  // barrier layout: full[kStages], empty[kStages], landed[kStages] (fp32 only), tmem_full[2], tmem_empty[2],
+  // nbr_full[kNbrBufs], nbr_empty[kNbrBufs]
   const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * C::kStages;
   const uint32_t bar_landed = bar_empty + 8 * C::kStages;
   const uint32_t bar_tfull = bar_landed + 8 * C::kStages, bar_tempty = bar_tfull + 16;
-  volatile int *stage_flags = reinterpret_cast<volatile int *>(bars + 3 * C::kStages + 4);  // [kStages]
-  volatile uint32_t *tile_mask = reinterpret_cast<volatile uint32_t *>(stage_flags + C::kStages);
-  uint32_t *tmem_slot = const_cast<uint32_t *>(tile_mask) + 1;
-  volatile int *next_tile_s = reinterpret_cast<volatile int *>(tmem_slot + 1);  // producers' broadcast slot
-  volatile int *tile_ring = next_tile_s + 1;                                     // [kTileRing] tile id per sequence no.
+  const uint32_t bar_nfull = bar_tempty + 16, bar_nempty = bar_nfull + 8 * C::kNbrBufs;
+  volatile int *stage_flags = reinterpret_cast<volatile int *>(bars + 3 * C::kStages + 4 + 2 * C::kNbrBufs);  // [kStages]
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(const_cast<int *>(stage_flags + C::kStages));
+  volatile int *tile_ring = reinterpret_cast<volatile int *>(tmem_slot + 1);  // [kTileRing] tile id per sequence no.
+  volatile int *tile_info = tile_ring + kTileRing;                            // [kNbrBufs][2]: tile id, offset mask
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int dbg = g_tc_debug;
@@ -323,6 +329,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
       mbar_init(bar_tfull + 8 * a, 1);
       mbar_init(bar_tempty + 8 * a, kEpiThreads);
     }
+    for (int b = 0; b < C::kNbrBufs; ++b) {
+      mbar_init(bar_nfull + 8 * b, 1);            // the scheduler's (expect_tx) arrive; bulk copies complete the bytes
+      mbar_init(bar_nempty + 8 * b, kProdWarps);  // every producer warp is done reading the buffer
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&feat_map) : "memory");
   }
@@ -338,9 +348,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp >= 4 && warp < kMmaWarp) {
-    // =============================== producers: tile fetch + neighbour prefetch + gather issue ===============
-    const int tid = threadIdx.x - kEpiThreads;
-    const int pwarp = tid >> 5;
+    // =============================== producers: gather issue ===============================
+    // No block-level synchronisation: a warp takes the tile's neighbour rows and offset mask from the scheduler's
+    // ring, issues the stages whose ring slot it owns, and hands the buffer back.
+    const int pwarp = (threadIdx.x - kEpiThreads) >> 5;
     const uint8_t *feat = static_cast<const uint8_t *>(feat_ptr);
     const size_t feat_row_bytes = (size_t)cin * kElem;
     uint32_t issued = 0;
@@ -351,62 +362,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
     const int my_chunk = lane & (chunks - 1);
     const int my_row0 = lane >> cshift;
     const int rows_per_instr = 32 >> cshift;
-    // Next tile of this CTA (thread 0 only), -1 when the work is used up; positions index `tile_order` (heaviest
-    // first).  The ids are needed one to two tiles ahead of their use, and claiming that early from a shared
-    // counter lets the first CTAs grab several of the heaviest tiles each when there are only 1-2 tiles per CTA
-    // (measured: 3 x 108 stages on some CTAs, none on others, on the 206-tile layers).  So the first two rounds are
-    // dealt statically in snake order - position b, then 2G-1-b: the CTA with the lightest first tile gets the
-    // heaviest second one - and only the rest comes from the counter (round-robin without scheduler scratch).
-    int fetches = 0;
-    auto fetch_tile = [&]() -> int {
-      const int G = (int)gridDim.x, b = (int)blockIdx.x;
-      int i;
-      if (fetches == 0) i = b;
-      else if (fetches == 1) i = 2 * G - 1 - b;
-      else if (sched) i = 2 * G + atomicAdd(&sched[0], 1);
-      else i = fetches * G + b;
-      ++fetches;
-      if (i >= n_tiles) return -1;
-      return tile_order ? __ldg(&tile_order[i]) : i;
-    };
-    // The neighbour rows of a tile are prefetched into registers one tile ahead: the loads of tile t+1 are in
-    // flight while tile t's stages are being issued.  Thread t serves row t%128 for the offsets of parity t/128.
-    constexpr int kNbrRegs = FV2P_MAX_KVOL / 2;
-    int nbr_next[kNbrRegs];
-    const int pre_r = tid & (kTileM - 1);
-    const int pre_k0 = tid >> 7;
-    auto prefetch = [&](int tile) {
-      const int row = tile * kTileM + pre_r;  // with a row order, `nbr` is the map permuted the same way
-#pragma unroll
-      for (int q = 0; q < kNbrRegs; ++q) {
-        const int k = pre_k0 + 2 * q;
-        nbr_next[q] = (tile >= 0 && k < kvol && row < n_out) ? __ldg(&nbr[(size_t)k * nbr_stride + row]) : -1;
-      }
-    };
     TC_TIMER_DECL(tm_pwait);
     TC_TIMER_DECL(tm_pissue);
     TC_TIMER_DECL(tm_ppro);
     TC_TIMER_DECL(tm_tiles);
-    int pending = -1;  // thread 0: the tile after the next one, fetched while the current tile's stages are issued
-    if (tid == 0) {
-      *next_tile_s = fetch_tile();
-      pending = fetch_tile();
-    }
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    int tile = *next_tile_s;
-    prefetch(tile);
     for (uint32_t seq = 0;; ++seq) {
-#ifdef FV2P_TC_TIMERS
-      const long long tc_pro0 = clock64();
-      tm_tiles += 1;
-#endif
-      asm volatile("bar.sync 1, 256;" ::: "memory");  // every producer warp finished reading nbr_s / next_tile_s
-      if (tid == 0) {
-        *tile_mask = 0u;
-        tile_ring[seq % kTileRing] = tile;
-        *next_tile_s = pending;
+      const uint32_t nb = seq % C::kNbrBufs;
+      {
+        TC_T0();
+        mbar_wait(bar_nfull + 8 * nb, (seq / C::kNbrBufs) & 1);
+        TC_ACC(tm_ppro);
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const int tile = tile_info[2 * nb];
+      uint32_t mask = (uint32_t)tile_info[2 * nb + 1];
+      const int *nbr_b = nbr_s + nb * kNbrBufInts;
       if (tile < 0) {
         // Sentinel stage: same arrivals as a real stage, no copies; tells the other roles to stop.
         const uint32_t s = issued % C::kStages;
@@ -428,27 +397,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
         }
         break;
       }
-      {
-        uint32_t mine = 0;
-#pragma unroll
-        for (int q = 0; q < kNbrRegs; ++q) {
-          const int k = pre_k0 + 2 * q;
-          if (k < kvol) {
-            const int src = nbr_next[q];
-            nbr_s[k * kTileM + pre_r] = (src < 0 && use_tma) ? oob_row : src;  // TMA: out-of-range row -> zero fill
-            if (__ballot_sync(0xFFFFFFFFu, src >= 0)) mine |= 1u << k;
-          }
-        }
-        if (lane == 0 && mine) atomicOr(const_cast<uint32_t *>(tile_mask), mine);
-      }
-      const int tile_after = *next_tile_s;
-      prefetch(tile_after);
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (tid == 0) pending = fetch_tile();  // consumed one iteration from now
 #ifdef FV2P_TC_TIMERS
-      tm_ppro += clock64() - tc_pro0;
+      tm_tiles += 1;
 #endif
-      uint32_t mask = *tile_mask;
       if (mask == 0u) mask = 1u;  // a tile nothing feeds still has to produce (zero) accumulators
       const uint32_t first_k = __ffs(mask) - 1;
       const uint32_t last_k = 31 - __clz(mask);
@@ -458,7 +409,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
         for (int sl = 0; sl < slices; ++sl, ++issued) {
           // A ring slot always belongs to the same producer warp, so each empty barrier is waited on by one warp
           // in program order (the parity wait cannot alias, whatever the drift between warps); warps without a
-          // slot of their own (ring shorter than the warp count) only help with the neighbour prefetch.
+          // slot of their own (ring shorter than the warp count) idle.
           const uint32_t s = issued % C::kStages;
           if ((int)(s % kProdWarps) != pwarp) continue;
           {
@@ -488,8 +439,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
           }
           __syncwarp();
           if (use_tma) {
-            // lane l gathers tile rows 4l..4l+3
-            const int4 rows = *reinterpret_cast<const int4 *>(&nbr_s[k * kTileM + 4 * lane]);
+            // lane l gathers tile rows 4l..4l+3; a missing neighbour becomes an out-of-range row (zero fill)
+            int4 rows = *reinterpret_cast<const int4 *>(&nbr_b[k * kTileM + 4 * lane]);
+            rows.x = rows.x < 0 ? oob_row : rows.x, rows.y = rows.y < 0 ? oob_row : rows.y;
+            rows.z = rows.z < 0 ? oob_row : rows.z, rows.w = rows.w < 0 ? oob_row : rows.w;
             tma_gather4(a_u32 + (uint32_t)(4 * lane) * row_bytes, &feat_map, sl * (row_bytes / kElem), rows.x, rows.y,
                         rows.z, rows.w, a_bar);
           } else {
@@ -498,7 +451,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
             // 128-byte slices) and writes conflict-free thanks to the swizzle.
             const uint8_t *src_base = feat + (size_t)sl * row_bytes + my_chunk * 16;
             if (chunks < 8) {  // narrow rows: interleaved rows per instruction measured faster (0.046 vs 0.053 ms, 16->16)
-              const int *rows_k = nbr_s + k * kTileM;
+              const int *rows_k = nbr_b + k * kTileM;
 #pragma unroll 4
               for (int r = my_row0; r < kTileM; r += rows_per_instr) {
                 const int src = rows_k[r];
@@ -512,7 +465,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
             }
             const int rpg = kTileM >> (5 - cshift);  // rows per lane group: 32, 16 or 8
             const int r_first = (lane >> cshift) * rpg;
-            const int4 *idx4 = reinterpret_cast<const int4 *>(nbr_s + k * kTileM + r_first);
+            const int4 *idx4 = reinterpret_cast<const int4 *>(nbr_b + k * kTileM + r_first);
             const uint32_t dst0 = a_u32 + (uint32_t)r_first * row_bytes;
             for (int q = 0; q < (rpg >> 2); ++q) {
               const int4 v = idx4[q];
@@ -531,10 +484,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
           TC_ACC(tm_pissue);
         }
       }
-      tile = tile_after;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_nempty + 8 * nb);  // this warp no longer reads the tile's neighbour rows
     }
 #ifdef FV2P_TC_TIMERS
-    if (tid == 0) {
+    if (threadIdx.x == kEpiThreads) {
       g_tc_timers[blockIdx.x][1] = issued;
       g_tc_timers[blockIdx.x][2] = tm_tiles;
       g_tc_timers[blockIdx.x][3] = tm_pwait;
@@ -542,6 +496,93 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
       g_tc_timers[blockIdx.x][5] = tm_ppro;
     }
 #endif
+  } else if (warp == kSchedWarp) {
+    // =============================== tile scheduler + neighbour-map loader ===============================
+    // Runs up to kNbrBufs tiles ahead of the producers: claims the next tile, and brings the rows of the
+    // neighbour map the tile needs (only the offsets in its mask) into the ring with bulk copies that complete
+    // on the buffer's barrier.  Tile positions index `tile_order` (heaviest first).  Claiming from a shared
+    // counter only would let the first CTAs take several of the heaviest tiles each when there are 1-2 tiles
+    // per CTA, so the first two rounds are dealt statically in snake order - position b, then 2G-1-b: the CTA
+    // with the lightest first tile gets the heaviest second one - and the rest comes from the counter
+    // (round-robin without scheduler scratch).
+    const int2 *order2 = reinterpret_cast<const int2 *>(tile_order);
+    const bool bulk_ok = (nbr_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(nbr) & 15) == 0;
+    int fetches = 0;
+    int2 pending = make_int2(-1, 0);  // lane 0: the claim in flight
+    auto claim = [&]() {
+      if (lane == 0) {
+        const int G = (int)gridDim.x, b = (int)blockIdx.x;
+        int i;
+        if (fetches == 0) i = b;
+        else if (fetches == 1) i = 2 * G - 1 - b;
+        else if (sched) i = 2 * G + atomicAdd(&sched[0], 1);
+        else i = fetches * G + b;
+        ++fetches;
+        pending = i >= n_tiles ? make_int2(-1, 0) : (order2 ? __ldg(&order2[i]) : make_int2(i, 0));
+      }
+    };
+    claim();
+    for (uint32_t seq = 0;; ++seq) {
+      const int tile = __shfl_sync(0xFFFFFFFFu, pending.x, 0);
+      uint32_t mask = (uint32_t)__shfl_sync(0xFFFFFFFFu, pending.y, 0);
+      if (tile >= 0) claim();  // the next claim (atomic + list entry) is in flight while this tile is set up
+      const uint32_t nb = seq % C::kNbrBufs;
+      mbar_wait(bar_nempty + 8 * nb, ((seq / C::kNbrBufs) & 1) ^ 1);
+      int *dst = nbr_s + nb * kNbrBufInts;
+      if (lane == 0) tile_ring[seq % kTileRing] = tile;
+      if (tile < 0) {
+        if (lane == 0) {
+          tile_info[2 * nb] = -1;
+          tile_info[2 * nb + 1] = 0;
+          mbar_arrive(bar_nfull + 8 * nb);
+        }
+        break;
+      }
+      const int row0 = tile * kTileM;
+      const int valid = min(kTileM, n_out - row0);
+      if (bulk_ok && order2 && mask != 0u && valid == kTileM) {
+        if (elect_one_sync()) {
+          tile_info[2 * nb] = tile;
+          tile_info[2 * nb + 1] = (int)mask;
+          mbar_arrive_expect_tx(bar_nfull + 8 * nb, (uint32_t)__popc(mask) * (kTileM * 4u));
+          uint32_t m = mask;
+          while (m) {
+            const int k = __ffs(m) - 1;
+            m &= m - 1;
+            bulk_g2s(smem_u32(dst + k * kTileM), nbr + (size_t)k * nbr_stride + row0, kTileM * 4u, bar_nfull + 8 * nb);
+          }
+        }
+        __syncwarp();
+      } else {
+        // Partial last tile, callers without a tile list, unaligned maps: plain loads by the whole warp (lane l
+        // serves rows 4l..4l+3), rows past the end read as "no neighbour", mask derived from the data.
+        uint32_t found = 0;
+        for (int k0 = 0; k0 < kvol; k0 += 8) {  // eight offsets' loads in flight at a time
+          int v[8][4];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int r = 4 * lane + u;
+              v[q][u] = (k0 + q < kvol && r < valid) ? __ldg(&nbr[(size_t)(k0 + q) * nbr_stride + row0 + r]) : -1;
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            if (k0 + q < kvol) {
+              *reinterpret_cast<int4 *>(dst + (k0 + q) * kTileM + 4 * lane) = make_int4(v[q][0], v[q][1], v[q][2], v[q][3]);
+              if (__ballot_sync(0xFFFFFFFFu, (v[q][0] & v[q][1] & v[q][2] & v[q][3]) >= 0)) found |= 1u << (k0 + q);
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) {
+          tile_info[2 * nb] = tile;
+          tile_info[2 * nb + 1] = (int)found;
+          mbar_arrive(bar_nfull + 8 * nb);
+        }
+      }
+    }
   } else if (warp == kMmaWarp) {
     // =============================== MMA issuer ===============================
     constexpr uint32_t idesc = instr_desc(N, kTf32);
@@ -624,8 +665,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
       }
     }
     __syncwarp();
-  } else if (warp > kMmaWarp) {
-    // =============================== fp32 split (warps 13-16, 3xTF32 kernels only) ===============================
+  } else if (warp > kSchedWarp) {
+    // =============================== fp32 split (warps 14-17, 3xTF32 kernels only) ===============================
     // Thread = tile row (the warp's TMEM lane quadrant is warp % 4): reads its landed fp32 row slice from the
     // swizzled tile, splits it and stores hi / lo to the stage's TMEM columns.
     if constexpr (kTf32) {

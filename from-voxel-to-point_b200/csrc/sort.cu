@@ -122,12 +122,12 @@ permute_nbr_kernel(const int *__restrict__ nbr, int64_t nbr_stride, int kvol, co
   }
 }
 
-// Tile weights for the conv's tile scheduler: weight[t] = number of offsets that have a neighbour in sorted rows
-// [128 t, 128 t + 128) = pipeline stages (per 128-byte slice) the conv spends on the tile.  One warp per tile.
+// Tile masks for the conv's tile scheduler: masks[t] = OR of the neighbour masks of sorted rows [128 t, 128 t + 128);
+// its population count = pipeline stages (per 128-byte slice) the conv spends on the tile.  One warp per tile.
 constexpr int kConvTile = 128;
 
 __global__ void __launch_bounds__(kThreads)
-tile_weight_kernel(const uint32_t *__restrict__ keys_sorted, const int *n_dev, int64_t n_cap, int *weights) {
+tile_mask_kernel(const uint32_t *__restrict__ keys_sorted, const int *n_dev, int64_t n_cap, uint32_t *masks) {
   const int n = live_n(n_dev, n_cap);
   const int n_tiles = (n + kConvTile - 1) / kConvTile;
   const int lane = threadIdx.x & 31;
@@ -140,15 +140,16 @@ tile_weight_kernel(const uint32_t *__restrict__ keys_sorted, const int *n_dev, i
       if (i < n) m |= keys_sorted[i];
     }
     m = __reduce_or_sync(0xFFFFFFFFu, m);
-    if (lane == 0) weights[t] = __popc(m);
+    if (lane == 0) masks[t] = m;
   }
 }
 
-// tile_order = the tiles by descending weight (counting sort over the 33 possible weights, one CTA).  The conv hands
-// tiles to its CTAs in this order from an atomic counter, i.e. longest-processing-time-first list scheduling.
-// Ties are placed in tile order (per-warp ballots under a block-ordered cursor), so the order is deterministic.
+// tile_order = (tile, mask) pairs by descending weight = popcount(mask) (counting sort over the 33 possible weights,
+// one CTA).  The conv hands tiles to its CTAs in this order, i.e. longest-processing-time-first list scheduling, and
+// takes the tile's active offsets from the mask.  Ties are placed in tile order (per-warp ballots under a
+// block-ordered cursor), so the order is deterministic.
 __global__ void __launch_bounds__(1024)
-tile_rank_kernel(const int *__restrict__ weights, const int *n_dev, int64_t n_cap, int *tile_order) {
+tile_rank_kernel(const uint32_t *__restrict__ masks, const int *n_dev, int64_t n_cap, int2 *tile_order) {
   __shared__ int hist[33], base[33];
   __shared__ int warp_cnt[32][33];
   const int n = live_n(n_dev, n_cap);
@@ -156,7 +157,7 @@ tile_rank_kernel(const int *__restrict__ weights, const int *n_dev, int64_t n_ca
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x < 33) hist[threadIdx.x] = 0;
   __syncthreads();
-  for (int t = threadIdx.x; t < n_tiles; t += blockDim.x) atomicAdd(&hist[weights[t]], 1);
+  for (int t = threadIdx.x; t < n_tiles; t += blockDim.x) atomicAdd(&hist[__popc(masks[t])], 1);
   __syncthreads();
   if (threadIdx.x == 0) {
     int run = 0;
@@ -168,7 +169,8 @@ tile_rank_kernel(const int *__restrict__ weights, const int *n_dev, int64_t n_ca
   __syncthreads();
   for (int t0 = 0; t0 < n_tiles; t0 += blockDim.x) {
     const int t = t0 + threadIdx.x;
-    const int w = t < n_tiles ? weights[t] : -1;
+    const uint32_t m = t < n_tiles ? masks[t] : 0u;
+    const int w = t < n_tiles ? __popc(m) : -1;
     const unsigned peers = __match_any_sync(0xFFFFFFFFu, w);
     for (int b = lane; b < 33; b += 32) warp_cnt[warp][b] = 0;
     __syncwarp();
@@ -177,7 +179,7 @@ tile_rank_kernel(const int *__restrict__ weights, const int *n_dev, int64_t n_ca
     if (w >= 0) {
       int before = 0;
       for (int q = 0; q < warp; ++q) before += warp_cnt[q][w];
-      tile_order[base[w] + before + __popc(peers & ((1u << lane) - 1u))] = t;
+      tile_order[base[w] + before + __popc(peers & ((1u << lane) - 1u))] = make_int2(t, (int)m);
     }
     __syncthreads();
     if (threadIdx.x < 33) {
@@ -191,7 +193,8 @@ tile_rank_kernel(const int *__restrict__ weights, const int *n_dev, int64_t n_ca
 
 struct SortWorkspace {
   uint32_t *keys_a, *keys_b;
-  int *vals_b, *counts, *totals, *weights;
+  int *vals_b, *counts, *totals;
+  uint32_t *tile_masks;
   int n_chunks;
   size_t bytes;
 };
@@ -207,7 +210,7 @@ SortWorkspace carve(void *ws, int64_t n_cap) {
   w.vals_b = c.take<int>(n);
   w.counts = c.take<int>((size_t)kBins * w.n_chunks);
   w.totals = c.take<int>(kBins);
-  w.weights = c.take<int>(n / kConvTile + 1);
+  w.tile_masks = c.take<uint32_t>(n / kConvTile + 1);
   w.bytes = c.used + 256;
   return w;
 }
@@ -263,8 +266,8 @@ extern "C" int fv2p_sort_rows_by_mask(const int32_t *nbr, int64_t nbr_stride, in
     permute_nbr_kernel<<<grid, kThreads, 0, stream>>>(nbr, nbr_stride, kvol, perm, n_dev, n_cap, nbr_sorted,
                                                       sorted_stride);
   if (tile_order) {  // k_src holds the sorted masks
-    tile_weight_kernel<<<grid, kThreads, 0, stream>>>(k_src, n_dev, n_cap, w.weights);
-    tile_rank_kernel<<<1, 1024, 0, stream>>>(w.weights, n_dev, n_cap, tile_order);
+    tile_mask_kernel<<<grid, kThreads, 0, stream>>>(k_src, n_dev, n_cap, w.tile_masks);
+    tile_rank_kernel<<<1, 1024, 0, stream>>>(w.tile_masks, n_dev, n_cap, reinterpret_cast<int2 *>(tile_order));
   }
   FV2P_LAUNCH_CHECK("sort_rows_by_mask");
   return FV2P_OK;

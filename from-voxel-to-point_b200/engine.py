@@ -232,14 +232,16 @@ class BackboneEngine(object):
         ws_bytes = 0
         for bk in self.books:
             cin_cap, cout_cap = caps[bk.in_level], caps[bk.out_level]
-            d = dict(nbr=torch.empty((bk.kvol, cout_cap), dtype=torch.int32, device=device),
+            # neighbour-map rows padded to whole 128-row tiles: the conv's bulk copies need 16-byte aligned rows
+            cols = (cout_cap + 127) // 128 * 128
+            d = dict(nbr=torch.empty((bk.kvol, cols), dtype=torch.int32, device=device),
                      pair_num=torch.zeros((bk.kvol,), dtype=torch.int32, device=device),
                      pairs=(torch.empty((bk.kvol, 2, cin_cap), dtype=torch.int32, device=device)
                             if self.materialize_pairs else None))
             if self.sort_rows:
                 d["perm"] = torch.empty((cout_cap,), dtype=torch.int32, device=device)
-                d["nbr_sorted"] = torch.empty((bk.kvol, cout_cap), dtype=torch.int32, device=device)
-                d["tile_order"] = torch.empty((cout_cap // 128 + 1,), dtype=torch.int32, device=device)
+                d["nbr_sorted"] = torch.empty((bk.kvol, cols), dtype=torch.int32, device=device)
+                d["tile_order"] = torch.empty((cout_cap // 128 + 1, 2), dtype=torch.int32, device=device)
                 ws_bytes = max(ws_bytes, lib.fv2p_sort_rows_workspace_bytes(cout_cap))
             books[bk.key] = d
             ws_bytes = max(ws_bytes, lib.fv2p_rulebook_workspace_bytes(cin_cap, cout_cap, bk.kvol))

@@ -135,14 +135,15 @@ def pack_weight(weight_flat, mode):
 
 def sort_rows_by_mask(nbr, num_activate_out=None, return_tile_order=False):
     """fv2p_sort_rows_by_mask: (perm [Nout], nbr_sorted [K,Nout]) for the tensor-core conv modes, plus the
-    128-row tiles by descending number of active offsets (``tile_order``) if asked for."""
+    128-row tiles as (tile, offset mask) pairs by descending number of active offsets (``tile_order`` [T,2]) if
+    asked for."""
     dev = _lib.require_device(nbr)
     kvol = nbr.shape[0]
     n = int(nbr.shape[1] if num_activate_out is None else num_activate_out)
     assert nbr.stride(1) == 1
     perm = torch.empty((max(n, 1),), dtype=torch.int32, device=nbr.device)
     nbr_sorted = torch.empty((kvol, max(n, 1)), dtype=torch.int32, device=nbr.device)
-    order = torch.empty(((n + 127) // 128 + 1,), dtype=torch.int32, device=nbr.device) if return_tile_order else None
+    order = torch.empty(((n + 127) // 128 + 1, 2), dtype=torch.int32, device=nbr.device) if return_tile_order else None
     lib = _lib.load()
     ws = _lib.Workspace.get(nbr.device, lib.fv2p_sort_rows_workspace_bytes(n), "sort")
     with torch.cuda.device(dev):

@@ -168,8 +168,8 @@ FV2P_API int fv2p_pairs_to_nbr(const int32_t *pairs, const int32_t *pair_num, in
  *   row_perm  NULL, or the row order from fv2p_sort_rows_by_mask (tensor-core modes only): `nbr` is then the map
  *             permuted the same way (nbr_sorted) and sorted position t writes output row row_perm[t]; results are
  *             identical either way
- *   tile_order NULL, or fv2p_sort_rows_by_mask's tile list (needs row_perm): the order in which the 128-row tiles are
- *             handed out (most active offsets first)
+ *   tile_order NULL, or fv2p_sort_rows_by_mask's tile list (needs row_perm): (tile, offset mask) pairs in the order
+ *             in which the 128-row tiles are handed out (most active offsets first)
  *   sched     NULL (tiles dealt round-robin to the CTAs), or two device int32 words, zero on entry, that the
  *             tensor-core kernel uses as its tile counter and leaves zeroed again; one pair per launch that may be
  *             in flight at the same time
@@ -183,7 +183,9 @@ FV2P_API int fv2p_conv_fwd(const void *features, int64_t n_in_cap, const void *w
 /* Row order for the tensor-core conv: stable sort of the output rows by their neighbour mask (bit k = offset k has
  * a neighbour).  perm[t] = output row at sorted position t; nbr_sorted[k][t] = nbr[k][perm[t]] (optional).  Tiles
  * cut from this order need about half the pipeline stages (rows of a tile share their active offsets); the conv
- * result does not change.  No reference counterpart (spconv_ops.h:308-357 works on per-offset pair lists). */
+ * result does not change.  tile_order (optional, 2 * ceil(n_cap / 128) int32): (tile, OR of the tile's masks) pairs by
+ * descending population count, ties by tile.  No reference counterpart (spconv_ops.h:308-357 works on per-offset
+ * pair lists). */
 FV2P_API size_t fv2p_sort_rows_workspace_bytes(int64_t n_cap);
 FV2P_API int fv2p_sort_rows_by_mask(const int32_t *nbr, int64_t nbr_stride, int kvol, int64_t n_cap,
                                     const int32_t *n_dev, int32_t *perm, int32_t *nbr_sorted,

@@ -425,10 +425,14 @@ def test_mask_sorted_row_order_gives_identical_results():
         expect = np.argsort(masks, kind="stable")
         assert np.array_equal(perm.cpu().numpy(), expect)
         assert np.array_equal(nbr_sorted.cpu().numpy(), m[:, expect])
-        # tile list: every 128-row tile once, by descending number of active offsets, ties in tile order
+        # tile list: every 128-row tile once with the OR of its rows' masks, by descending number of active offsets,
+        # ties in tile order
         sm = masks[expect]
-        weight = np.array([bin(int(np.bitwise_or.reduce(sm[t:t + 128]))).count("1") for t in range(0, n_out, 128)])
-        assert np.array_equal(order.cpu().numpy(), np.argsort(-weight, kind="stable"))
+        tmask = np.array([int(np.bitwise_or.reduce(sm[t:t + 128])) for t in range(0, n_out, 128)])
+        weight = np.array([bin(m_).count("1") for m_ in tmask])
+        by_weight = np.argsort(-weight, kind="stable")
+        assert np.array_equal(order.cpu().numpy()[:, 0], by_weight)
+        assert np.array_equal(order.cpu().numpy()[:, 1], tmask[by_weight])
         for mode, dt in ((_lib.MODE_TF32X3_TC, torch.float32), (_lib.MODE_BF16_TC, torch.bfloat16)):
             feats = cuda(rng.standard_normal((ind.shape[0], 64)).astype(np.float32), dt)
             w = cuda((rng.standard_normal((27, 64, 64)) / 40).astype(np.float32))
