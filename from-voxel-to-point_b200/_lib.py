@@ -32,9 +32,9 @@ PROTOTYPES = {
     "fv2p_mean_vfe": (_c_int, [_c_vp, _c_vp, _c_i64, _c_int, _c_int, _c_vp, _c_vp]),
     "fv2p_rulebook_workspace_bytes": (_c_sz, [_c_i64, _c_i64, _c_int]),
     "fv2p_rulebook_subm": (_c_int, [_c_vp, _c_i64, _c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp,
-                                    _c_i64, _c_vp, _c_sz, _c_vp]),
+                                    _c_i64, _c_vp, _c_sz, _c_vp, _c_vp]),
     "fv2p_rulebook_conv": (_c_int, [_c_vp, _c_i64, _c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64,
-                                    _c_vp, _c_vp, _c_i64, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp, _c_sz, _c_vp]),
+                                    _c_vp, _c_vp, _c_i64, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp, _c_sz, _c_vp, _c_vp]),
     "fv2p_get_indice_pairs_3d": (_c_int, [_c_vp, _c_i64, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp,
                                           _c_int, _c_int, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp,
                                           _c_sz, _c_vp]),

@@ -500,6 +500,19 @@ int fill_geom(Geom &g, const int32_t *out_shape3, const int32_t *ksize3, const i
 
 using namespace fv2p;
 
+// The pair lists are only needed by consumers of the reference-layout tensors; with a second stream their compaction
+// leaves the caller's dependency chain (the neighbour map is complete before it).  Returns the stream to compact on.
+static cudaStream_t fork_for_pairs(cudaStream_t stream, fv2p_stream_t pairs_stream_) {
+  cudaStream_t ps = static_cast<cudaStream_t>(pairs_stream_);
+  if (!pairs_stream_ || ps == stream) return stream;
+  cudaEvent_t ev;
+  if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return stream;
+  cudaEventRecord(ev, stream);
+  cudaStreamWaitEvent(ps, ev, 0);
+  cudaEventDestroy(ev);
+  return ps;
+}
+
 extern "C" size_t fv2p_rulebook_workspace_bytes(int64_t n_in_cap, int64_t n_out_cap, int kvol) {
   if (n_in_cap < 0 || n_out_cap < 0 || kvol < 1 || kvol > FV2P_MAX_KVOL) return 0;
   return carve(nullptr, n_in_cap, n_out_cap, kvol).bytes;
@@ -509,7 +522,7 @@ extern "C" int fv2p_rulebook_subm(const int32_t *indices, int64_t n_cap, const i
                                   const int32_t *shape3, const int32_t *ksize3, const int32_t *dilation3,
                                   int32_t *pairs, int64_t pair_stride, int32_t *pair_num, int32_t *nbr,
                                   int64_t nbr_stride, void *workspace, size_t workspace_bytes,
-                                  fv2p_stream_t stream_) {
+                                  fv2p_stream_t stream_, fv2p_stream_t pairs_stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   FV2P_REQUIRE(shape3 && ksize3, "rulebook_subm: null geometry");
   FV2P_REQUIRE(batch >= 1 && n_cap >= 0 && n_cap < (1ll << 26), "rulebook_subm: bad batch or row count");
@@ -550,6 +563,7 @@ extern "C" int fv2p_rulebook_subm(const int32_t *indices, int64_t n_cap, const i
   if (want_pairs) {
     const int *src_mat = out_mat;
     int64_t src_stride = out_stride;
+    if (mirror) stream = fork_for_pairs(stream, pairs_stream_);  // (the other probe still needs the hash table)
     if (!mirror) {
       subm_probe_in_kernel<<<grid, kThreads, 0, stream>>>(ind4, n_dev, n_cap, g, w.keys, w.vals, w.mat, n_cap,
                                                           w.counts, w.n_chunks);
@@ -571,7 +585,8 @@ extern "C" int fv2p_rulebook_conv(const int32_t *indices, int64_t n_cap, const i
                                   const int32_t *pad3, const int32_t *dilation3, int32_t *out_indices,
                                   int64_t out_cap, int32_t *n_out_dev, int32_t *pairs, int64_t pair_stride,
                                   int32_t *pair_num, int32_t *nbr, int64_t nbr_stride, int32_t *status_dev,
-                                  void *workspace, size_t workspace_bytes, fv2p_stream_t stream_) {
+                                  void *workspace, size_t workspace_bytes, fv2p_stream_t stream_,
+                                  fv2p_stream_t pairs_stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   FV2P_REQUIRE(out_shape3 && ksize3 && stride3 && pad3, "rulebook_conv: null geometry");
   FV2P_REQUIRE(batch >= 1 && n_cap >= 0 && n_cap < (1ll << 26), "rulebook_conv: bad batch or row count");
@@ -615,6 +630,7 @@ extern "C" int fv2p_rulebook_conv(const int32_t *indices, int64_t n_cap, const i
     conv_pairs_kernel<<<grid, kThreads, 0, stream>>>(ind4, n_dev, n_cap, g, w.vals, w.cand_slot, nbr, nbr_stride,
                                                      want_pairs ? w.mat : nullptr, n_cap, w.counts, w.n_chunks);
   if (want_pairs) {
+    stream = fork_for_pairs(stream, pairs_stream_);
     launch_scan_chunk_counts(w.counts, g.kvol, w.n_chunks, n_live, (int64_t)w.n_chunks * kChunk, w.row_totals,
                              stream);
     compact_pairs_kernel<<<grid, kThreads, 0, stream>>>(w.mat, n_cap, n_dev, n_cap, g.kvol, 0, w.counts,
@@ -642,7 +658,7 @@ extern "C" int fv2p_get_indice_pairs_3d(const int32_t *indices, int64_t n, int b
     for (int a = 0; a < 3; ++a)
       FV2P_REQUIRE(out_shape3[a] == spatial_shape3[a], "get_indice_pairs_3d: subm needs out_shape == spatial_shape");
     int st = fv2p_rulebook_subm(indices, n, nullptr, batch, spatial_shape3, ksize3, dilation3, pairs, n, pair_num,
-                                nbr, nbr_stride, workspace, workspace_bytes, stream_);
+                                nbr, nbr_stride, workspace, workspace_bytes, stream_, nullptr);
     if (st) return st;
     if (out_indices && out_indices != indices && n > 0) {
       // spconv_ops.h:104 returns the input tensor itself; a separate buffer gets a copy
@@ -658,7 +674,7 @@ extern "C" int fv2p_get_indice_pairs_3d(const int32_t *indices, int64_t n, int b
   int *n_out_dev = static_cast<int *>(workspace);
   int st = fv2p_rulebook_conv(indices, n, nullptr, batch, out_shape3, ksize3, stride3, pad3, dilation3, out_indices,
                               out_cap, n_out_dev, pairs, n, pair_num, nbr, nbr_stride, n_out_dev + 1,
-                              static_cast<char *>(workspace) + 256, workspace_bytes - 256, stream_);
+                              static_cast<char *>(workspace) + 256, workspace_bytes - 256, stream_, nullptr);
   if (st) return st;
   int host[2] = {0, 0};
   if (n > 0) {

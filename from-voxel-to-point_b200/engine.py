@@ -243,13 +243,15 @@ class BackboneEngine(object):
                 d["nbr_sorted"] = torch.empty((bk.kvol, cols), dtype=torch.int32, device=device)
                 d["tile_order"] = torch.empty((cout_cap // 128 + 1, 2), dtype=torch.int32, device=device)
                 ws_bytes = max(ws_bytes, lib.fv2p_sort_rows_workspace_bytes(cout_cap))
+            # own scratch per book: the pair compaction runs on a stream of its own and keeps reading it while the
+            # next book is already being built
+            d["ws"] = torch.empty(lib.fv2p_rulebook_workspace_bytes(cin_cap, cout_cap, bk.kvol) + 1024,
+                                  dtype=torch.uint8, device=device)
             books[bk.key] = d
-            ws_bytes = max(ws_bytes, lib.fv2p_rulebook_workspace_bytes(cin_cap, cout_cap, bk.kvol))
         a["books"] = books
         # two scheduler words per conv step (tile counter, CTAs done); zero between launches, the kernel re-arms them
         a["sched"] = torch.zeros((len(self.steps), 2), dtype=torch.int32, device=device)
-        a["ws"] = torch.empty(ws_bytes + 1024, dtype=torch.uint8, device=device)       # strided chain
-        # submanifold books + mask sorts: one workspace per side stream
+        # mask sorts: one workspace per side stream
         a["ws_side"] = [torch.empty(ws_bytes + 1024, dtype=torch.uint8, device=device)
                         for _ in range(self.SIDE_STREAMS)]
         # feature buffers with liveness-based reuse
@@ -298,10 +300,11 @@ class BackboneEngine(object):
             main = torch.cuda.current_stream(device)
             if self.concurrent:
                 if self._side is None or self._side[0].device != device:
-                    self._side = [torch.cuda.Stream(device=device) for _ in range(self.SIDE_STREAMS + 1)]
-                side, s_conv = self._side[:-1], self._side[-1]
+                    self._side = [torch.cuda.Stream(device=device) for _ in range(self.SIDE_STREAMS + 2)]
+                side, s_pairs, s_conv = self._side[:-2], self._side[-2], self._side[-1]
             else:
-                side, s_conv = [main], main
+                side, s_pairs, s_conv = [main], main, main
+            pairs_ptr = _lib.ctypes.c_void_p(s_pairs.cuda_stream)
             counts[len(caps):].zero_()
             if n0_dev is None:
                 counts[0:1].fill_(cap0)
@@ -320,6 +323,8 @@ class BackboneEngine(object):
             #   main   the strided rulebooks, level by level (each needs the previous level's output coordinates)
             #   side   the submanifold rulebooks and every mask sort: leaves of that chain, independent of each
             #          other, dealt round-robin to SIDE_STREAMS streams (each with its own workspace)
+            #   s_pairs the compaction of the reference-layout pair lists (forked inside the rulebook calls once the
+            #          neighbour map is complete; nothing in the step waits for it but the final join)
             #   s_conv the feature pass, each layer waiting only for what it reads (the sorted set for the
             #          tensor-core kernels, the plain neighbour map otherwise)
             # The geometry kernels are small and latency bound, so they hide behind the conv kernels.
@@ -344,8 +349,8 @@ class BackboneEngine(object):
                                                     _lib.i32x3(bk.dil), _lib.ptr(pairs),
                                                     pairs.shape[2] if pairs is not None else 0,
                                                     _lib.ptr(d["pair_num"]) if pairs is not None else None,
-                                                    _lib.ptr(d["nbr"]), d["nbr"].shape[1], _lib.ptr(ws_side),
-                                                    ws_side.numel(), _lib.stream_ptr(device))
+                                                    _lib.ptr(d["nbr"]), d["nbr"].shape[1], _lib.ptr(d["ws"]),
+                                                    d["ws"].numel(), _lib.stream_ptr(device), pairs_ptr)
                     book_built[bk.key] = mark(s_side)
                 else:
                     with torch.cuda.stream(main):
@@ -358,7 +363,8 @@ class BackboneEngine(object):
                                                     pairs.shape[2] if pairs is not None else 0,
                                                     _lib.ptr(d["pair_num"]) if pairs is not None else None,
                                                     _lib.ptr(d["nbr"]), d["nbr"].shape[1], status_ptr,
-                                                    _lib.ptr(a["ws"]), a["ws"].numel(), _lib.stream_ptr(device))
+                                                    _lib.ptr(d["ws"]), d["ws"].numel(), _lib.stream_ptr(device),
+                                                    pairs_ptr)
                     level_ready[bk.out_level] = book_built[bk.key] = mark(main)
                     s_side.wait_event(book_built[bk.key])
                 _lib.check(st, "rulebook[%s]" % bk.key)
@@ -380,7 +386,7 @@ class BackboneEngine(object):
                 with torch.cuda.stream(s_conv):
                     self.run_conv_step(a, i, p, voxel_features, cap0)
             if self.concurrent:  # join: everything this step enqueued is ordered before what the caller does next
-                for s_ in side + [s_conv]:
+                for s_ in side + [s_pairs, s_conv]:
                     main.wait_event(mark(s_))
         return a
 

@@ -120,6 +120,9 @@ FV2P_API int fv2p_mean_vfe(const float *voxels, const int32_t *num_points, int64
  *             beyond index n-1 (the -1 tail is written up to n)
  *   pair_num  device [K] int32 out or NULL
  *   nbr       device [K,nbr_stride] int32 out or NULL (see header comment)
+ *   pairs_stream  NULL, or a second stream for the compaction of pairs / pair_num: it is forked from `stream`
+ *             once the neighbour map is complete, so that consumers of `nbr` need not wait for the pair lists.
+ *             The caller joins it and must leave `workspace` alone until it has drained.
  * ------------------------------------------------------------------------------------------- */
 FV2P_API size_t fv2p_rulebook_workspace_bytes(int64_t n_in_cap, int64_t n_out_cap, int kvol);
 
@@ -127,7 +130,7 @@ FV2P_API int fv2p_rulebook_subm(const int32_t *indices, int64_t n_cap, const int
                        const int32_t *shape3, const int32_t *ksize3, const int32_t *dilation3,
                        int32_t *pairs, int64_t pair_stride, int32_t *pair_num, int32_t *nbr,
                        int64_t nbr_stride, void *workspace, size_t workspace_bytes,
-                       fv2p_stream_t stream);
+                       fv2p_stream_t stream, fv2p_stream_t pairs_stream);
 
 /*   out_indices device [out_cap,4] int32 out;  n_out_dev device int32 out (live output rows)      */
 FV2P_API int fv2p_rulebook_conv(const int32_t *indices, int64_t n_cap, const int32_t *n_dev, int batch,
@@ -135,7 +138,8 @@ FV2P_API int fv2p_rulebook_conv(const int32_t *indices, int64_t n_cap, const int
                        const int32_t *pad3, const int32_t *dilation3, int32_t *out_indices,
                        int64_t out_cap, int32_t *n_out_dev, int32_t *pairs, int64_t pair_stride,
                        int32_t *pair_num, int32_t *nbr, int64_t nbr_stride, int32_t *status_dev,
-                       void *workspace, size_t workspace_bytes, fv2p_stream_t stream);
+                       void *workspace, size_t workspace_bytes, fv2p_stream_t stream,
+                       fv2p_stream_t pairs_stream);
 
 /* Reference-shaped entry: sparse_conv_ext.get_indice_pairs_3d (all.cc:26, spconv_ops.h:28-33), same
  * argument order.  subm != 0 forces stride 1 / padding ksize/2 like spconv_ops.h:76-80 and copies

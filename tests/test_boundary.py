@@ -44,7 +44,7 @@ def test_invalid_arguments_are_rejected_before_any_launch():
     lib = _lib.load()
     three = _lib.i32x3([3, 3, 3])
     st = lib.fv2p_rulebook_subm(None, 10, None, 1, three, _lib.i32x3([9, 9, 9]), three, None, 0, None, None, 0,
-                                None, 0, None)
+                                None, 0, None, None)
     assert st == -1 and b"kernel volume" in lib.fv2p_last_error()
     st = lib.fv2p_conv_fwd(None, 0, None, None, 0, None, None, None, 99, 0, None, 4, 4, None, None, None, None, 0, 0, None, None)
     assert st == -1
