@@ -57,6 +57,7 @@ constexpr int kXformThreads = 128;                           // warps 14-17, fp3
 constexpr int kTcThreadsBase = kEpiThreads + kProdThreads + 64;
 constexpr int kMaxStages = 8;
 constexpr int kSmemLimit = 232448;                 // 227 KB of dynamic shared memory per CTA
+constexpr int kSmemGuest = 12288;                  // left free so that a geometry CTA (rulebook, sort) can co-reside
 constexpr int kSmemMisc = 2048;                    // barriers and small rings + 1024-byte alignment slack
 constexpr int kNbrBufInts = FV2P_MAX_KVOL * 128;   // one tile of the neighbour map: [offset][128 rows]
 constexpr int kTileRing = 16;  // > kMaxStages + 2: how far the producers can run ahead of the epilogue, in tiles
@@ -253,7 +254,11 @@ struct Cfg {
   static constexpr int kNbrBufs = N == 128 ? 2 : (N == 64 ? 3 : 4);
   static constexpr int kNbrBytes = kNbrBufs * kNbrBufInts * 4;
   static constexpr int kAColsPerStage = 64;
-  static constexpr int kStagesSmem = (kSmemLimit - kSmemMisc - kNbrBytes) / kStageBytes;
+  // The geometry of later levels (and of the next batch) runs on other streams under the feature pass; it only
+  // gets onto an SM if the conv CTA leaves it some shared memory.  The fp32 128-wide layers come last, when little
+  // geometry is left, and lose more from a 3-deep ring than they gain (0.115 vs 0.096 ms), so they take it all.
+  static constexpr int kSmemAvail = kSmemLimit - ((kTf32 && N == 128) ? 0 : kSmemGuest);
+  static constexpr int kStagesSmem = (kSmemAvail - kSmemMisc - kNbrBytes) / kStageBytes;
   static constexpr int kStagesTmem = kTf32 ? (512 - 2 * N) / kAColsPerStage : kMaxStages;
   static constexpr int kStagesRaw = kStagesSmem < kStagesTmem ? kStagesSmem : kStagesTmem;
   static constexpr int kStages = kStagesRaw > kMaxStages ? kMaxStages : kStagesRaw;

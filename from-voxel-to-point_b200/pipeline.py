@@ -10,17 +10,22 @@ pcdet/datasets/dataset.py:137-183, pcdet/models/__init__.py:15-21, detectors/det
 
 `upload` / `launch_resident` / `launch_graph` / `finish` split the step for callers that keep the points in HBM
 and for the benchmark.  Between the H2D copy and the final D2H copy nothing synchronises with the host.
+
+`run_stream` keeps `lanes` batches in flight on the device, each with its own engine state (arena, rulebooks,
+voxel buffers) and stream: the geometry of batch i+1 (voxelize, rulebooks, sorts - small latency-bound kernels)
+runs under the feature pass of batch i instead of in front of its own.
 """
 import numpy as np
 import torch
 
 from . import _lib
+from .engine import BackboneEngine
 from .voxel_generator import BatchVoxelizer
 
 
 class HotPath(object):
     def __init__(self, backbone, voxel_size, point_cloud_range, max_points_per_voxel, max_voxels,
-                 precision=None, use_graph=False):
+                 precision=None, use_graph=False, lanes=2):
         self.backbone = backbone
         if precision is not None:
             try:
@@ -29,6 +34,11 @@ class HotPath(object):
                 setattr(backbone.model_cfg, 'PRECISION', precision)
         self.engine = backbone.get_engine()
         self.voxelizer = BatchVoxelizer(voxel_size, point_cloud_range, max_points_per_voxel, max_voxels)
+        # lane 0 is the engine the backbone module itself uses; further lanes are built on first use by run_stream
+        self._vox_args = (voxel_size, point_cloud_range, max_points_per_voxel, max_voxels)
+        self._lanes = [(self.engine, self.voxelizer)]
+        self._lane_streams = {}
+        self.lanes = max(1, int(lanes))
         self.use_graph = use_graph
         self._slots = {}
         self._graphs = {}
@@ -83,15 +93,26 @@ class HotPath(object):
         return s["dev_pts"][:total], s["dev_off"], max(sizes) if sizes else 0, nbytes
 
     # ------------------------------------------------------------------ device step
-    def launch_resident(self, points_dev, frame_offsets_dev, max_frame_points=None):
+    def _lane(self, lane):
+        """(engine, voxelizer) of `lane`; lanes beyond the first get their own state (same network, same options)."""
+        while len(self._lanes) <= lane:
+            e0 = self.engine
+            eng = BackboneEngine(self.backbone, precision=e0.precision, materialize_pairs=e0.materialize_pairs,
+                                 use_tensor_cores=e0.use_tensor_cores, sort_rows=e0.sort_rows,
+                                 concurrent=e0.concurrent)
+            self._lanes.append((eng, BatchVoxelizer(*self._vox_args)))
+        return self._lanes[lane]
+
+    def launch_resident(self, points_dev, frame_offsets_dev, max_frame_points=None, lane=0):
         """All kernels of the step on the current stream; no host sync.  Returns a handle for finish()."""
         batch = frame_offsets_dev.numel() - 1
-        vox = self.voxelizer(points_dev, frame_offsets_dev, max_frame_points)
+        engine, voxelizer = self._lane(lane)
+        vox = voxelizer(points_dev, frame_offsets_dev, max_frame_points)
         n0 = vox["voxel_offsets"][batch:batch + 1]
-        arena = self.engine.launch(vox["voxel_features"], vox["voxel_coords"], batch, n0_dev=n0, cap0=vox["cap"])
+        arena = engine.launch(vox["voxel_features"], vox["voxel_coords"], batch, n0_dev=n0, cap0=vox["cap"])
         return dict(vox=vox, arena=arena, batch=batch)
 
-    def launch_graph(self, slot=0):
+    def launch_graph(self, slot=0, lane=0):
         """Same step as launch_resident over the WHOLE staging buffer of `slot`, replayed from a CUDA graph.
 
         The step has no host synchronisation and every buffer (points staging, voxel outputs, rulebooks, feature
@@ -101,9 +122,10 @@ class HotPath(object):
         s = self._slots.get(slot)
         if s is None:
             raise RuntimeError("launch_graph: call upload() first")
-        key = (s["dev_pts"].data_ptr(), s["dev_off"].data_ptr(), s["pcap"], s["batch"])
+        key = (s["dev_pts"].data_ptr(), s["dev_off"].data_ptr(), s["pcap"], s["batch"], lane)
+        engine, voxelizer = self._lane(lane)
         entry = self._graphs.get(key)
-        if entry is not None and entry[2] != (self.engine.arena_gen, self.voxelizer.gen, self.engine._param_key):
+        if entry is not None and entry[2] != (engine.arena_gen, voxelizer.gen, engine._param_key):
             entry = None  # buffers or parameters behind the captured addresses changed: capture again
         if entry is None:
             cur = torch.cuda.current_stream(s["device"])
@@ -111,13 +133,13 @@ class HotPath(object):
             side.wait_stream(cur)
             with torch.cuda.stream(side):  # warm-up: allocates arenas, packs weights, sets kernel attributes
                 for _ in range(2):
-                    handle = self.launch_resident(s["dev_pts"], s["dev_off"], s["pcap"])
+                    handle = self.launch_resident(s["dev_pts"], s["dev_off"], s["pcap"], lane)
             cur.wait_stream(side)
             torch.cuda.synchronize(s["device"])
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                handle = self.launch_resident(s["dev_pts"], s["dev_off"], s["pcap"])
-            entry = (graph, handle, (self.engine.arena_gen, self.voxelizer.gen, self.engine._param_key))
+                handle = self.launch_resident(s["dev_pts"], s["dev_off"], s["pcap"], lane)
+            entry = (graph, handle, (engine.arena_gen, voxelizer.gen, engine._param_key))
             self._graphs[key] = entry
         entry[0].replay()
         return entry[1]
@@ -193,34 +215,50 @@ class HotPath(object):
         copy, main = self._copy_stream, torch.cuda.current_stream(device)
         lib = _lib.load()
         out_step = [st for st in self.engine.steps if st.export == "out"][0]
+        n_lanes = min(self.lanes, depth)
+        streams = []
+        for lane in range(n_lanes):
+            if lane == 0:
+                streams.append(main)
+                continue
+            st = self._lane_streams.get((device, lane))
+            if st is None:
+                st = self._lane_streams[(device, lane)] = torch.cuda.Stream(device=device)
+            st.wait_stream(main)
+            streams.append(st)
         pending = []
         for i, frames in enumerate(batches):
             slot = i % depth
+            lane = slot % n_lanes
+            stream = streams[lane]
             pts, off, mfp, h2d = self.upload(frames, device, slot=slot, stream=copy)
             up = torch.cuda.Event()
             up.record(copy)
-            main.wait_event(up)
-            handle = self.launch_graph(slot) if self.use_graph else self.launch_resident(pts, off, mfp)
-            arena = handle["arena"]
-            last = len(arena["caps"]) - 1
-            src_f = arena["bufs"][out_step.out_buf]
-            src_i = arena["indices"][last]
-            snap = self._snapshot(slot, src_f, src_i, arena["counts"])
-            n_ptr = _lib.ctypes.c_void_p(arena["counts"].data_ptr() + 4 * last)
-            with torch.cuda.device(device):
-                _lib.check(lib.fv2p_copy_rows(_lib.ptr(src_f), _lib.ptr(snap["feat"]),
-                                              src_f.shape[1] * src_f.element_size(), src_f.shape[0], n_ptr,
-                                              _lib.stream_ptr(device)), "copy_rows")
-                _lib.check(lib.fv2p_copy_rows(_lib.ptr(src_i), _lib.ptr(snap["ind"]), 16, src_i.shape[0], n_ptr,
-                                              _lib.stream_ptr(device)), "copy_rows")
-                snap["counts"].copy_(arena["counts"], non_blocking=True)
-            done = torch.cuda.Event()
-            done.record(main)
+            stream.wait_event(up)
+            with torch.cuda.stream(stream):
+                handle = self.launch_graph(slot, lane) if self.use_graph else self.launch_resident(pts, off, mfp, lane)
+                arena = handle["arena"]
+                last = len(arena["caps"]) - 1
+                src_f = arena["bufs"][out_step.out_buf]
+                src_i = arena["indices"][last]
+                snap = self._snapshot(slot, src_f, src_i, arena["counts"])
+                n_ptr = _lib.ctypes.c_void_p(arena["counts"].data_ptr() + 4 * last)
+                with torch.cuda.device(device):
+                    _lib.check(lib.fv2p_copy_rows(_lib.ptr(src_f), _lib.ptr(snap["feat"]),
+                                                  src_f.shape[1] * src_f.element_size(), src_f.shape[0], n_ptr,
+                                                  _lib.stream_ptr(device)), "copy_rows")
+                    _lib.check(lib.fv2p_copy_rows(_lib.ptr(src_i), _lib.ptr(snap["ind"]), 16, src_i.shape[0], n_ptr,
+                                                  _lib.stream_ptr(device)), "copy_rows")
+                    snap["counts"].copy_(arena["counts"], non_blocking=True)
+                done = torch.cuda.Event()
+                done.record(stream)
             pending.append((slot, snap, done, h2d, src_f.shape[1], src_f.dtype))
             if len(pending) >= depth:
                 yield self._collect(pending.pop(0), copy)
         while pending:
             yield self._collect(pending.pop(0), copy)
+        for st in streams[1:]:
+            main.wait_stream(st)
 
     def _snapshot(self, slot, feat, ind, counts):
         key = ("snap", slot)
