@@ -325,7 +325,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
       // fp32: gathers land on `landed` (one expect_tx arrive), the transform warps + the weight copy on `full`.
       // LSU gather: + the 32 cp.async arrivals of the owning warp (the fp32 `landed` barrier also gets one plain
       // arrive that publishes the stage flags).
-      const uint32_t a_arrivals = use_tma ? 1u : 33u;
+      // A slot of a ring shorter than the producer warp count is filled by two warps (half the rows each).
+      const uint32_t a_arrivals = use_tma ? 1u : (s + C::kStages < kProdWarps ? 65u : 33u);
       mbar_init(bar_full + 8 * s, kTf32 ? kXformThreads + 1 : a_arrivals);
       mbar_init(bar_empty + 8 * s, 1);
       mbar_init(bar_landed + 8 * s, a_arrivals);
@@ -357,6 +358,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
     // No block-level synchronisation: a warp takes the tile's neighbour rows and offset mask from the scheduler's
     // ring, issues the stages whose ring slot it owns, and hands the buffer back.
     const int pwarp = (threadIdx.x - kEpiThreads) >> 5;
+    // Warp w fills ring slot w % kStages, always the same one, so that each empty barrier is waited on in program
+    // order by its owners (the parity wait cannot alias, whatever the drift between warps).  Slots with a second
+    // owner (w + kStages is still a producer warp) are filled half and half; a third owner would idle.
+    const int my_slot = pwarp % C::kStages, my_part = pwarp / C::kStages;
     const uint8_t *feat = static_cast<const uint8_t *>(feat_ptr);
     const size_t feat_row_bytes = (size_t)cin * kElem;
     uint32_t issued = 0;
@@ -384,10 +389,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
       if (tile < 0) {
         // Sentinel stage: same arrivals as a real stage, no copies; tells the other roles to stop.
         const uint32_t s = issued % C::kStages;
-        if ((int)(s % kProdWarps) == pwarp) {
+        if ((int)s == my_slot && my_part < 2) {
           mbar_wait(bar_empty + 8 * s, ((issued / C::kStages) & 1) ^ 1);
           const uint32_t a_bar = kTf32 ? bar_landed + 8 * s : bar_full + 8 * s;
-          if (lane == 0) {
+          if (lane == 0 && my_part == 0) {
             stage_flags[s] = kFlagStop;
             if constexpr (kTf32) {
               if (use_tma) mbar_arrive_expect_tx(bar_landed + 8 * s, 0u);
@@ -412,11 +417,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
         const int k = __ffs(mask) - 1;
         mask &= mask - 1;
         for (int sl = 0; sl < slices; ++sl, ++issued) {
-          // A ring slot always belongs to the same producer warp, so each empty barrier is waited on by one warp
-          // in program order (the parity wait cannot alias, whatever the drift between warps); warps without a
-          // slot of their own (ring shorter than the warp count) idle.
           const uint32_t s = issued % C::kStages;
-          if ((int)(s % kProdWarps) != pwarp) continue;
+          if ((int)s != my_slot || my_part >= 2) continue;
+          const int rows_here = (s + C::kStages < kProdWarps) ? kTileM / 2 : kTileM;  // rows this warp gathers
+          const int row_base = my_part * rows_here;
           {
             TC_T0();
             mbar_wait(bar_empty + 8 * s, ((issued / C::kStages) & 1) ^ 1);
@@ -425,7 +429,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
           TC_T0();
           const uint32_t a_u32 = smem_u32(stage_base + (size_t)s * C::kStageBytes);
           const uint32_t a_bar = kTf32 ? bar_landed + 8 * s : bar_full + 8 * s;
-          if (lane == 0) {
+          if (lane == 0 && my_part == 0) {
             stage_flags[s] = ((k == (int)first_k && sl == 0) ? kFlagFirst : 0) |
                              ((k == (int)last_k && sl == slices - 1) ? kFlagLast : 0);
             const uint32_t wb = w_stage_bytes * (kTf32 ? 2 : 1);
@@ -444,12 +448,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
           }
           __syncwarp();
           if (use_tma) {
-            // lane l gathers tile rows 4l..4l+3; a missing neighbour becomes an out-of-range row (zero fill)
-            int4 rows = *reinterpret_cast<const int4 *>(&nbr_b[k * kTileM + 4 * lane]);
-            rows.x = rows.x < 0 ? oob_row : rows.x, rows.y = rows.y < 0 ? oob_row : rows.y;
-            rows.z = rows.z < 0 ? oob_row : rows.z, rows.w = rows.w < 0 ? oob_row : rows.w;
-            tma_gather4(a_u32 + (uint32_t)(4 * lane) * row_bytes, &feat_map, sl * (row_bytes / kElem), rows.x, rows.y,
-                        rows.z, rows.w, a_bar);
+            // lane l gathers four of this warp's rows; a missing neighbour becomes an out-of-range row (zero fill)
+            if (4 * lane < rows_here) {
+              const int r4 = row_base + 4 * lane;
+              int4 rows = *reinterpret_cast<const int4 *>(&nbr_b[k * kTileM + r4]);
+              rows.x = rows.x < 0 ? oob_row : rows.x, rows.y = rows.y < 0 ? oob_row : rows.y;
+              rows.z = rows.z < 0 ? oob_row : rows.z, rows.w = rows.w < 0 ? oob_row : rows.w;
+              tma_gather4(a_u32 + (uint32_t)r4 * row_bytes, &feat_map, sl * (row_bytes / kElem), rows.x, rows.y,
+                          rows.z, rows.w, a_bar);
+            }
           } else {
             // Lane group g = lane / chunks owns the contiguous rows [g*rpg, (g+1)*rpg): its row indices come in
             // with 16-byte shared loads, and every warp instruction still reads whole rows (full 128-byte lines for
@@ -458,7 +465,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
             if (chunks < 8) {  // narrow rows: interleaved rows per instruction measured faster (0.046 vs 0.053 ms, 16->16)
               const int *rows_k = nbr_b + k * kTileM;
 #pragma unroll 4
-              for (int r = my_row0; r < kTileM; r += rows_per_instr) {
+              for (int r = row_base + my_row0; r < row_base + rows_here; r += rows_per_instr) {
                 const int src = rows_k[r];
                 const uint32_t swz = (uint32_t)(my_chunk ^ ((r >> (3 - cshift)) & (chunks - 1)));
                 cp_async16(a_u32 + (uint32_t)r * row_bytes + (swz << 4),
@@ -468,8 +475,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
               TC_ACC(tm_pissue);
               continue;
             }
-            const int rpg = kTileM >> (5 - cshift);  // rows per lane group: 32, 16 or 8
-            const int r_first = (lane >> cshift) * rpg;
+            const int rpg = rows_here >> (5 - cshift);  // rows per lane group: 32, 16 or 8 (half with two owners)
+            const int r_first = row_base + (lane >> cshift) * rpg;
             const int4 *idx4 = reinterpret_cast<const int4 *>(nbr_b + k * kTileM + r_first);
             const uint32_t dst0 = a_u32 + (uint32_t)r_first * row_bytes;
             for (int q = 0; q < (rpg >> 2); ++q) {
@@ -961,7 +968,7 @@ int launch_one(const void *features, int64_t feat_rows, const void *weight, cons
   // path also has to feed the transform warps there), the swizzled cp.async gather everywhere else.  (A third
   // producer, LDG + hi/lo split in registers + STS without transform warps, never won and was removed:
   // 0.182 vs 0.172 ms on 64->64, 0.248 vs 0.221 ms on 128->128.)
-  const int use_tma = g_tc_gather_mode >= 0 ? g_tc_gather_mode : ((kTf32 && cin >= 32) ? 1 : 0);
+  const int use_tma = g_tc_gather_mode >= 0 ? g_tc_gather_mode : 0;
   int64_t tiles = (n_out_cap + kTileM - 1) / kTileM;
   int grid = (int)(tiles < sm_count() ? tiles : sm_count());
   if (grid < 1) grid = 1;
