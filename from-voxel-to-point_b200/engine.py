@@ -456,8 +456,8 @@ class BackboneEngine(object):
                 n += 5 if self.materialize_pairs else 3  # clear, insert, probe (+ scan, compact)
             else:
                 n += 9 if self.materialize_pairs else 7  # clear, insert, winners, scan, assign, fill, pairs (+2)
-            if self.sort_rows:
-                n += 2 + 3 * ((bk.kvol + 8) // 9)  # mask, 3 kernels per 9-bit radix pass, permute
+            if self.sort_rows:  # mask, 3 kernels per 9-bit radix pass, permute, tile masks, tile ranking
+                n += 4 + 3 * ((bk.kvol + 8) // 9)
         return n
 
     def __call__(self, voxel_features, voxel_coords, batch_size):
