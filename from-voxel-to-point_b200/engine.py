@@ -451,12 +451,14 @@ class BackboneEngine(object):
     def launch_count(self):
         """Kernels of libfv2p_b200 enqueued by one launch(): rulebook chains + one fused conv per layer."""
         n = len(self.steps)
+        tc_modes = (_lib.MODE_BF16_TC, _lib.MODE_TF32X3_TC)
+        tc_books = {st.key for st in self.steps if self._mode_for(st) in tc_modes}
         for bk in self.books:
             if bk.subm:
                 n += 5 if self.materialize_pairs else 3  # clear, insert, probe (+ scan, compact)
             else:
                 n += 9 if self.materialize_pairs else 7  # clear, insert, winners, scan, assign, fill, pairs (+2)
-            if self.sort_rows:  # mask, 3 kernels per 9-bit radix pass, permute, tile masks, tile ranking
+            if self.sort_rows and bk.key in tc_books:  # mask, 3 per 9-bit radix pass, permute, tile masks, ranking
                 n += 4 + 3 * ((bk.kvol + 8) // 9)
         return n
 
