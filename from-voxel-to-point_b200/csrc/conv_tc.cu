@@ -9,30 +9,31 @@
 //   K loop        the kernel offsets that have at least one neighbour in the tile  x  Cin in 128-byte slices
 //   A operand     the gathered input rows in the 128B/64B/32B-swizzled K-major tile tcgen05.mma reads.  Two
 //                 interchangeable producers (profiles/r1_notes.md has the measurements):
-//                   * TMA: cp.async.bulk.tensor ... tile::gather4 pulls four arbitrary feature rows per
-//                     instruction; a missing neighbour is an out-of-range row index that the TMA zero fills;
-//                   * LSU: 16-byte cp.async (LDGSTS), eight lanes per row so that every warp instruction reads
-//                     whole 128-byte lines and, thanks to the swizzle, writes conflict-free; a missing
+//                   * LSU (default): 16-byte cp.async (LDGSTS), eight lanes per row so that every warp instruction
+//                     reads whole 128-byte lines and, thanks to the swizzle, writes conflict-free; a missing
 //                     neighbour is a zero-fill cp.async; the stage is handed over with
-//                     cp.async.mbarrier.arrive, so the issuing warp never waits for its copies.
-//                 Each ring slot is owned by one producer warp, so the waits and arrivals of one stage overlap
-//                 the copy issue of the next ones.  Either way the MMA needs no predication
-//                 and nothing is scattered afterwards.
+//                     cp.async.mbarrier.arrive, so the issuing warp never waits for its copies;
+//                   * TMA: cp.async.bulk.tensor ... tile::gather4 pulls four arbitrary feature rows per
+//                     instruction; a missing neighbour is an out-of-range row index that the TMA zero fills.
+//                 Warps 4-11; each ring slot is owned by one warp (two, half the rows each, when the ring is
+//                 shorter than eight), so the waits and arrivals of one stage overlap the copy issue of the next
+//                 ones.  Either way the MMA needs no predication and nothing is scattered afterwards.
 //   B operand     W[k] slices, pre-packed once per layer into the exact (swizzled) shared-memory image and
 //                 pulled with one TMA bulk copy per stage
-//   MMA           one elected lane of warp 12 issues tcgen05.mma (kind::f16 for bf16, kind::tf32 for fp32);
-//                 tcgen05.commit releases the smem stage / publishes the accumulator through mbarriers
+//   MMA           one elected thread of warp 12 runs the whole tcgen05.mma issue loop (kind::f16 for bf16,
+//                 kind::tf32 for fp32); tcgen05.commit releases the smem stage / publishes the accumulator
 //   epilogue      warps 0-3 read TMEM with tcgen05.ld (one accumulator row per thread), apply
 //                 bias + folded BatchNorm + residual + ReLU and store 16-byte vectors
-//   tiles         handed out from an atomic counter in the order fv2p_sort_rows_by_mask computed (most active
-//                 offsets first = longest-processing-time-first list scheduling): with mask-sorted rows a tile
-//                 takes 1..27 offsets, and dealing tiles round-robin left the busiest CTA with 1.3-2.2x the mean
-//                 work (KITTI: 180 stages against a mean of 81 on the 128->128 layers).  The producers fetch the
-//                 tile ids (one tile ahead of the neighbour prefetch, so the atomic's latency is hidden), publish
-//                 them through a small shared ring for the epilogue, and end the stream with a sentinel stage.
+//   tiles         warp 13 is the scheduler: it claims tiles in the order fv2p_sort_rows_by_mask computed (most
+//                 active offsets first = longest-processing-time-first list scheduling; with mask-sorted rows a
+//                 tile takes 1..27 offsets, and dealing tiles round-robin left the busiest CTA with 1.3-2.2x the
+//                 mean work: 180 stages against a mean of 81 on KITTI's 128->128 layers), and streams the rows of
+//                 the neighbour map the tile needs - only the offsets in its mask - into a shared-memory ring with
+//                 bulk copies, a few tiles ahead of the producers.  Tile ids reach the epilogue through a small
+//                 ring; a sentinel tile / stage ends the stream for every role.
 //
 // fp32 path = 3xTF32 with the A operand in tensor memory: the gathered fp32 tile lands in shared memory, four
-// transform warps (13-16, one per TMEM lane quadrant, one row per thread) split it into hi = rn_tf32(x) and
+// transform warps (14-17, one per TMEM lane quadrant, one row per thread) split it into hi = rn_tf32(x) and
 // lo = rn_tf32(x - hi) and write both with tcgen05.st into a TMEM ring; W is packed as hi/lo shared-memory images, and
 // each K step issues A_lo*W_hi + A_hi*W_lo + A_hi*W_hi with A read from TMEM (tcgen05.mma [d], [a], b-desc).
 // Shared memory then only carries the raw tile once and the W slices: with both operands in shared memory the
