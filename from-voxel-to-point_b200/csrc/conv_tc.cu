@@ -34,12 +34,14 @@
 //
 // fp32 path = 3xTF32 with the A operand in tensor memory: the gathered fp32 tile lands in shared memory, four
 // transform warps (14-17, one per TMEM lane quadrant, one row per thread) split it into hi = rn_tf32(x) and
-// lo = rn_tf32(x - hi) and write both with tcgen05.st into a TMEM ring; W is packed as hi/lo shared-memory images, and
-// each K step issues A_lo*W_hi + A_hi*W_lo + A_hi*W_hi with A read from TMEM (tcgen05.mma [d], [a], b-desc).
+// lo = x - hi and write hi (tf32) and the pair [lo | hi] (bf16) with tcgen05.st into a TMEM ring; W is packed as a
+// tf32 W_hi image and a bf16 [W_hi; W_lo] image, and each 8-channel K step issues two MMAs with A read from TMEM
+// (tcgen05.mma [d], [a], b-desc): A_hi*W_hi as kind::tf32 and both correction terms A_lo*W_hi + A_hi*W_lo as ONE
+// kind::f16 MMA of K = 16 (they only need ~2^-9 relative accuracy: the products are already 2^-11 down).
 // Shared memory then only carries the raw tile once and the W slices: with both operands in shared memory the
 // kernel was bound by that pipe (16 KB landed + 48 KB split traffic + 12 x 8 KB operand reads per stage
-// ~ 1500 cycles at 128 B/cycle, against 768 cycles of tensor work at N=128).  The dropped lo*lo term and the
-// rounding of the lo parts are O(2^-22) relative and unbiased.  What remains (measured 1-2e-5 at 27*128 terms) is
+// ~ 1500 cycles at 128 B/cycle, against 768 cycles of tensor work at N=128).  The dropped lo*lo term is O(2^-22)
+// relative, the bf16 rounding of the correction operands O(2^-20), both unbiased.  What remains (measured 1-2e-5 at 27*128 terms) is
 // the tensor core's truncating fp32 accumulation, 5x inside the 1e-4 bar.
 #include <cuda.h>
 
@@ -167,6 +169,19 @@ __device__ __forceinline__ void tc_mma_ts_tf32(uint32_t d_tmem, uint32_t a_tmem,
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
       "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// Same with 16-bit A elements (two per 32-bit column, K-consecutive)
+__device__ __forceinline__ void tc_mma_ts_f16(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo_elem, hi_elem);  // .x (low half) = first K element
+  return *reinterpret_cast<uint32_t *>(&v);
 }
 // 16 consecutive 32-bit columns of this thread's TMEM lane (the warp covers its 32-lane quadrant)
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t *r) {
@@ -599,6 +614,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
   } else if (warp == kMmaWarp) {
     // =============================== MMA issuer ===============================
     constexpr uint32_t idesc = instr_desc(N, kTf32);
+    constexpr uint32_t idesc_corr = instr_desc(N, false);  // fp32 path: bf16 correction MMAs
+    (void)idesc_corr;
     const uint32_t sbo = 8u * (uint32_t)row_bytes;
     const uint32_t layout = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
     const int ksteps = row_bytes >> 5;  // 32 bytes of K per MMA (16 bf16 / 8 tf32)
@@ -651,9 +668,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
             if (j < ksteps) {
               const uint64_t adv = (uint64_t)(2 * j);  // 32 bytes of K
               if constexpr (kTf32) {
-                const uint32_t a_hi = a_tmem0 + s * (uint32_t)C::kAColsPerStage + 8u * (uint32_t)j;  // 8 tf32 of K
-                tc_mma_ts_tf32(d_tmem, a_hi + 32u, b_desc + adv, idesc, accumulate);
-                tc_mma_ts_tf32(d_tmem, a_hi, b_desc + w_lo_off + adv, idesc, 1u);
+                // 8 input channels per step: hi*hi as tf32, both correction terms as one bf16 MMA of K = 16
+                const uint32_t a_hi = a_tmem0 + s * (uint32_t)C::kAColsPerStage + 8u * (uint32_t)j;
+                tc_mma_ts_f16(d_tmem, a_hi + 32u, b_desc + w_lo_off + adv, idesc_corr, accumulate);
                 tc_mma_ts_tf32(d_tmem, a_hi, b_desc + adv, idesc, 1u);
               } else {
                 tc_mma<false>(d_tmem, a_desc + adv, b_desc + adv, idesc, accumulate);
@@ -711,19 +728,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
 #pragma unroll
               for (int c = 0; c < 4; ++c)
                 x[c] = *reinterpret_cast<const float4 *>(row + (((uint32_t)(half * 4 + c) ^ swz_row) << 4));
-              uint32_t hi[16], lo[16];
+              // hi: 16 tf32 columns.  corr: per 8-channel K step, [lo0..lo7 | hi0..hi7] as bf16 pairs = 8 columns,
+              // the A operand of the correction MMA (its B operand is [W_hi; W_lo] in bf16, see pack_weight_kernel).
+              uint32_t hi[16], corr[16];
 #pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                const float v[4] = {x[c].x, x[c].y, x[c].z, x[c].w};
+              for (int u = 0; u < 2; ++u) {  // K step inside this half = chunks 2u, 2u+1
+                float h[8], l[8];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float h = tf32_rn_alu(v[e]);
-                  hi[4 * c + e] = __float_as_uint(h);
-                  lo[4 * c + e] = __float_as_uint(tf32_rn_alu(v[e] - h));
+                for (int c = 0; c < 2; ++c) {
+                  const float v[4] = {x[2 * u + c].x, x[2 * u + c].y, x[2 * u + c].z, x[2 * u + c].w};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    h[4 * c + e] = tf32_rn_alu(v[e]);
+                    l[4 * c + e] = v[e] - h[4 * c + e];
+                    hi[8 * u + 4 * c + e] = __float_as_uint(h[4 * c + e]);
+                  }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  corr[8 * u + q] = pack_bf16x2(l[2 * q], l[2 * q + 1]);
+                  corr[8 * u + 4 + q] = pack_bf16x2(h[2 * q], h[2 * q + 1]);
                 }
               }
               tmem_st16(a_cols + 16u * half, hi);
-              tmem_st16(a_cols + 32u + 16u * half, lo);
+              tmem_st16(a_cols + 32u + 16u * half, corr);
             }
           }
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -892,9 +920,15 @@ pack_weight_kernel(const float *__restrict__ w, int kvol, int cin, int cout, uin
     const float val = w[e];
     uint8_t *base = packed + ((size_t)k * slices + sl) * image * (kTf32 ? 2 : 1);
     if constexpr (kTf32) {
+      // image 0: W_hi as tf32.  image 1: the B operand of the bf16 correction MMA - per 8-channel K step the 16
+      // K elements [W_hi(8) | W_lo(8)], matching A = [A_lo(8) | A_hi(8)]: sum A_lo*W_hi + A_hi*W_lo.
       const float hi = tf32_rn(val);
       reinterpret_cast<float *>(base + off)[t] = hi;
-      reinterpret_cast<float *>(base + image + off)[t] = tf32_rn(val - hi);
+      const int j = within / 8, q = within % 8;
+      uint8_t *corr = base + image;
+      reinterpret_cast<__nv_bfloat16 *>(corr + swizzled_offset(n, 2 * j, row_bytes))[q] = __float2bfloat16_rn(hi);
+      reinterpret_cast<__nv_bfloat16 *>(corr + swizzled_offset(n, 2 * j + 1, row_bytes))[q] =
+          __float2bfloat16_rn(val - hi);
     } else {
       reinterpret_cast<__nv_bfloat16 *>(base + off)[t] = __float2bfloat16_rn(val);
     }
