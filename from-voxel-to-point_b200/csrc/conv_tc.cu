@@ -235,7 +235,7 @@ __host__ __device__ constexpr uint32_t instr_desc(int n, bool tf32) {
 // 7 = CTA 0 stamps %globaltimer at entry/exit into g_tc_stamps (profiles/timeline.py).  0 in production.
 __device__ int g_tc_debug = 0;
 constexpr int kStampSlots = 256;
-__device__ unsigned long long g_tc_stamps[kStampSlots][2];
+__device__ unsigned long long g_tc_stamps[kStampSlots][4];  // start, end, cin * 1000 + N, output pointer
 __device__ unsigned int g_tc_stamp_n = 0;
 #ifdef FV2P_TC_TIMERS
 // Role timers (profiling builds only: FV2P_EXTRA_NVCC_FLAGS=-DFV2P_TC_TIMERS python build.py --force).
@@ -325,6 +325,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
   if (dbg == 7 && blockIdx.x == 0 && threadIdx.x == 0) {
     stamp_slot = atomicAdd(&g_tc_stamp_n, 1u) % kStampSlots;
     g_tc_stamps[stamp_slot][0] = global_timer();
+    g_tc_stamps[stamp_slot][2] = (unsigned long long)(cin * 1000 + N);
+    g_tc_stamps[stamp_slot][3] = (unsigned long long)(uintptr_t)ep.out;
   }
   const bool use_tma = use_tma_arg == 1;
   int n_out = n_out_dev ? *n_out_dev : (int)n_out_cap;
@@ -1057,12 +1059,12 @@ extern "C" __attribute__((visibility("default"))) int fv2p_debug_poll(int v) {
   return (int)cudaMemcpyToSymbol(g_tc_poll, &v, sizeof(int));
 }
 
-// copies the stamp table to `out` ([256][2] u64), returns the number of stamps taken and resets the counter
+// copies the stamp table to `out` ([256][4] u64), returns the number of stamps taken and resets the counter
 extern "C" __attribute__((visibility("default"))) int fv2p_debug_stamps(unsigned long long *out) {
   unsigned int n = 0, zero = 0;
   cudaDeviceSynchronize();
   cudaMemcpyFromSymbol(&n, g_tc_stamp_n, sizeof(n));
-  cudaMemcpyFromSymbol(out, g_tc_stamps, sizeof(unsigned long long) * kStampSlots * 2);
+  cudaMemcpyFromSymbol(out, g_tc_stamps, sizeof(unsigned long long) * kStampSlots * 4);
   cudaMemcpyToSymbol(g_tc_stamp_n, &zero, sizeof(zero));
   return (int)n;
 }
