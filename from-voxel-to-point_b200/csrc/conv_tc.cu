@@ -138,6 +138,12 @@ __device__ __forceinline__ bool elect_one_sync() {
       : "r"(0xFFFFFFFFu));
   return pred != 0;
 }
+// Programmatic dependent launch: let the next kernel on the stream start its set-up / wait for the previous one's
+// results (no-ops when the kernel was not launched with the attribute).
+__device__ __forceinline__ void griddep_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -258,6 +264,7 @@ __device__ __forceinline__ unsigned long long global_timer() {
 }
 // Host-side choice of the A-tile producer: -1 = auto (measured best per shape), 0 = LSU (cp.async), 1 = TMA gather4.
 int g_tc_gather_mode = -1;
+int g_tc_pdl = 1;  // programmatic dependent launch of the tensor-core conv kernels (debug switch: fv2p_debug_pdl)
 
 template <bool kTf32, int N>
 struct Cfg {
@@ -329,6 +336,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
     g_tc_stamps[stamp_slot][3] = (unsigned long long)(uintptr_t)ep.out;
   }
   const bool use_tma = use_tma_arg == 1;
+  griddep_launch_dependents();
   int n_out = n_out_dev ? *n_out_dev : (int)n_out_cap;
   if (n_out > n_out_cap) n_out = (int)n_out_cap;
   const int n_tiles = (n_out + kTileM - 1) / kTileM;
@@ -394,6 +402,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
     TC_TIMER_DECL(tm_pissue);
     TC_TIMER_DECL(tm_ppro);
     TC_TIMER_DECL(tm_tiles);
+    griddep_wait();  // the features gathered below are the previous layer's output
     for (uint32_t seq = 0;; ++seq) {
       const uint32_t nb = seq % C::kNbrBufs;
       {
@@ -778,6 +787,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
     uint32_t acc_phase = 0;
     TC_TIMER_DECL(tm_ewait);
     TC_TIMER_DECL(tm_ework);
+    griddep_wait();  // residual rows come from an earlier layer; the output buffer may still be read by the previous one
     for (uint32_t seq = 0;; ++seq) {
       {
         TC_T0();
@@ -1009,10 +1019,25 @@ int launch_one(const void *features, int64_t feat_rows, const void *weight, cons
   int64_t tiles = (n_out_cap + kTileM - 1) / kTileM;
   int grid = (int)(tiles < sm_count() ? tiles : sm_count());
   if (grid < 1) grid = 1;
-  conv_tc_kernel<kTf32, N><<<grid, C::kThreads, C::kSmemBytes, stream>>>(
-      map, features, static_cast<const uint8_t *>(weight), nbr, nbr_stride, row_perm, tile_order, sched, kvol,
-      n_out_cap, n_out_dev, cin, (int)feat_rows, use_tma, ep);
-  return cuda_status(cudaGetLastError(), "conv_fwd(tc)");
+  // Programmatic dependent launch: the layers of a backbone follow each other on one stream, and this kernel's
+  // set-up (barriers, TMEM, the scheduler's first tiles, which only read geometry) does not depend on the previous
+  // layer.  Its CTAs may therefore start while the previous kernel drains; the roles that touch feature memory
+  // execute griddepcontrol.wait first.
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)C::kThreads);
+  cfg.dynamicSmemBytes = C::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = g_tc_pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const uint8_t *wp = static_cast<const uint8_t *>(weight);
+  const int oob = (int)feat_rows;
+  return cuda_status(cudaLaunchKernelEx(&cfg, conv_tc_kernel<kTf32, N>, map, features, wp, nbr, nbr_stride, row_perm,
+                                        tile_order, sched, kvol, n_out_cap, n_out_dev, cin, oob, use_tma, ep),
+                     "conv_fwd(tc)");
 }
 
 }  // namespace
@@ -1053,6 +1078,11 @@ using namespace fv2p;
 extern "C" int fv2p_tc_gather_mode(int mode) {
   g_tc_gather_mode = mode < 0 ? -1 : (mode > 1 ? 1 : mode);
   return FV2P_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int fv2p_debug_pdl(int v) {
+  g_tc_pdl = v ? 1 : 0;
+  return 0;
 }
 
 extern "C" __attribute__((visibility("default"))) int fv2p_debug_poll(int v) {
