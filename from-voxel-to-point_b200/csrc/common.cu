@@ -35,6 +35,19 @@ int sm_count() {
   return cached;
 }
 
+// Work that is off the caller's dependency chain moves to a second stream: `to` waits for what `from` has enqueued
+// so far.  Returns the stream to continue on (`from` itself when there is no second stream).
+cudaStream_t fork_stream(cudaStream_t from, void *to_) {
+  cudaStream_t to = static_cast<cudaStream_t>(to_);
+  if (!to_ || to == from) return from;
+  cudaEvent_t ev;
+  if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return from;
+  cudaEventRecord(ev, from);
+  cudaStreamWaitEvent(to, ev, 0);
+  cudaEventDestroy(ev);
+  return to;
+}
+
 __global__ void set_scalar_kernel(int *dst, int value) { *dst = value; }
 
 void launch_set_scalar(int *dst, int value, cudaStream_t stream) {

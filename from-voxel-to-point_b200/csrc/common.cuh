@@ -160,6 +160,7 @@ void launch_scan_chunk_counts(int *counts, int segments, int64_t seg_stride, con
                               int64_t n_cap, int *totals, cudaStream_t stream);
 
 __global__ void set_scalar_kernel(int *dst, int value);
+cudaStream_t fork_stream(cudaStream_t from, void *to);
 void launch_set_scalar(int *dst, int value, cudaStream_t stream);
 
 }  // namespace fv2p

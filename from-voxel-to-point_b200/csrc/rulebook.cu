@@ -501,16 +501,9 @@ int fill_geom(Geom &g, const int32_t *out_shape3, const int32_t *ksize3, const i
 using namespace fv2p;
 
 // The pair lists are only needed by consumers of the reference-layout tensors; with a second stream their compaction
-// leaves the caller's dependency chain (the neighbour map is complete before it).  Returns the stream to compact on.
+// leaves the caller's dependency chain (the neighbour map is complete before it).
 static cudaStream_t fork_for_pairs(cudaStream_t stream, fv2p_stream_t pairs_stream_) {
-  cudaStream_t ps = static_cast<cudaStream_t>(pairs_stream_);
-  if (!pairs_stream_ || ps == stream) return stream;
-  cudaEvent_t ev;
-  if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return stream;
-  cudaEventRecord(ev, stream);
-  cudaStreamWaitEvent(ps, ev, 0);
-  cudaEventDestroy(ev);
-  return ps;
+  return fork_stream(stream, pairs_stream_);
 }
 
 extern "C" size_t fv2p_rulebook_workspace_bytes(int64_t n_in_cap, int64_t n_out_cap, int kvol) {

@@ -295,7 +295,7 @@ extern "C" int fv2p_voxelize_mean(const float *points, const int32_t *frame_offs
                                   int max_voxels, int32_t *coords, float *voxel_features,
                                   int32_t *num_points, float *voxels, int32_t *voxel_offsets, int64_t cap,
                                   int32_t *status_dev, void *workspace, size_t workspace_bytes,
-                                  fv2p_stream_t stream_) {
+                                  fv2p_stream_t stream_, fv2p_stream_t features_stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   FV2P_REQUIRE(batch >= 1 && batch <= 4096, "voxelize: batch must be in [1,4096], got %d", batch);
   FV2P_REQUIRE(num_features >= 3 && num_features <= kMaxFeatures,
@@ -334,6 +334,8 @@ extern "C" int fv2p_voxelize_mean(const float *points, const int32_t *frame_offs
   vox_assign_kernel<<<grid, kThreads, 0, stream>>>(frame_offsets, batch, w.max_chunks, w.pslot, w.first, w.keys,
                                                    w.counts, voxel_offsets, max_voxels, max_points, g,
                                                    w.slot_vid, w.cut, coords, w.sel);
+  // coords and voxel_offsets are final here; the point selection and the means can leave the caller's chain
+  stream = fork_stream(stream, features_stream_);
   vox_select_kernel<<<grid, kThreads, 0, stream>>>(frame_offsets, batch, w.max_chunks, w.pslot, w.slot_vid, w.cut,
                                                    max_points, w.sel);
   vox_reduce_kernel<<<grid, kThreads, 0, stream>>>(points, num_features, voxel_offsets, batch, max_points, w.sel,
@@ -356,7 +358,8 @@ extern "C" int fv2p_voxel_generate(const float *points, int64_t num_points_in, i
   launch_set_scalar(offs + 1, (int)num_points_in, stream);
   int st = fv2p_voxelize_mean(points, offs, num_points_in, 1, num_points_in, num_features, range6, vsize3,
                               max_points, max_voxels, coords, voxel_features, num_points, voxels, offs + 4, cap,
-                              nullptr, static_cast<char *>(workspace) + 1024, workspace_bytes - 1024, stream_);
+                              nullptr, static_cast<char *>(workspace) + 1024, workspace_bytes - 1024, stream_,
+                              nullptr);
   if (st) return st;
   int voff[2] = {0, 0};
   st = cuda_status(cudaMemcpyAsync(voff, offs + 4, sizeof(voff), cudaMemcpyDeviceToHost, stream), "voxel_generate");

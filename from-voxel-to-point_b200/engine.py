@@ -278,8 +278,9 @@ class BackboneEngine(object):
         return a
 
     # ------------------------------------------------------------------ run
-    def launch(self, voxel_features, voxel_coords, batch_size, n0_dev=None, cap0=None):
+    def launch(self, voxel_features, voxel_coords, batch_size, n0_dev=None, cap0=None, features_ready=None):
         """Enqueues geometry + feature passes on the current stream.  No host sync.
+        ``features_ready``: event after which voxel_features may be read (None: already ordered on this stream).
 
         voxel_features [>=cap0, F] fp32, voxel_coords [>=cap0, 4] int32, both CUDA and contiguous;
         live row count = *n0_dev (device int32) if given, else cap0 (defaults to voxel_coords.shape[0]).
@@ -378,6 +379,8 @@ class BackboneEngine(object):
                     _lib.check(st, "sort_rows[%s]" % bk.key)
                     book_sorted[bk.key] = mark(s_side)
             waited = set()
+            if features_ready is not None:
+                s_conv.wait_event(features_ready)
             for i, (st_, p) in enumerate(zip(self.steps, prm)):
                 needs = book_sorted if self.conv_operands(a, st_, p)[1] is not None else book_built
                 if (st_.key, id(needs)) not in waited:

@@ -107,9 +107,17 @@ class HotPath(object):
         """All kernels of the step on the current stream; no host sync.  Returns a handle for finish()."""
         batch = frame_offsets_dev.numel() - 1
         engine, voxelizer = self._lane(lane)
-        vox = voxelizer(points_dev, frame_offsets_dev, max_frame_points)
+        # the rulebooks only read coordinates: the means are finished on a stream of their own (joined by the
+        # engine before the entry layer reads them)
+        fs = None
+        if engine.concurrent:
+            fs = self._lane_streams.get((points_dev.device, "feat", lane))
+            if fs is None:
+                fs = self._lane_streams[(points_dev.device, "feat", lane)] = torch.cuda.Stream(device=points_dev.device)
+        vox = voxelizer(points_dev, frame_offsets_dev, max_frame_points, features_stream=fs)
         n0 = vox["voxel_offsets"][batch:batch + 1]
-        arena = engine.launch(vox["voxel_features"], vox["voxel_coords"], batch, n0_dev=n0, cap0=vox["cap"])
+        arena = engine.launch(vox["voxel_features"], vox["voxel_coords"], batch, n0_dev=n0, cap0=vox["cap"],
+                              features_ready=vox["features_ready"])
         return dict(vox=vox, arena=arena, batch=batch)
 
     def launch_graph(self, slot=0, lane=0):

@@ -121,9 +121,12 @@ class BatchVoxelizer(object):
             self.gen += 1
         return b
 
-    def __call__(self, points, frame_offsets, max_frame_points=None):
+    def __call__(self, points, frame_offsets, max_frame_points=None, features_stream=None):
         """points [P,F] fp32 CUDA, frame_offsets [B+1] int32 CUDA.  Returns a dict of device buffers sized at
-        capacity plus 'voxel_offsets' [B+1]; live rows are [:voxel_offsets[B]]."""
+        capacity plus 'voxel_offsets' [B+1]; live rows are [:voxel_offsets[B]].
+
+        With ``features_stream`` the coordinates are complete on the current stream and the means / point counts on
+        that stream; 'features_ready' is then the event to wait for before reading them."""
         dev = _lib.require_device(points)
         assert points.dtype == torch.float32 and points.is_contiguous()
         assert frame_offsets.dtype == torch.int32 and frame_offsets.is_cuda
@@ -137,7 +140,13 @@ class BatchVoxelizer(object):
                 _lib.f32arr(vg._point_cloud_range), _lib.f32arr(vg._voxel_size), int(vg._max_num_points),
                 int(vg._max_voxels), _lib.ptr(b["coords"]), _lib.ptr(b["feats"]), _lib.ptr(b["num"]),
                 _lib.ptr(b["voxels"]), _lib.ptr(b["voff"]), b["cap"], _lib.ptr(b["status"]), _lib.ptr(b["ws"]),
-                b["ws"].numel(), _lib.stream_ptr(points.device))
+                b["ws"].numel(), _lib.stream_ptr(points.device),
+                _lib.ctypes.c_void_p(features_stream.cuda_stream) if features_stream is not None else None)
         _lib.check(st, "voxelize_mean")
+        ready = None
+        if features_stream is not None:
+            ready = torch.cuda.Event()
+            ready.record(features_stream)
         return dict(voxel_coords=b["coords"], voxel_features=b["feats"], voxel_num_points=b["num"],
-                    voxels=b["voxels"], voxel_offsets=b["voff"], status=b["status"], cap=b["cap"])
+                    voxels=b["voxels"], voxel_offsets=b["voff"], status=b["status"], cap=b["cap"],
+                    features_ready=ready)

@@ -87,6 +87,10 @@ FV2P_API int fv2p_device_check(int *sm_count, int *cc_major, int *cc_minor);
  * Semantics are the numba loop's: voxel ids in first-arrival order of the points, at most max_points
  * lowest-index points kept per voxel, and the `break` when voxel number max_voxels would be opened
  * (every later point of that frame is dropped).
+ *   features_stream  NULL, or a second stream: coords / voxel_offsets are complete on `stream` when the call
+ *                 returns control to it, while voxel_features / num_points / voxels are finished on
+ *                 features_stream (forked from `stream` inside the call; the caller joins it), so that the
+ *                 rulebooks, which only read coordinates, need not wait for the means.
  * ------------------------------------------------------------------------------------------- */
 FV2P_API size_t fv2p_voxelize_workspace_bytes(int64_t total_points, int batch, int64_t max_frame_points,
                                      int max_points, int64_t cap);
@@ -95,7 +99,7 @@ FV2P_API int fv2p_voxelize_mean(const float *points, const int32_t *frame_offset
                        const float *vsize3, int max_points, int max_voxels, int32_t *coords,
                        float *voxel_features, int32_t *num_points, float *voxels,
                        int32_t *voxel_offsets, int64_t cap, int32_t *status_dev, void *workspace,
-                       size_t workspace_bytes, fv2p_stream_t stream);
+                       size_t workspace_bytes, fv2p_stream_t stream, fv2p_stream_t features_stream);
 
 /* Reference-shaped single-frame entry (VoxelGenerator.generate): synchronises and returns the voxel
  * count through *num_voxels_host.  Outputs as above with batch = 1 (coords still [M,4]). */
