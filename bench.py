@@ -399,10 +399,16 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
 
+    # stdout carries exactly one JSON line: anything libraries print there (NCCL's version banner, for one) goes
+    # to stderr instead
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
     if args.impl == "reference":
         line = run_reference(args, wl, rank, world)
         if line is not None:
-            print(json.dumps(line), flush=True)
+            print(json.dumps(line), file=json_out, flush=True)
         return 0
 
     import torch
@@ -416,7 +422,7 @@ def main():
         dist.init_process_group("nccl", device_id=device)
     line = run_ours(args, wl, rank, world, device)
     if line is not None:
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=json_out, flush=True)
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
