@@ -11,7 +11,8 @@ independent batches (weak scaling, no data-path collective); only the elapsed ti
           stream, L2 flushed between steps, untimed).
 `e2e`     the same metric through HotPath(frames) with HOST buffers: pinned-memory H2D of the points, all kernels,
           D2H of the row counts and of the stride-8 output features inside the timed region.
-`roofline` the dominant kernel (the conv layer with the largest share of the step), timed alone with CUDA events.
+`roofline` the dominant kernel (slowest launch of the conv layer shape with the largest share of the step), timed
+          alone with CUDA events.
 `cpu_baseline` the reference's compiled CPU path (oracle/_ref sparse_conv_ext) + the C port of its numba voxelizer,
           timed on this box's host cores on a bounded sample.  Only this leg and --impl reference execute oracle/.
 """
@@ -227,7 +228,12 @@ def run_ours(args, wl, rank, world, device):
     hp.finish(handle)
     recs = layer_profile(hp, handle, flush)
     pk = peaks()
-    dom = max(recs, key=lambda r: r["ms"])
+    # dominant kernel = the layer shape (cin, cout, rulebook) that takes the largest share of the step, represented
+    # by its slowest launch (stable from run to run, unlike the single slowest launch)
+    fam = {}
+    for r in recs:
+        fam.setdefault((r["cin"], r["cout"], r["key"]), []).append(r)
+    dom = max(max(fam.values(), key=lambda rs: sum(r["ms"] for r in rs)), key=lambda r: r["ms"])
     conv_ms = sum(r["ms"] for r in recs)
     tflops = dom["flops"] / (dom["ms"] * 1e-3) / 1e12
     gbs = dom["bytes"] / (dom["ms"] * 1e-3) / 1e9
@@ -242,7 +248,7 @@ def run_ours(args, wl, rank, world, device):
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
     if os.path.exists(tpath):  # dram bytes per launch of the same kernel shape from the committed ncu --set full capture
-        traffic = json.load(open(tpath)).get("%s:%d:%d" % (precision, dom["cin"], dom["cout"]))
+        traffic = json.load(open(tpath)).get("%s:%s:%d:%d" % (args.workload, precision, dom["cin"], dom["cout"]))
     roof.update(traffic=traffic, peak_source=pk["source"],
                 kernel="conv_fwd layer %d (%s, %d->%d, N_out=%d, pairs=%d, mode=%d)" % (
                     dom["layer"], dom["key"], dom["cin"], dom["cout"], dom["n_out"], dom["pairs"], dom["mode"]),
