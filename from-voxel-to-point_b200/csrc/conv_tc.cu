@@ -554,7 +554,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
         int i;
         if (fetches == 0) i = b;
         else if (fetches == 1) i = 2 * G - 1 - b;
-        else if (sched) i = 2 * G + atomicAdd(&sched[0], 1);
+        else if (sched) {
+          // the counter words may still be in use by the previous launch of the same layer (programmatic dependent
+          // launch lets this kernel start before it has finished)
+          if (fetches == 2) griddep_wait();
+          i = 2 * G + atomicAdd(&sched[0], 1);
+        }
         else i = fetches * G + b;
         ++fetches;
         pending = i >= n_tiles ? make_int2(-1, 0) : (order2 ? __ldg(&order2[i]) : make_int2(i, 0));
