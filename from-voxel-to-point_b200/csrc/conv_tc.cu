@@ -78,21 +78,8 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ int g_tc_poll = 0;  // experiment: 1 = poll with test_wait instead of the suspending try_wait
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done;
-  if (g_tc_poll) {
-    do {
-      asm volatile(
-          "{\n\t.reg .pred p;\n\t"
-          "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-          "selp.u32 %0, 1, 0, p;\n\t}"
-          : "=r"(done)
-          : "r"(bar), "r"(parity)
-          : "memory");
-    } while (!done);
-    return;
-  }
   do {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -144,7 +131,6 @@ __device__ __forceinline__ void griddep_launch_dependents() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -1088,10 +1074,6 @@ extern "C" int fv2p_tc_gather_mode(int mode) {
 extern "C" __attribute__((visibility("default"))) int fv2p_debug_pdl(int v) {
   g_tc_pdl = v ? 1 : 0;
   return 0;
-}
-
-extern "C" __attribute__((visibility("default"))) int fv2p_debug_poll(int v) {
-  return (int)cudaMemcpyToSymbol(g_tc_poll, &v, sizeof(int));
 }
 
 // copies the stamp table to `out` ([256][4] u64), returns the number of stamps taken and resets the counter

@@ -18,7 +18,6 @@ ap.add_argument("--workload", default="kitti_b8")
 ap.add_argument("--layer", type=int, default=12)
 ap.add_argument("--repeat", type=int, default=3)
 ap.add_argument("--tma", type=int, default=-1)
-ap.add_argument("--poll", type=int, default=0)
 ap.add_argument("--debug", type=int, nargs="*", default=[])
 a = ap.parse_args()
 wl = bench.WORKLOADS[a.workload]
@@ -28,7 +27,6 @@ frames = bench.make_frames(wl, 0, wl["batch"])
 pts, off, mfp, _ = hp.upload(frames, dev)
 from fv2p_b200 import _lib as _L  # noqa: E402
 _L.load().fv2p_tc_gather_mode(a.tma)
-_L.load().fv2p_debug_poll(a.poll)
 for _ in range(2):
     h = hp.launch_resident(pts, off, mfp)
     hp.finish(h)
