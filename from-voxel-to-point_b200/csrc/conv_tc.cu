@@ -262,7 +262,11 @@ struct Cfg {
   // The scheduler warp streams neighbour-map tiles into a ring of kNbrBufs buffers ahead of the producers.
   static constexpr int kNbrBufs = N == 128 ? 2 : (N == 64 ? 3 : 4);
   static constexpr int kNbrBytes = kNbrBufs * kNbrBufInts * 4;
-  static constexpr int kAColsPerStage = 64;
+  // fp32, N <= 64: the hi product reads the landed fp32 tile straight from shared memory (kind::tf32 ignores the low
+  // 13 mantissa bits, i.e. hi = trunc(x)); only the correction operand goes through the transform warps and TMEM.
+  // At N = 128 the extra operand reads would put the kernel back on the shared-memory roofline, so hi stays in TMEM.
+  static constexpr bool kHiFromSmem = kTf32 && N <= 64;
+  static constexpr int kAColsPerStage = kHiFromSmem ? 32 : 64;
   // The geometry of later levels (and of the next batch) runs on other streams under the feature pass; it only
   // gets onto an SM if the conv CTA leaves it some shared memory.  The fp32 128-wide layers come last, when little
   // geometry is left, and lose more from a 3-deep ring than they gain (0.115 vs 0.096 ms), so they take it all.
@@ -671,9 +675,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
               const uint64_t adv = (uint64_t)(2 * j);  // 32 bytes of K
               if constexpr (kTf32) {
                 // 8 input channels per step: hi*hi as tf32, both correction terms as one bf16 MMA of K = 16
-                const uint32_t a_hi = a_tmem0 + s * (uint32_t)C::kAColsPerStage + 8u * (uint32_t)j;
-                tc_mma_ts_f16(d_tmem, a_hi + 32u, b_desc + w_lo_off + adv, idesc_corr, accumulate);
-                tc_mma_ts_tf32(d_tmem, a_hi, b_desc + adv, idesc, 1u);
+                const uint32_t a_cols = a_tmem0 + s * (uint32_t)C::kAColsPerStage + 8u * (uint32_t)j;
+                if constexpr (C::kHiFromSmem) {
+                  tc_mma_ts_f16(d_tmem, a_cols, b_desc + w_lo_off + adv, idesc_corr, accumulate);
+                  tc_mma<true>(d_tmem, a_desc + adv, b_desc + adv, idesc, 1u);
+                } else {
+                  tc_mma_ts_f16(d_tmem, a_cols + 32u, b_desc + w_lo_off + adv, idesc_corr, accumulate);
+                  tc_mma_ts_tf32(d_tmem, a_cols, b_desc + adv, idesc, 1u);
+                }
               } else {
                 tc_mma<false>(d_tmem, a_desc + adv, b_desc + adv, idesc, accumulate);
               }
@@ -741,7 +750,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
                   const float v[4] = {x[2 * u + c].x, x[2 * u + c].y, x[2 * u + c].z, x[2 * u + c].w};
 #pragma unroll
                   for (int e = 0; e < 4; ++e) {
-                    h[4 * c + e] = tf32_rn_alu(v[e]);
+                    // hi as the tensor core will see it: rounded here when it is stored to TMEM, truncated when
+                    // the MMA reads the raw tile from shared memory
+                    h[4 * c + e] = C::kHiFromSmem ? __uint_as_float(__float_as_uint(v[e]) & 0xFFFFE000u)
+                                                  : tf32_rn_alu(v[e]);
                     l[4 * c + e] = v[e] - h[4 * c + e];
                     hi[8 * u + 4 * c + e] = __float_as_uint(h[4 * c + e]);
                   }
@@ -752,8 +764,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
                   corr[8 * u + 4 + q] = pack_bf16x2(h[2 * q], h[2 * q + 1]);
                 }
               }
-              tmem_st16(a_cols + 16u * half, hi);
-              tmem_st16(a_cols + 32u + 16u * half, corr);
+              if constexpr (C::kHiFromSmem) {
+                tmem_st16(a_cols + 16u * half, corr);
+              } else {
+                tmem_st16(a_cols + 16u * half, hi);
+                tmem_st16(a_cols + 32u + 16u * half, corr);
+              }
             }
           }
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
