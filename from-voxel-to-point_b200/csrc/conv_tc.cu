@@ -41,7 +41,10 @@
 // Shared memory then only carries the raw tile once and the W slices: with both operands in shared memory the
 // kernel was bound by that pipe (16 KB landed + 48 KB split traffic + 12 x 8 KB operand reads per stage
 // ~ 1500 cycles at 128 B/cycle, against 768 cycles of tensor work at N=128).  The dropped lo*lo term is O(2^-22)
-// relative, the bf16 rounding of the correction operands O(2^-20), both unbiased.  What remains (measured 1-2e-5 at 27*128 terms) is
+// relative, the bf16 rounding of the correction operands O(2^-20), both unbiased.  For N <= 64 the hi product does not
+// go through TMEM at all: kind::tf32 ignores the low 13 mantissa bits of its operands, so the MMA reads the landed
+// fp32 tile as it is (hi = trunc(x)) and the transform warps only produce the correction operand from
+// lo = x - trunc(x) (exact), which halves their work; at N = 128 the extra operand reads did not pay.  What remains (measured 1-2e-5 at 27*128 terms) is
 // the tensor core's truncating fp32 accumulation, 5x inside the 1e-4 bar.
 #include <cuda.h>
 
