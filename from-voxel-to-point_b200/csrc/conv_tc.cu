@@ -19,7 +19,8 @@
 //                 shorter than eight), so the waits and arrivals of one stage overlap the copy issue of the next
 //                 ones.  Either way the MMA needs no predication and nothing is scattered afterwards.
 //   B operand     W[k] slices, pre-packed once per layer into the exact (swizzled) shared-memory image and
-//                 pulled with one TMA bulk copy per stage
+//                 pulled with one TMA bulk copy per stage by warp 14 into a ring of their own (three slots; the
+//                 gathered tiles have a deeper ring of 16 KB slots, since their round trip is the long one)
 //   MMA           one elected thread of warp 12 runs the whole tcgen05.mma issue loop (kind::f16 for bf16,
 //                 kind::tf32 for fp32); tcgen05.commit releases the smem stage / publishes the accumulator
 //   epilogue      warps 0-3 read TMEM with tcgen05.ld (one accumulator row per thread), apply
@@ -32,20 +33,18 @@
 //                 bulk copies, a few tiles ahead of the producers.  Tile ids reach the epilogue through a small
 //                 ring; a sentinel tile / stage ends the stream for every role.
 //
-// fp32 path = 3xTF32 with the A operand in tensor memory: the gathered fp32 tile lands in shared memory, four
-// transform warps (14-17, one per TMEM lane quadrant, one row per thread) split it into hi = rn_tf32(x) and
-// lo = x - hi and write hi (tf32) and the pair [lo | hi] (bf16) with tcgen05.st into a TMEM ring; W is packed as a
-// tf32 W_hi image and a bf16 [W_hi; W_lo] image, and each 8-channel K step issues two MMAs with A read from TMEM
-// (tcgen05.mma [d], [a], b-desc): A_hi*W_hi as kind::tf32 and both correction terms A_lo*W_hi + A_hi*W_lo as ONE
-// kind::f16 MMA of K = 16 (they only need ~2^-9 relative accuracy: the products are already 2^-11 down).
-// Shared memory then only carries the raw tile once and the W slices: with both operands in shared memory the
-// kernel was bound by that pipe (16 KB landed + 48 KB split traffic + 12 x 8 KB operand reads per stage
-// ~ 1500 cycles at 128 B/cycle, against 768 cycles of tensor work at N=128).  The dropped lo*lo term is O(2^-22)
-// relative, the bf16 rounding of the correction operands O(2^-20), both unbiased.  For N <= 64 the hi product does not
-// go through TMEM at all: kind::tf32 ignores the low 13 mantissa bits of its operands, so the MMA reads the landed
-// fp32 tile as it is (hi = trunc(x)) and the transform warps only produce the correction operand from
-// lo = x - trunc(x) (exact), which halves their work; at N = 128 the extra operand reads did not pay.  What remains (measured 1-2e-5 at 27*128 terms) is
-// the tensor core's truncating fp32 accumulation, 5x inside the 1e-4 bar.
+// fp32 path = 3xTF32, x = hi + lo with hi = x with its low 13 mantissa bits cleared - which is exactly what a
+// kind::tf32 MMA sees when it reads fp32 data - and lo = x - hi (exact).  Per 8-channel K step two MMAs:
+//   A_hi*W_hi   kind::tf32, A read straight from the landed fp32 tile in shared memory, W_hi = rn_tf32(W);
+//   A_lo*W_hi + A_hi*W_lo   ONE kind::f16 MMA of K = 16 on bf16 copies (the products are already 2^-11 down, bf16's
+//               2^-9 is enough): A = [lo | hi] from tensor memory, B = the packed [W_hi; W_lo] bf16 image.
+// Four transform warps (15-18, one per TMEM lane quadrant, one row per thread) read the landed tile, form the bf16
+// pairs and tcgen05.st them into a TMEM ring (32 columns per A slot); the MMA reads them with tcgen05.mma [d], [a], b.
+// History: with hi/lo tiles in shared memory and three tf32 passes the kernel was bound by the shared-memory pipe
+// (16 KB landed + 48 KB split traffic + 12 x 8 KB operand reads per stage ~ 1500 cycles at 128 B/cycle); cvt.rna
+// pairs on the conversion pipe cost another ~500 cycles per stage.  The dropped lo*lo term is O(2^-22) relative, the
+// bf16 rounding of the correction operands O(2^-20), both unbiased.  What remains (measured 1-2e-5 at 27*128 terms)
+// is the tensor core's truncating fp32 accumulation, 5x inside the 1e-4 bar.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -59,8 +58,9 @@ constexpr int kProdThreads = 256;  // warps 4-11: neighbour prefetch + gather is
 constexpr int kProdWarps = kProdThreads / 32;
 constexpr int kMmaWarp = (kEpiThreads + kProdThreads) / 32;  // warp 12
 constexpr int kSchedWarp = kMmaWarp + 1;                     // warp 13: tile scheduler + neighbour-map loader
-constexpr int kXformThreads = 128;                           // warps 14-17, fp32 (3xTF32) kernels only
-constexpr int kTcThreadsBase = kEpiThreads + kProdThreads + 64;
+constexpr int kWLoadWarp = kSchedWarp + 1;                   // warp 14: weight-slice loader (W ring)
+constexpr int kXformThreads = 128;                           // warps 15-18, fp32 (3xTF32) kernels only
+constexpr int kTcThreadsBase = kEpiThreads + kProdThreads + 96;
 constexpr int kMaxStages = 8;
 constexpr int kSmemLimit = 232448;                 // 227 KB of dynamic shared memory per CTA
 constexpr int kSmemGuest = 12288;                  // left free so that a geometry CTA (rulebook, sort) can co-reside
@@ -156,16 +156,8 @@ __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_
         : "memory");
   }
 }
-// A operand from tensor memory (lane = tile row, one 32-bit column per tf32 element), B from shared memory
-__device__ __forceinline__ void tc_mma_ts_tf32(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
-                                               uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// Same with 16-bit A elements (two per 32-bit column, K-consecutive)
+// A operand from tensor memory (lane = tile row, two 16-bit elements per 32-bit column, K-consecutive), B from
+// shared memory
 __device__ __forceinline__ void tc_mma_ts_f16(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
                                               uint32_t accumulate) {
   asm volatile(
@@ -192,12 +184,6 @@ __device__ __forceinline__ float tf32_rn(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
-}
-// The same rounding (nearest, ties away from zero, on the sign-magnitude bit pattern) with integer ALU instructions:
-// cvt runs on the quarter-rate conversion pipe, and the transform warps do two per element - 8192 per 16 KB stage,
-// ~512 cycles of that pipe alone.
-__device__ __forceinline__ float tf32_rn_alu(float x) {
-  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 // 16 consecutive fp32 accumulator columns of this thread's TMEM lane
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
@@ -259,30 +245,37 @@ template <bool kTf32, int N>
 struct Cfg {
   static constexpr int kABytes = kTileM * 128;  // one (up to) 128-byte slice per row
   static constexpr int kWBytes = N * 128;
-  // bf16: A tile + W slice.  fp32: the raw fp32 A tile + W_hi + W_lo; the split A operand lives in TMEM
-  // (kAColsPerStage columns per ring slot: hi in the first 32, lo in the next 32).
-  static constexpr int kStageBytes = kABytes + (kTf32 ? 2 : 1) * kWBytes;
+  // Two rings.  A: the gathered tile (bf16 rows, or the raw fp32 rows), kStages slots of 16 KB - deep, because a
+  // slot's round trip (gather issue -> L2 -> [split] -> MMA -> commit, ~5000 cycles) sets the pace of the kernel.
+  // W: the weight slice of the stage (bf16: N x 128 B; fp32: W_hi tf32 + [W_hi; W_lo] bf16), kWStages slots - one
+  // sequential bulk copy each, so three are enough.  (One ring of A+W slots was 4 deep at N = 128.)
+  static constexpr int kWSlotBytes = (kTf32 ? 2 : 1) * kWBytes;
+  static constexpr int kWStages = 3;
   // The scheduler warp streams neighbour-map tiles into a ring of kNbrBufs buffers ahead of the producers.
   static constexpr int kNbrBufs = N == 128 ? 2 : (N == 64 ? 3 : 4);
   static constexpr int kNbrBytes = kNbrBufs * kNbrBufInts * 4;
-  // fp32, N <= 64: the hi product reads the landed fp32 tile straight from shared memory (kind::tf32 ignores the low
-  // 13 mantissa bits, i.e. hi = trunc(x)); only the correction operand goes through the transform warps and TMEM.
-  // At N = 128 the extra operand reads would put the kernel back on the shared-memory roofline, so hi stays in TMEM.
-  static constexpr bool kHiFromSmem = kTf32 && N <= 64;
-  static constexpr int kAColsPerStage = kHiFromSmem ? 32 : 64;
+  // fp32: the hi product reads the landed fp32 tile straight from shared memory (kind::tf32 ignores the low 13
+  // mantissa bits, i.e. hi = trunc(x)); only the correction operand goes through the transform warps and TMEM,
+  // kAColsPerStage columns per A slot.
+  static constexpr int kAColsPerStage = 32;
   // The geometry of later levels (and of the next batch) runs on other streams under the feature pass; it only
-  // gets onto an SM if the conv CTA leaves it some shared memory.  The fp32 128-wide layers come last, when little
-  // geometry is left, and lose more from a 3-deep ring than they gain (0.115 vs 0.096 ms), so they take it all.
-  static constexpr int kSmemAvail = kSmemLimit - ((kTf32 && N == 128) ? 0 : kSmemGuest);
-  static constexpr int kStagesSmem = (kSmemAvail - kSmemMisc - kNbrBytes) / kStageBytes;
+  // gets onto an SM if the conv CTA leaves it some shared memory.
+  static constexpr int kSmemAvail = kSmemLimit - kSmemGuest;
+  static constexpr int kStagesSmem = (kSmemAvail - kSmemMisc - kNbrBytes - kWStages * kWSlotBytes) / kABytes;
   static constexpr int kStagesTmem = kTf32 ? (512 - 2 * N) / kAColsPerStage : kMaxStages;
   static constexpr int kStagesRaw = kStagesSmem < kStagesTmem ? kStagesSmem : kStagesTmem;
   static constexpr int kStages = kStagesRaw > kMaxStages ? kMaxStages : kStagesRaw;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kNbrBytes + kSmemMisc;
+  static constexpr int kSmemBytes = kStages * kABytes + kWStages * kWSlotBytes + kNbrBytes + kSmemMisc;
   static constexpr int kTmemCols = kTf32 ? 512 : (2 * N < 32 ? 32 : 2 * N);  // power of two
   static constexpr int kThreads = kTcThreadsBase + (kTf32 ? kXformThreads : 0);
   static_assert(kStages >= 3, "pipeline too shallow");
 };
+
+// Producer warps that share A-ring slot `s` (warp w fills slot w % stages): 1 or 2, half the rows each.
+template <int kStages>
+__host__ __device__ constexpr int slot_parts(int s) {
+  return (s + kStages < kProdWarps) ? 2 : 1;
+}
 
 struct Epilogue {
   const float *bias, *scale, *shift;
@@ -302,16 +295,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
   constexpr int kElem = kTf32 ? 4 : 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t *stage_base = smem;
-  int *nbr_s = reinterpret_cast<int *>(smem + C::kStages * C::kStageBytes);
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C::kStages * C::kStageBytes + C::kNbrBytes);
+  uint8_t *stage_base = smem;                               // A ring
+  uint8_t *w_base = smem + C::kStages * C::kABytes;         // W ring
+  int *nbr_s = reinterpret_cast<int *>(w_base + C::kWStages * C::kWSlotBytes);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(nbr_s) + C::kNbrBytes);
   // barrier layout: full[kStages], empty[kStages], landed[kStages] (fp32 only), tmem_full[2], tmem_empty[2],
-  // nbr_full[kNbrBufs], nbr_empty[kNbrBufs]
+  // nbr_full[kNbrBufs], nbr_empty[kNbrBufs], w_full[kWStages], w_empty[kWStages]
   const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * C::kStages;
   const uint32_t bar_landed = bar_empty + 8 * C::kStages;
   const uint32_t bar_tfull = bar_landed + 8 * C::kStages, bar_tempty = bar_tfull + 16;
   const uint32_t bar_nfull = bar_tempty + 16, bar_nempty = bar_nfull + 8 * C::kNbrBufs;
-  volatile int *stage_flags = reinterpret_cast<volatile int *>(bars + 3 * C::kStages + 4 + 2 * C::kNbrBufs);  // [kStages]
+  const uint32_t bar_wfull = bar_nempty + 8 * C::kNbrBufs, bar_wempty = bar_wfull + 8 * C::kWStages;
+  volatile int *stage_flags =
+      reinterpret_cast<volatile int *>(bars + 3 * C::kStages + 4 + 2 * C::kNbrBufs + 2 * C::kWStages);  // [kStages]
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(const_cast<int *>(stage_flags + C::kStages));
   volatile int *tile_ring = reinterpret_cast<volatile int *>(tmem_slot + 1);  // [kTileRing] tile id per sequence no.
   volatile int *tile_info = tile_ring + kTileRing;                            // [kNbrBufs][2]: tile id, offset mask
@@ -340,15 +336,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::kStages; ++s) {
-      // bf16: the producer's expect_tx arrive; the TMA gathers and the weight copy complete the transaction.
-      // fp32: gathers land on `landed` (one expect_tx arrive), the transform warps + the weight copy on `full`.
-      // LSU gather: + the 32 cp.async arrivals of the owning warp (the fp32 `landed` barrier also gets one plain
-      // arrive that publishes the stage flags).
-      // A slot of a ring shorter than the producer warp count is filled by two warps (half the rows each).
-      const uint32_t a_arrivals = use_tma ? 1u : (s + C::kStages < kProdWarps ? 65u : 33u);
-      mbar_init(bar_full + 8 * s, kTf32 ? kXformThreads + 1 : a_arrivals);
+      // A side of a stage.  The owning warps' cp.async arrivals (32 each) + the primary owner's arrive, which
+      // publishes the stage flags (TMA gather: that arrive carries the expected bytes instead), land on `full`
+      // for bf16 and on `landed` for fp32, where the 128 transform threads then complete `full`.
+      const uint32_t a_arrivals = use_tma ? 1u : 32u * (uint32_t)slot_parts<C::kStages>(s) + 1u;
+      mbar_init(bar_full + 8 * s, kTf32 ? (uint32_t)kXformThreads : a_arrivals);
       mbar_init(bar_empty + 8 * s, 1);
       mbar_init(bar_landed + 8 * s, a_arrivals);
+    }
+    for (int w = 0; w < C::kWStages; ++w) {
+      mbar_init(bar_wfull + 8 * w, 1);   // the expect_tx arrive of the warp that issues the bulk copy
+      mbar_init(bar_wempty + 8 * w, 1);  // tcgen05.commit
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
@@ -356,7 +354,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
     }
     for (int b = 0; b < C::kNbrBufs; ++b) {
       mbar_init(bar_nfull + 8 * b, 1);            // the scheduler's (expect_tx) arrive; bulk copies complete the bytes
-      mbar_init(bar_nempty + 8 * b, kProdWarps);  // every producer warp is done reading the buffer
+      mbar_init(bar_nempty + 8 * b, kProdWarps + 1);  // every producer warp and the W loader are done with the buffer
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&feat_map) : "memory");
@@ -414,13 +412,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
           const uint32_t a_bar = kTf32 ? bar_landed + 8 * s : bar_full + 8 * s;
           if (lane == 0 && my_part == 0) {
             stage_flags[s] = kFlagStop;
-            if constexpr (kTf32) {
-              if (use_tma) mbar_arrive_expect_tx(bar_landed + 8 * s, 0u);
-              else mbar_arrive(bar_landed + 8 * s);
-              mbar_arrive_expect_tx(bar_full + 8 * s, 0u);
-            } else {
-              mbar_arrive_expect_tx(bar_full + 8 * s, 0u);
-            }
+            mbar_arrive(a_bar);
           }
           __syncwarp();
           if (!use_tma) cp_async_arrive(a_bar);
@@ -447,24 +439,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
             TC_ACC(tm_pwait);
           }
           TC_T0();
-          const uint32_t a_u32 = smem_u32(stage_base + (size_t)s * C::kStageBytes);
+          const uint32_t a_u32 = smem_u32(stage_base + (size_t)s * C::kABytes);
           const uint32_t a_bar = kTf32 ? bar_landed + 8 * s : bar_full + 8 * s;
           if (lane == 0 && my_part == 0) {
             stage_flags[s] = ((k == (int)first_k && sl == 0) ? kFlagFirst : 0) |
                              ((k == (int)last_k && sl == slices - 1) ? kFlagLast : 0);
-            const uint32_t wb = w_stage_bytes * (kTf32 ? 2 : 1);
-            const uint8_t *wsrc = wpacked + ((size_t)k * slices + sl) * wb;
-            const uint32_t w_u32 = a_u32 + C::kABytes;
-            const uint32_t a_tx = use_tma ? a_stage_bytes : 0u;
-            const uint32_t wtx = dbg == 3 ? 0u : wb;  // dbg 3: no weight copy
-            if constexpr (kTf32) {
-              if (use_tma) mbar_arrive_expect_tx(bar_landed + 8 * s, a_tx);
-              else mbar_arrive(bar_landed + 8 * s);
-              mbar_arrive_expect_tx(bar_full + 8 * s, wtx);
-            } else {
-              mbar_arrive_expect_tx(bar_full + 8 * s, a_tx + wtx);
-            }
-            if (dbg != 3) bulk_g2s(w_u32, wsrc, wb, bar_full + 8 * s);
+            if (use_tma) mbar_arrive_expect_tx(a_bar, a_stage_bytes);
+            else mbar_arrive(a_bar);
           }
           __syncwarp();
           if (use_tma) {
@@ -631,16 +612,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
     // This loop is a single thread's instruction stream, so it is kept short: the descriptor of a slot is the
     // descriptor of slot 0 plus a constant in the 16-byte start-address field (no carry: smem is < 256 KB).
     const uint64_t a_desc0 = smem_desc(smem_u32(stage_base), sbo, layout);
-    constexpr uint64_t kStageStep = (uint64_t)(C::kStageBytes >> 4);
-    constexpr uint64_t kWOff = (uint64_t)(C::kABytes >> 4);
+    const uint64_t w_desc0 = smem_desc(smem_u32(w_base), sbo, layout);
+    constexpr uint64_t kStageStep = (uint64_t)(C::kABytes >> 4);
+    constexpr uint64_t kWSlotStep = (uint64_t)(C::kWSlotBytes >> 4);
     const uint64_t w_lo_off = (uint64_t)(w_stage_bytes >> 4);
     const uint32_t a_tmem0 = tmem_base + 2u * (uint32_t)N;  // fp32: TMEM ring of split A tiles behind the accumulators
     // One elected thread runs the whole loop on its own (waits included).  Re-electing per stage with the warp
     // waiting and re-synchronising around the issue costs ~300 cycles per stage and ~50 per tcgen05.mma
     // (profiles/micro/mma_issue_bench.cu: 4 MMAs + commit per stage take 760 cycles that way, 280 this way).
     if (elect_one_sync()) {
-      uint32_t s = 0, phase = 0;
-      uint64_t a_desc = a_desc0;
+      uint32_t s = 0, phase = 0;      // A ring slot
+      uint32_t ws = 0, wphase = 0;    // W ring slot
+      uint64_t a_desc = a_desc0, b_desc = w_desc0;
       uint32_t acc = 0, acc_phase = 0;
       TC_TIMER_DECL(tm_mfull);
       TC_TIMER_DECL(tm_mtmem);
@@ -668,8 +651,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
 #endif
           break;
         }
+        {
+          TC_T0();
+          mbar_wait(bar_wfull + 8 * ws, wphase);  // the stage's weight slice
+          TC_ACC(tm_mfull);
+        }
+        tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * (uint32_t)N;
-        const uint64_t b_desc = a_desc + kWOff;
         uint32_t accumulate = (flags & kFlagFirst) ? 0u : 1u;
         if (dbg != 4) {
 #pragma unroll
@@ -679,13 +667,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
               if constexpr (kTf32) {
                 // 8 input channels per step: hi*hi as tf32, both correction terms as one bf16 MMA of K = 16
                 const uint32_t a_cols = a_tmem0 + s * (uint32_t)C::kAColsPerStage + 8u * (uint32_t)j;
-                if constexpr (C::kHiFromSmem) {
-                  tc_mma_ts_f16(d_tmem, a_cols, b_desc + w_lo_off + adv, idesc_corr, accumulate);
-                  tc_mma<true>(d_tmem, a_desc + adv, b_desc + adv, idesc, 1u);
-                } else {
-                  tc_mma_ts_f16(d_tmem, a_cols + 32u, b_desc + w_lo_off + adv, idesc_corr, accumulate);
-                  tc_mma_ts_tf32(d_tmem, a_cols, b_desc + adv, idesc, 1u);
-                }
+                tc_mma_ts_f16(d_tmem, a_cols, b_desc + w_lo_off + adv, idesc_corr, accumulate);
+                tc_mma<true>(d_tmem, a_desc + adv, b_desc + adv, idesc, 1u);
               } else {
                 tc_mma<false>(d_tmem, a_desc + adv, b_desc + adv, idesc, accumulate);
               }
@@ -693,7 +676,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
             }
           }
         }
-        tc_commit(bar_empty + 8 * s);  // smem stage reusable once these MMAs retire
+        tc_commit(bar_empty + 8 * s);    // both ring slots are reusable once these MMAs retire
+        tc_commit(bar_wempty + 8 * ws);
         if (flags & kFlagLast) {
           tc_commit(bar_tfull + 8 * acc);  // accumulator complete
           acc ^= 1u;
@@ -705,12 +689,49 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
           phase ^= 1;
           a_desc = a_desc0;
         }
+        b_desc += kWSlotStep;
+        if (++ws == (uint32_t)C::kWStages) {
+          ws = 0;
+          wphase ^= 1;
+          b_desc = w_desc0;
+        }
         TC_ACC(tm_missue);
       }
     }
     __syncwarp();
-  } else if (warp > kSchedWarp) {
-    // =============================== fp32 split (warps 14-17, 3xTF32 kernels only) ===============================
+  } else if (warp == kWLoadWarp) {
+    // =============================== weight-slice loader ===============================
+    // One thread walks the same stage sequence as the producers (tile masks from the scheduler's ring) and keeps
+    // the W ring full: stage i's slice goes to slot i % kWStages with one bulk copy.  A single in-order waiter per
+    // barrier, so the W ring may be shallower than the A ring without a parity wait ever being two phases ahead.
+    if (elect_one_sync()) {
+      const uint32_t wb = w_stage_bytes * (kTf32 ? 2 : 1);
+      uint32_t n = 0;
+      for (uint32_t seq = 0;; ++seq) {
+        const uint32_t nb = seq % C::kNbrBufs;
+        mbar_wait(bar_nfull + 8 * nb, (seq / C::kNbrBufs) & 1);
+        const int tile = tile_info[2 * nb];
+        uint32_t mask = (uint32_t)tile_info[2 * nb + 1];
+        if (tile < 0) break;
+        if (mask == 0u) mask = 1u;
+        while (mask) {
+          const int k = __ffs(mask) - 1;
+          mask &= mask - 1;
+          for (int sl = 0; sl < slices; ++sl, ++n) {
+            const uint32_t w = n % C::kWStages;
+            mbar_wait(bar_wempty + 8 * w, ((n / C::kWStages) & 1) ^ 1);
+            mbar_arrive_expect_tx(bar_wfull + 8 * w, dbg == 3 ? 0u : wb);  // dbg 3: no weight copy
+            if (dbg != 3)
+              bulk_g2s(smem_u32(w_base + (size_t)w * C::kWSlotBytes), wpacked + ((size_t)k * slices + sl) * wb, wb,
+                       bar_wfull + 8 * w);
+          }
+        }
+        mbar_arrive(bar_nempty + 8 * nb);
+      }
+    }
+    __syncwarp();
+  } else if (warp > kWLoadWarp) {
+    // =============================== fp32 split (warps 15-18, 3xTF32 kernels only) ===============================
     // Thread = tile row (the warp's TMEM lane quadrant is warp % 4): reads its landed fp32 row slice from the
     // swizzled tile, splits it and stores hi / lo to the stage's TMEM columns.
     if constexpr (kTf32) {
@@ -733,7 +754,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
         TC_T0();
         const bool stop = (stage_flags[s] & kFlagStop) != 0;
         if (!stop) {
-          const uint8_t *row = stage_base + (size_t)s * C::kStageBytes + (size_t)r * row_bytes;
+          const uint8_t *row = stage_base + (size_t)s * C::kABytes + (size_t)r * row_bytes;
           const uint32_t a_cols = lane_addr + s * (uint32_t)C::kAColsPerStage;
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
@@ -742,9 +763,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
 #pragma unroll
               for (int c = 0; c < 4; ++c)
                 x[c] = *reinterpret_cast<const float4 *>(row + (((uint32_t)(half * 4 + c) ^ swz_row) << 4));
-              // hi: 16 tf32 columns.  corr: per 8-channel K step, [lo0..lo7 | hi0..hi7] as bf16 pairs = 8 columns,
-              // the A operand of the correction MMA (its B operand is [W_hi; W_lo] in bf16, see pack_weight_kernel).
-              uint32_t hi[16], corr[16];
+              // corr: per 8-channel K step, [lo0..lo7 | hi0..hi7] as bf16 pairs = 8 columns, the A operand of the
+              // correction MMA (its B operand is [W_hi; W_lo] in bf16, see pack_weight_kernel).  hi is what the
+              // tensor core sees when it reads the raw tile as tf32: the value with its low 13 mantissa bits cleared.
+              uint32_t corr[16];
 #pragma unroll
               for (int u = 0; u < 2; ++u) {  // K step inside this half = chunks 2u, 2u+1
                 float h[8], l[8];
@@ -753,12 +775,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
                   const float v[4] = {x[2 * u + c].x, x[2 * u + c].y, x[2 * u + c].z, x[2 * u + c].w};
 #pragma unroll
                   for (int e = 0; e < 4; ++e) {
-                    // hi as the tensor core will see it: rounded here when it is stored to TMEM, truncated when
-                    // the MMA reads the raw tile from shared memory
-                    h[4 * c + e] = C::kHiFromSmem ? __uint_as_float(__float_as_uint(v[e]) & 0xFFFFE000u)
-                                                  : tf32_rn_alu(v[e]);
+                    h[4 * c + e] = __uint_as_float(__float_as_uint(v[e]) & 0xFFFFE000u);
                     l[4 * c + e] = v[e] - h[4 * c + e];
-                    hi[8 * u + 4 * c + e] = __float_as_uint(h[4 * c + e]);
                   }
                 }
 #pragma unroll
@@ -767,12 +785,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
                   corr[8 * u + 4 + q] = pack_bf16x2(h[2 * q], h[2 * q + 1]);
                 }
               }
-              if constexpr (C::kHiFromSmem) {
-                tmem_st16(a_cols + 16u * half, corr);
-              } else {
-                tmem_st16(a_cols + 16u * half, hi);
-                tmem_st16(a_cols + 32u + 16u * half, corr);
-              }
+              tmem_st16(a_cols + 16u * half, corr);
             }
           }
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
