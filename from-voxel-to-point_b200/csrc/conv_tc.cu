@@ -248,9 +248,11 @@ struct Cfg {
   // Two rings.  A: the gathered tile (bf16 rows, or the raw fp32 rows), kStages slots of 16 KB - deep, because a
   // slot's round trip (gather issue -> L2 -> [split] -> MMA -> commit, ~5000 cycles) sets the pace of the kernel.
   // W: the weight slice of the stage (bf16: N x 128 B; fp32: W_hi tf32 + [W_hi; W_lo] bf16), kWStages slots - one
-  // sequential bulk copy each, so three are enough.  (One ring of A+W slots was 4 deep at N = 128.)
+  // sequential bulk copy each, so three are enough (two at fp32 N = 128, where a slice is 32 KB and the shared
+  // memory is better spent on the A ring: 0.080 ms with 5 A slots, 0.073 with 6, 0.070 with 8).  (One ring of A+W
+  // slots was 4 deep at N = 128.)
   static constexpr int kWSlotBytes = (kTf32 ? 2 : 1) * kWBytes;
-  static constexpr int kWStages = 3;
+  static constexpr int kWStages = (kTf32 && N == 128) ? 2 : 3;
   // The scheduler warp streams neighbour-map tiles into a ring of kNbrBufs buffers ahead of the producers.
   static constexpr int kNbrBufs = N == 128 ? 2 : (N == 64 ? 3 : 4);
   static constexpr int kNbrBytes = kNbrBufs * kNbrBufInts * 4;
@@ -259,8 +261,9 @@ struct Cfg {
   // kAColsPerStage columns per A slot.
   static constexpr int kAColsPerStage = 32;
   // The geometry of later levels (and of the next batch) runs on other streams under the feature pass; it only
-  // gets onto an SM if the conv CTA leaves it some shared memory.
-  static constexpr int kSmemAvail = kSmemLimit - kSmemGuest;
+  // gets onto an SM if the conv CTA leaves it some shared memory.  The fp32 128-wide layers come last, when little
+  // geometry is left, and take it all.
+  static constexpr int kSmemAvail = kSmemLimit - ((kTf32 && N == 128) ? 0 : kSmemGuest);
   static constexpr int kStagesSmem = (kSmemAvail - kSmemMisc - kNbrBytes - kWStages * kWSlotBytes) / kABytes;
   static constexpr int kStagesTmem = kTf32 ? (512 - 2 * N) / kAColsPerStage : kMaxStages;
   static constexpr int kStagesRaw = kStagesSmem < kStagesTmem ? kStagesSmem : kStagesTmem;
