@@ -280,6 +280,7 @@ extern "C" int fv2p_conv_fwd(const void *features, int64_t n_in_cap, const void 
   FV2P_REQUIRE((!row_perm && !tile_order && !sched) || mode == FV2P_MODE_BF16_TC || mode == FV2P_MODE_TF32X3_TC,
                "conv_fwd: row_perm / tile_order / sched are only used by the tensor-core modes");
   FV2P_REQUIRE(!tile_order || row_perm, "conv_fwd: tile_order comes with the row order it was computed for");
+  FV2P_REQUIRE((reinterpret_cast<uintptr_t>(tile_order) & 7) == 0, "conv_fwd: tile_order must be 8-byte aligned");
   switch (mode) {
     case FV2P_MODE_F32:
       return launch_simt<float, float>(features, static_cast<const float *>(weight), nbr, nbr_stride, kvol,
