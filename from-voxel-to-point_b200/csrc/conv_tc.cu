@@ -271,6 +271,9 @@ struct Cfg {
   static constexpr int kSmemBytes = kStages * kABytes + kWStages * kWSlotBytes + kNbrBytes + kSmemMisc;
   static constexpr int kTmemCols = kTf32 ? 512 : (2 * N < 32 ? 32 : 2 * N);  // power of two
   static constexpr int kThreads = kTcThreadsBase + (kTf32 ? kXformThreads : 0);
+  // Register cap: leaves >= 10 K of the 64 K registers so that one 256-thread geometry CTA (<= 40 registers per
+  // thread) fits next to the conv CTA.
+  static constexpr int kMaxRegs = kTf32 ? 88 : 112;
   static_assert(kStages >= 3, "pipeline too shallow");
 };
 
@@ -288,7 +291,7 @@ struct Epilogue {
 };
 
 template <bool kTf32, int N>
-__global__ void __launch_bounds__((Cfg<kTf32, N>::kThreads), 1)
+__global__ void __launch_bounds__((Cfg<kTf32, N>::kThreads)) __maxnreg__((Cfg<kTf32, N>::kMaxRegs))
 conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restrict__ feat_ptr,
                const uint8_t *__restrict__ wpacked,
                const int *__restrict__ nbr, int64_t nbr_stride, const int *__restrict__ row_perm,
