@@ -7,6 +7,7 @@ repository root registers it under an importable name).  All compute goes throug
 (include/fv2p_b200.h); nothing here falls back to CPU or to plain PyTorch.
 """
 from . import _lib, spconv, synth
+from .height_compression import HeightCompression
 from .mean_vfe import MeanVFE
 from .spconv_backbone import SparseBasicBlock, VoxelBackBone8x, VoxelResBackBone8x, post_act_block
 from .voxel_generator import BatchVoxelizer, VoxelGenerator
@@ -17,7 +18,8 @@ from . import sharding
 # name lookup tables like pcdet/models/backbones_3d/__init__.py:6-12 and vfe/__init__.py:5-9
 BACKBONES_3D = {'VoxelBackBone8x': VoxelBackBone8x, 'VoxelResBackBone8x': VoxelResBackBone8x}
 VFE = {'MeanVFE': MeanVFE}
+MAP_TO_BEV = {'HeightCompression': HeightCompression}  # backbones_2d/map_to_bev/__init__.py
 
 __all__ = ['spconv', 'synth', 'MeanVFE', 'VoxelGenerator', 'BatchVoxelizer', 'VoxelBackBone8x',
            'VoxelResBackBone8x', 'SparseBasicBlock', 'post_act_block', 'BackboneEngine', 'HotPath', 'BACKBONES_3D',
-           'VFE']
+           'VFE', 'HeightCompression', 'MAP_TO_BEV']

@@ -238,9 +238,10 @@ copy_rows_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dst, int vec
 }
 
 // SparseConvTensor.dense(): out[b][c][z][y][x] = features[row][c]
+template <typename T>
 __global__ void __launch_bounds__(kThreads)
-dense_ncdhw_kernel(const float *__restrict__ features, const int4 *__restrict__ indices, int64_t n_cap,
-                   const int *n_dev, int channels, int D, int H, int W, float *dense) {
+dense_ncdhw_kernel(const T *__restrict__ features, const int4 *__restrict__ indices, int64_t n_cap,
+                   const int *n_dev, int channels, int D, int H, int W, T *dense) {
   int n = n_dev ? *n_dev : (int)n_cap;
   if (n > n_cap) n = (int)n_cap;
   const int64_t total = (int64_t)n * channels;
@@ -327,17 +328,42 @@ extern "C" int fv2p_indice_conv_fp32(const float *features, const float *filters
                        nullptr, nullptr, nullptr, 0, FV2P_MODE_F32, out, stream_);
 }
 
+static int launch_dense(const void *features, const int32_t *indices, int64_t n_cap, const int32_t *n_dev,
+                        int channels, const int32_t *shape3, int elem_bytes, void *dense, cudaStream_t stream) {
+  const int4 *ind4 = reinterpret_cast<const int4 *>(indices);
+  if (elem_bytes == 4)
+    dense_ncdhw_kernel<float><<<persistent_grid(), kThreads, 0, stream>>>(
+        static_cast<const float *>(features), ind4, n_cap, n_dev, channels, shape3[0], shape3[1], shape3[2],
+        static_cast<float *>(dense));
+  else
+    dense_ncdhw_kernel<__nv_bfloat16><<<persistent_grid(), kThreads, 0, stream>>>(
+        static_cast<const __nv_bfloat16 *>(features), ind4, n_cap, n_dev, channels, shape3[0], shape3[1], shape3[2],
+        static_cast<__nv_bfloat16 *>(dense));
+  FV2P_LAUNCH_CHECK("dense");
+  return FV2P_OK;
+}
+
 extern "C" int fv2p_dense_ncdhw(const float *features, const int32_t *indices, int64_t n_cap, const int32_t *n_dev,
                                 int channels, const int32_t *shape3, float *dense, fv2p_stream_t stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   FV2P_REQUIRE(shape3 && channels >= 1 && n_cap >= 0, "dense: bad arguments");
   if (n_cap == 0) return FV2P_OK;
   FV2P_REQUIRE(features && indices && dense, "dense: null pointer argument");
-  dense_ncdhw_kernel<<<persistent_grid(), kThreads, 0, stream>>>(features, reinterpret_cast<const int4 *>(indices),
-                                                                n_cap, n_dev, channels, shape3[0], shape3[1],
-                                                                shape3[2], dense);
-  FV2P_LAUNCH_CHECK("dense");
-  return FV2P_OK;
+  return launch_dense(features, indices, n_cap, n_dev, channels, shape3, 4, dense, static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int fv2p_height_compression(const void *features, const int32_t *indices, int64_t n_cap,
+                                       const int32_t *n_dev, int batch, int channels, const int32_t *shape3,
+                                       int elem_bytes, void *spatial_features, fv2p_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  FV2P_REQUIRE(shape3 && channels >= 1 && n_cap >= 0 && batch >= 1, "height_compression: bad arguments");
+  FV2P_REQUIRE(elem_bytes == 4 || elem_bytes == 2, "height_compression: elem_bytes must be 4 (fp32) or 2 (bf16)");
+  FV2P_REQUIRE(spatial_features, "height_compression: null output");
+  const size_t bytes = (size_t)batch * channels * shape3[0] * shape3[1] * shape3[2] * (size_t)elem_bytes;
+  int st = cuda_status(cudaMemsetAsync(spatial_features, 0, bytes, stream), "height_compression");
+  if (st) return st;
+  if (n_cap == 0) return FV2P_OK;
+  FV2P_REQUIRE(features && indices, "height_compression: null pointer argument");
+  return launch_dense(features, indices, n_cap, n_dev, channels, shape3, elem_bytes, spatial_features, stream);
 }
 
 extern "C" int fv2p_copy_rows(const void *src, void *dst, int64_t row_bytes, int64_t n_cap, const int32_t *n_dev,

@@ -25,7 +25,7 @@ from .voxel_generator import BatchVoxelizer
 
 class HotPath(object):
     def __init__(self, backbone, voxel_size, point_cloud_range, max_points_per_voxel, max_voxels,
-                 precision=None, use_graph=False, lanes=2):
+                 precision=None, use_graph=False, lanes=2, bev=False):
         self.backbone = backbone
         if precision is not None:
             try:
@@ -39,6 +39,8 @@ class HotPath(object):
         self._lanes = [(self.engine, self.voxelizer)]
         self._lane_streams = {}
         self.lanes = max(1, int(lanes))
+        self.bev = bool(bev)  # append HeightCompression (the BEV map of the stride-8 output) to the step
+        self._bev_bufs = {}
         self.use_graph = use_graph
         self._slots = {}
         self._graphs = {}
@@ -118,7 +120,28 @@ class HotPath(object):
         n0 = vox["voxel_offsets"][batch:batch + 1]
         arena = engine.launch(vox["voxel_features"], vox["voxel_coords"], batch, n0_dev=n0, cap0=vox["cap"],
                               features_ready=vox["features_ready"])
-        return dict(vox=vox, arena=arena, batch=batch)
+        handle = dict(vox=vox, arena=arena, batch=batch)
+        if self.bev:
+            handle["spatial_features"] = self._height_compression(engine, arena, batch, lane)
+        return handle
+
+    def _height_compression(self, engine, arena, batch, lane):
+        """HeightCompression of the stride-8 output into this lane's BEV buffer, row count read on the device."""
+        from .height_compression import height_compression
+        out_step = [st for st in engine.steps if st.export == "out"][0]
+        feats = arena["bufs"][out_step.out_buf]
+        last = len(arena["caps"]) - 1
+        shape = [int(v) for v in engine.level_shapes[last]]
+        key = (lane, batch, feats.shape[1], tuple(shape), feats.dtype, str(feats.device))
+        buf = self._bev_bufs.get(key)
+        if buf is None:
+            buf = torch.empty((batch, feats.shape[1] * shape[0], shape[1], shape[2]), dtype=feats.dtype,
+                              device=feats.device)
+            self._bev_bufs = {k: v for k, v in self._bev_bufs.items() if k[0] != lane}
+            self._bev_bufs[key] = buf
+            engine.arena_gen += 1  # a new buffer behind captured addresses
+        return height_compression(feats, arena["indices"][last], shape, batch, out=buf,
+                                  n_dev=arena["counts"][last:last + 1])
 
     def launch_graph(self, slot=0, lane=0):
         """Same step as launch_resident over the WHOLE staging buffer of `slot`, replayed from a CUDA graph.
@@ -203,6 +226,9 @@ class HotPath(object):
             'multi_scale_3d_features': {k: outs[k] for k in ('x_conv1', 'x_conv2', 'x_conv3', 'x_conv4')},
             'multi_scale_3d_strides': {'x_conv1': 1, 'x_conv2': 2, 'x_conv3': 4, 'x_conv4': 8},
         }
+        if "spatial_features" in handle:  # HeightCompression.forward's keys (height_compression.py:23-24)
+            batch_dict['spatial_features'] = handle["spatial_features"]
+            batch_dict['spatial_features_stride'] = 8
         return batch_dict, info
 
     # ------------------------------------------------------------------ pipelined throughput mode

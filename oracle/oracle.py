@@ -168,6 +168,18 @@ def rulebook_conv(indices, batch, in_shape, ksize, stride, pad, dilation=1):
     return outids[:n_out].copy(), pairs, num, out_shape
 
 
+def height_compression(features, indices, spatial_shape, batch_size):
+    """HeightCompression.forward (pcdet/models/backbones_2d/map_to_bev/height_compression.py:20-25) on top of
+    SparseConvTensor.dense() (pcdet/ops/spconv/structure.py:5-18, 57-66): scatter [N,C] rows at (b,z,y,x) into zeros
+    [B,D,H,W,C], permute to [B,C,D,H,W], view as [B,C*D,H,W]."""
+    features = np.asarray(features)
+    indices = _i32(indices)
+    d, h, w = (int(v) for v in spatial_shape)
+    dense = np.zeros((int(batch_size), d, h, w, features.shape[1]), features.dtype)
+    dense[indices[:, 0], indices[:, 1], indices[:, 2], indices[:, 3]] = features
+    return np.ascontiguousarray(dense.transpose(0, 4, 1, 2, 3)).reshape(int(batch_size), features.shape[1] * d, h, w)
+
+
 # --------------------------------------------------------------------------------------------
 # convolution
 # --------------------------------------------------------------------------------------------

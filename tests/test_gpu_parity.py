@@ -539,3 +539,40 @@ def test_module_path_trains():
     assert torch.allclose(gw, w.grad, atol=1e-3, rtol=1e-3)
     assert torch.allclose(gb, b.grad, atol=1e-3, rtol=1e-3)
     assert torch.allclose(gx, f2.grad, atol=1e-3, rtol=1e-3)
+
+
+def test_height_compression_matches_reference_and_oracle():
+    """HeightCompression is pure data movement: bit-exact against the reference fixture, against
+    the oracle at the KITTI BEV shape, in fp32 and bf16, as a module and appended to the HotPath step."""
+    g = load_golden("height_compression")
+    shape, batch = [int(v) for v in g["spatial_shape"]], int(g["batch_size"])
+    x = spconv.SparseConvTensor(cuda(g["features"]), cuda(g["indices"]), shape, batch)
+    hc = fv2p_b200.HeightCompression({"NUM_BEV_FEATURES": g["features"].shape[1] * shape[0]})
+    bd = hc({"encoded_spconv_tensor": x, "encoded_spconv_tensor_stride": 8})
+    assert bd["spatial_features_stride"] == 8
+    assert np.array_equal(bd["spatial_features"].cpu().numpy(), g["spatial_features"])
+    # KITTI stride-8 shape, fp32 and bf16, against the oracle
+    rng = np.random.default_rng(21)
+    shape, batch, c = [2, 200, 176], 2, 128
+    ind = synth.random_voxels(shape, 5000, batch, seed=22).astype(np.int32)
+    feats = rng.standard_normal((ind.shape[0], c)).astype(np.float32)
+    want = O.height_compression(feats, ind, shape, batch)
+    for dt in (torch.float32, torch.bfloat16):
+        f = cuda(feats, dt)
+        got = fv2p_b200.height_compression.height_compression(f, cuda(ind), shape, batch)
+        assert got.shape == (batch, c * shape[0], shape[1], shape[2]) and got.dtype == dt
+        ref_dt = torch.from_numpy(want).to(dt)
+        assert torch.equal(got.cpu(), ref_dt)
+    # appended to the step (row count read on the device), eager and graph replay
+    cfg = synth.DATASETS["kitti"]
+    net, _ = _load_backbone("VoxelResBackBone8x", 4, synth.grid_size(cfg), 4)
+    frames = [synth.lidar_frame("kitti", seed=300 + i, az_steps=40) for i in range(2)]
+    for use_graph in (False, True):
+        hp = fv2p_b200.HotPath(net, cfg["voxel_size"], cfg["point_cloud_range"], 5, 16000, use_graph=use_graph,
+                               bev=True)
+        for _ in range(2):
+            bd, info = hp(frames)
+        enc = bd["encoded_spconv_tensor"]
+        want = O.height_compression(enc.features.cpu().numpy(), enc.indices.cpu().numpy(), enc.spatial_shape, 2)
+        assert bd["spatial_features_stride"] == 8
+        assert np.array_equal(bd["spatial_features"].cpu().numpy(), want)

@@ -96,3 +96,11 @@ def test_empty_inputs():
     assert v.shape == (0, 5, 4) and c.shape == (0, 3) and n.shape == (0,)
     outids, pairs, num = O.rulebook_subm(np.zeros((0, 4), np.int32), 1, [5, 6, 7])
     assert pairs.shape == (27, 2, 0) and num.sum() == 0
+
+
+def test_height_compression_matches_reference_module():
+    """the oracle against the reference's own HeightCompression + SparseConvTensor.dense()."""
+    g = load_golden("height_compression")
+    got = O.height_compression(g["features"], g["indices"], g["spatial_shape"], int(g["batch_size"]))
+    assert got.shape == g["spatial_features"].shape
+    assert np.array_equal(got, g["spatial_features"])
