@@ -280,6 +280,16 @@ def run_ours(args, wl, rank, world, device):
         n_in, n_o = counts[bk.in_level], counts[bk.out_level]
         rb_bytes += n_in * 16 + bk.kvol * 2 * n_in * 4 + bk.kvol * 4 + (0 if bk.subm else n_o * 16) + bk.kvol * n_o * 4
     rb_ms = max(geo_conv_ms - conv_ms, 1e-3)
+    # ---- the step right after the path (not part of `value`): HeightCompression of the stride-8
+    # output, zero fill + scatter; algorithmic bytes = rows read + indices + the whole BEV map written
+    from fv2p_b200.height_compression import height_compression
+    enc = outs["out"]
+    bev_shape = [int(v) for v in enc.spatial_shape]
+    bev_buf = torch.empty((wl["batch"], enc.features.shape[1] * bev_shape[0], bev_shape[1], bev_shape[2]),
+                          dtype=enc.features.dtype, device=device)
+    bev_ms = timed(lambda: height_compression(enc.features, enc.indices, bev_shape, wl["batch"], out=bev_buf))
+    bev_bytes = enc.features.numel() * enc.features.element_size() + enc.indices.numel() * 4 + \
+        bev_buf.numel() * bev_buf.element_size()
     launches = hp.engine.launch_count() + 8
     line = {
         "metric": METRIC, "value": round(value, 2), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
@@ -301,6 +311,9 @@ def run_ours(args, wl, rank, world, device):
                    "voxelize_frac_of_hbm": round(vox_bytes / vox_ms / 1e6 / pk["hbm_gbs"], 4),
                    "rulebooks_ms": round(rb_ms, 4), "rulebooks_gbs": round(rb_bytes / rb_ms / 1e6, 1),
                    "rulebooks_frac_of_hbm": round(rb_bytes / rb_ms / 1e6 / pk["hbm_gbs"], 4),
+                   "height_compression_ms": round(bev_ms, 4),
+                   "height_compression_gbs": round(bev_bytes / bev_ms / 1e6, 1),
+                   "height_compression_frac_of_hbm": round(bev_bytes / bev_ms / 1e6 / pk["hbm_gbs"], 4),
                    "conv_ms_sum": round(conv_ms, 4), "step_ms_median": round(statistics.median(step_ms), 4),
                    "host_wall_ms_per_step": round(wall_s * 1000 / args.steps, 3),
                    "total_gflop": round(sum(r["flops"] for r in recs) / 1e9, 3),
