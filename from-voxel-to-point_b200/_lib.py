@@ -51,7 +51,9 @@ PROTOTYPES = {
     "fv2p_indice_conv_fp32": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_int, _c_int, _c_int, _c_int,
                                        _c_int, _c_vp, _c_vp, _c_sz, _c_vp]),
     "fv2p_dense_ncdhw": (_c_int, [_c_vp, _c_vp, _c_i64, _c_vp, _c_int, _c_vp, _c_vp, _c_vp]),
-    "fv2p_height_compression": (_c_int, [_c_vp, _c_vp, _c_i64, _c_vp, _c_int, _c_int, _c_vp, _c_int, _c_vp, _c_vp]),
+    "fv2p_height_compression_workspace_bytes": (_c_sz, [_c_int, _c_vp]),
+    "fv2p_height_compression": (_c_int, [_c_vp, _c_vp, _c_i64, _c_vp, _c_int, _c_int, _c_vp, _c_int, _c_vp, _c_vp, _c_sz,
+                                         _c_vp]),
     "fv2p_copy_rows": (_c_int, [_c_vp, _c_vp, _c_i64, _c_i64, _c_vp, _c_vp]),
     "fv2p_cast_f32_to_bf16": (_c_int, [_c_vp, _c_vp, _c_i64, _c_vp]),
     "fv2p_cast_bf16_to_f32": (_c_int, [_c_vp, _c_vp, _c_i64, _c_vp]),

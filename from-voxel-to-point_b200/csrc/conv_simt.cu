@@ -328,6 +328,79 @@ extern "C" int fv2p_indice_conv_fp32(const float *features, const float *filters
                        nullptr, nullptr, nullptr, 0, FV2P_MODE_F32, out, stream_);
 }
 
+namespace fv2p {
+namespace {
+
+// HeightCompression in one pass over the output: cell -> row map first (tiny), then every 16 bytes of the BEV map are
+// written exactly once, coalesced, with the row's value where a row exists and zero elsewhere.  (Zero fill + scatter
+// wrote the occupied cells twice and the scatter's 4-byte stores cost a sector each: 87 us against 45 us for the
+// fill alone on the KITTI map.)
+__global__ void __launch_bounds__(kThreads)
+bev_cell_rows_kernel(const int4 *__restrict__ indices, int64_t n_cap, const int *n_dev, int D, int H, int W,
+                     int *cell_row) {
+  int n = n_dev ? *n_dev : (int)n_cap;
+  if (n > n_cap) n = (int)n_cap;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int4 q = __ldg(&indices[i]);
+    cell_row[(((size_t)q.x * D + q.y) * H + q.z) * W + q.w] = i;
+  }
+}
+
+// Work item = (frame, z, 8 rows of y, 8 channels): a thread takes 16 bytes of x, reads the cell -> row ids once and
+// writes the same 16 bytes of all eight channel planes (rows' values are 8 consecutive channels = one 16/32-byte
+// load per occupied cell).  No 64-bit index arithmetic per element.
+constexpr int kBevRows = 8, kBevChannels = 8;
+
+template <typename T, int kVec>  // kVec elements = 16 bytes
+__global__ void __launch_bounds__(kThreads)
+bev_write_kernel(const T *__restrict__ features, const int *__restrict__ cell_row, int batch, int channels, int D,
+                 int H, int W, T *out) {
+  const int wv = W / kVec;
+  const int tiles_y = (H + kBevRows - 1) / kBevRows;
+  const int cgroups = channels / kBevChannels;
+  const int items = batch * D * tiles_y * cgroups;
+  const size_t plane = (size_t)H * W;
+  for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    int r = item;
+    const int cg = r % cgroups;
+    r /= cgroups;
+    const int ty = r % tiles_y;
+    r /= tiles_y;
+    const int z = r % D, b = r / D;
+    const int *cells = cell_row + ((size_t)b * D + z) * plane;
+    T *dst = out + (((size_t)b * channels + (size_t)cg * kBevChannels) * D + z) * plane;
+    for (int t = threadIdx.x; t < kBevRows * wv; t += blockDim.x) {
+      const int y = ty * kBevRows + t / wv, xv = t % wv;
+      if (y >= H) break;
+      const size_t off = (size_t)y * W + (size_t)xv * kVec;
+      int ids[kVec];
+#pragma unroll
+      for (int u = 0; u < kVec; u += 4) {
+        const int4 id = __ldg(reinterpret_cast<const int4 *>(cells + off + u));
+        ids[u] = id.x, ids[u + 1] = id.y, ids[u + 2] = id.z, ids[u + 3] = id.w;
+      }
+      T v[kBevChannels][kVec];
+#pragma unroll
+      for (int u = 0; u < kVec; ++u) {
+        if (ids[u] >= 0) {
+          const T *src = features + (size_t)ids[u] * channels + (size_t)cg * kBevChannels;
+#pragma unroll
+          for (int q = 0; q < kBevChannels; ++q) v[q][u] = src[q];
+        } else {
+#pragma unroll
+          for (int q = 0; q < kBevChannels; ++q) v[q][u] = T(0.f);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < kBevChannels; ++q)
+        *reinterpret_cast<uint4 *>(dst + (size_t)q * D * plane + off) = *reinterpret_cast<const uint4 *>(v[q]);
+    }
+  }
+}
+
+}  // namespace
+}  // namespace fv2p
+
 static int launch_dense(const void *features, const int32_t *indices, int64_t n_cap, const int32_t *n_dev,
                         int channels, const int32_t *shape3, int elem_bytes, void *dense, cudaStream_t stream) {
   const int4 *ind4 = reinterpret_cast<const int4 *>(indices);
@@ -351,19 +424,53 @@ extern "C" int fv2p_dense_ncdhw(const float *features, const int32_t *indices, i
   return launch_dense(features, indices, n_cap, n_dev, channels, shape3, 4, dense, static_cast<cudaStream_t>(stream_));
 }
 
+extern "C" size_t fv2p_height_compression_workspace_bytes(int batch, const int32_t *shape3) {
+  if (!shape3 || batch < 1) return 0;
+  return (size_t)batch * shape3[0] * shape3[1] * shape3[2] * sizeof(int) + 256;
+}
+
 extern "C" int fv2p_height_compression(const void *features, const int32_t *indices, int64_t n_cap,
                                        const int32_t *n_dev, int batch, int channels, const int32_t *shape3,
-                                       int elem_bytes, void *spatial_features, fv2p_stream_t stream_) {
+                                       int elem_bytes, void *spatial_features, void *workspace,
+                                       size_t workspace_bytes, fv2p_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   FV2P_REQUIRE(shape3 && channels >= 1 && n_cap >= 0 && batch >= 1, "height_compression: bad arguments");
   FV2P_REQUIRE(elem_bytes == 4 || elem_bytes == 2, "height_compression: elem_bytes must be 4 (fp32) or 2 (bf16)");
   FV2P_REQUIRE(spatial_features, "height_compression: null output");
-  const size_t bytes = (size_t)batch * channels * shape3[0] * shape3[1] * shape3[2] * (size_t)elem_bytes;
-  int st = cuda_status(cudaMemsetAsync(spatial_features, 0, bytes, stream), "height_compression");
+  FV2P_REQUIRE(n_cap == 0 || (features && indices), "height_compression: null pointer argument");
+  const int D = shape3[0], H = shape3[1], W = shape3[2];
+  const size_t cells = (size_t)batch * D * H * W;
+  const int vec = 16 / elem_bytes;
+  // measured on the KITTI map (8 x 256 x 200 x 176): fp32 79 us in one pass against 87 us for fill + scatter; bf16
+  // 93 us against 56 us (16-byte stores of 2-byte elements cost the one-pass kernel too many instructions)
+  const bool one_pass = elem_bytes == 4 && workspace && workspace_bytes >= cells * sizeof(int) && W % vec == 0 &&
+                        W % 4 == 0 &&
+                        channels % fv2p::kBevChannels == 0 &&
+                        (reinterpret_cast<uintptr_t>(spatial_features) & 15) == 0 &&
+                        (reinterpret_cast<uintptr_t>(workspace) & 15) == 0;
+  if (!one_pass) {  // zero fill + scatter (any shape, no scratch)
+    int st = cuda_status(cudaMemsetAsync(spatial_features, 0, cells * channels * (size_t)elem_bytes, stream),
+                         "height_compression");
+    if (st) return st;
+    if (n_cap == 0) return FV2P_OK;
+    return launch_dense(features, indices, n_cap, n_dev, channels, shape3, elem_bytes, spatial_features, stream);
+  }
+  int *cell_row = static_cast<int *>(workspace);
+  int st = cuda_status(cudaMemsetAsync(cell_row, 0xFF, cells * sizeof(int), stream), "height_compression");
   if (st) return st;
-  if (n_cap == 0) return FV2P_OK;
-  FV2P_REQUIRE(features && indices, "height_compression: null pointer argument");
-  return launch_dense(features, indices, n_cap, n_dev, channels, shape3, elem_bytes, spatial_features, stream);
+  if (n_cap > 0)
+    bev_cell_rows_kernel<<<persistent_grid(), kThreads, 0, stream>>>(reinterpret_cast<const int4 *>(indices), n_cap,
+                                                                   n_dev, D, H, W, cell_row);
+  if (elem_bytes == 4)
+    bev_write_kernel<float, 4><<<persistent_grid() * 2, kThreads, 0, stream>>>(
+        static_cast<const float *>(features), cell_row, batch, channels, D, H, W,
+        static_cast<float *>(spatial_features));
+  else
+    bev_write_kernel<__nv_bfloat16, 8><<<persistent_grid() * 2, kThreads, 0, stream>>>(
+        static_cast<const __nv_bfloat16 *>(features), cell_row, batch, channels, D, H, W,
+        static_cast<__nv_bfloat16 *>(spatial_features));
+  FV2P_LAUNCH_CHECK("height_compression");
+  return FV2P_OK;
 }
 
 extern "C" int fv2p_copy_rows(const void *src, void *dst, int64_t row_bytes, int64_t n_cap, const int32_t *n_dev,

@@ -2,8 +2,9 @@
 (pcdet/models/backbones_2d/map_to_bev/height_compression.py:4-26): the stride-8 sparse tensor densified to
 [B, C, D, H, W] and viewed as the BEV feature map [B, C*D, H, W] the 2D backbone reads.
 
-On CUDA the densification is one fv2p_height_compression call (zero fill + scatter of the live rows); the view is
-free because [B, C, D, H, W] and [B, C*D, H, W] are the same bytes.  HotPath(..., bev=True) appends the same call to
+On CUDA the densification is one fv2p_height_compression call (a cell -> row map, then one coalesced pass that
+writes every element of the map once); the view is free because [B, C, D, H, W] and [B, C*D, H, W] are the same
+bytes.  HotPath(..., bev=True) appends the same call to
 the graph-captured step, with the row count read on the device.
 """
 import torch
@@ -12,7 +13,7 @@ import torch.nn as nn
 from . import _lib
 
 
-def height_compression(features, indices, spatial_shape, batch_size, out=None, n_dev=None):
+def height_compression(features, indices, spatial_shape, batch_size, out=None, n_dev=None, workspace=None):
     """features [N, C] fp32/bf16 CUDA, indices [N, 4] int32 (b, z, y, x) -> [B, C*D, H, W] (zeros elsewhere)."""
     dev = _lib.require_device(features)
     if features.dtype not in (torch.float32, torch.bfloat16) or indices.dtype != torch.int32:
@@ -24,11 +25,15 @@ def height_compression(features, indices, spatial_shape, batch_size, out=None, n
         out = torch.empty((int(batch_size), c * d, h, w), dtype=features.dtype, device=features.device)
     if tuple(out.shape) != (int(batch_size), c * d, h, w) or out.dtype != features.dtype or not out.is_contiguous():
         raise ValueError("height_compression: output buffer has the wrong shape, dtype or layout")
+    lib = _lib.load()
+    shape3 = _lib.i32x3([d, h, w])
+    if workspace is None:  # the cell -> row map; callers inside a captured graph pass their own fixed buffer
+        workspace = _lib.Workspace.get(features.device, lib.fv2p_height_compression_workspace_bytes(int(batch_size),
+                                                                                                      shape3), "bev")
     with torch.cuda.device(dev):
-        st = _lib.load().fv2p_height_compression(_lib.ptr(features), _lib.ptr(indices), features.shape[0],
-                                                 _lib.ptr(n_dev), int(batch_size), c, _lib.i32x3([d, h, w]),
-                                                 features.element_size(), _lib.ptr(out),
-                                                 _lib.stream_ptr(features.device))
+        st = lib.fv2p_height_compression(_lib.ptr(features), _lib.ptr(indices), features.shape[0], _lib.ptr(n_dev),
+                                         int(batch_size), c, shape3, features.element_size(), _lib.ptr(out),
+                                         _lib.ptr(workspace), workspace.numel(), _lib.stream_ptr(features.device))
     _lib.check(st, "height_compression")
     return out
 

@@ -135,13 +135,15 @@ class HotPath(object):
         key = (lane, batch, feats.shape[1], tuple(shape), feats.dtype, str(feats.device))
         buf = self._bev_bufs.get(key)
         if buf is None:
-            buf = torch.empty((batch, feats.shape[1] * shape[0], shape[1], shape[2]), dtype=feats.dtype,
-                              device=feats.device)
+            ws_bytes = _lib.load().fv2p_height_compression_workspace_bytes(batch, _lib.i32x3(shape))
+            buf = (torch.empty((batch, feats.shape[1] * shape[0], shape[1], shape[2]), dtype=feats.dtype,
+                               device=feats.device),
+                   torch.empty(ws_bytes, dtype=torch.uint8, device=feats.device))
             self._bev_bufs = {k: v for k, v in self._bev_bufs.items() if k[0] != lane}
             self._bev_bufs[key] = buf
-            engine.arena_gen += 1  # a new buffer behind captured addresses
-        return height_compression(feats, arena["indices"][last], shape, batch, out=buf,
-                                  n_dev=arena["counts"][last:last + 1])
+            engine.arena_gen += 1  # new buffers behind captured addresses
+        return height_compression(feats, arena["indices"][last], shape, batch, out=buf[0],
+                                  n_dev=arena["counts"][last:last + 1], workspace=buf[1])
 
     def launch_graph(self, slot=0, lane=0):
         """Same step as launch_resident over the WHOLE staging buffer of `slot`, replayed from a CUDA graph.

@@ -227,13 +227,17 @@ FV2P_API int fv2p_dense_ncdhw(const float *features, const int32_t *indices, int
                      fv2p_stream_t stream);
 
 /* HeightCompression.forward (pcdet/models/backbones_2d/map_to_bev/height_compression.py:20-25): the dense() of the
- * stride-8 output viewed as [batch, channels*D, H, W] - the same bytes as [batch, channels, D, H, W].  Zero-fills
- * `spatial_features` and scatters the live rows (count *n_dev if given, else n_cap); rows are
- * (batch, z, y, x).  elem_bytes 4 = fp32, 2 = bf16.  Stream-ordered, no host sync: can follow the backbone in the
- * same CUDA graph. */
+ * stride-8 output viewed as [batch, channels*D, H, W] - the same bytes as [batch, channels, D, H, W].  Every
+ * element of `spatial_features` is written (zero where no row exists); the live rows are *n_dev if given, else
+ * n_cap; rows are (batch, z, y, x).  elem_bytes 4 = fp32, 2 = bf16.  With a workspace of
+ * fv2p_height_compression_workspace_bytes (a cell -> row map) the map is written in one coalesced pass; without
+ * one (NULL) it is zero fill + scatter.  Stream-ordered, no host sync: can follow the backbone in the same CUDA
+ * graph. */
+FV2P_API size_t fv2p_height_compression_workspace_bytes(int batch, const int32_t *shape3);
 FV2P_API int fv2p_height_compression(const void *features, const int32_t *indices, int64_t n_cap,
                             const int32_t *n_dev, int batch, int channels, const int32_t *shape3,
-                            int elem_bytes, void *spatial_features, fv2p_stream_t stream);
+                            int elem_bytes, void *spatial_features, void *workspace, size_t workspace_bytes,
+                            fv2p_stream_t stream);
 
 /* Copies the live rows (count on the device) of a capacity-sized row buffer; row_bytes must be a multiple of 16.
  * Used to snapshot a step's result so that its D2H copy overlaps the next step. */
