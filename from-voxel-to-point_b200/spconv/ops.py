@@ -213,13 +213,25 @@ def fused_indice_conv(features, filters, bias, indice_pairs, indice_pair_num, nu
 
 
 def indice_conv_backward(features, filters, out_bp, indice_pairs, indice_pair_num, inverse=False, subm=False):
-    """ops.py:143-158 / spconv_ops.h:365-457.  NOT on the hot path: composed from
-    torch index ops so that the modules stay trainable; a fused CUDA backward is a later row."""
+    """ops.py:143-158 / spconv_ops.h:365-457.  NOT on the hot path.
+
+    grad_input is the same contraction as the forward pass with the roles of the two row sets swapped and W
+    transposed -- dX[j] = sum_k dY[out(k, j)] W[k]^T -- so on CUDA fp32 it runs through fv2p_conv_fwd on the
+    input-major neighbour map (fv2p_pairs_to_nbr with the pair columns swapped); every input row accumulates its
+    offsets in ascending k, no atomics.  grad_filters[k] = X[in]^T dY[out] stays a gather + library GEMM per
+    offset, as in the reference (torch::mm, spconv_ops.h:433-436)."""
     cin, cout = filters.shape[-2], filters.shape[-1]
     w = filters.reshape(-1, cin, cout)
-    grad_in = torch.zeros_like(features)
     grad_w = torch.zeros_like(w)
     nums = indice_pair_num.tolist()
+    use_cuda = features.is_cuda and features.dtype == torch.float32 and out_bp.dtype == torch.float32 and \
+        indice_pairs.dtype == torch.int32
+    if use_cuda:
+        nbr_in = pairs_to_nbr(indice_pairs, indice_pair_num, features.shape[0], inverse=not inverse)
+        grad_in = conv_forward(out_bp.contiguous(), w.transpose(1, 2).contiguous(), nbr_in.contiguous(),
+                               features.shape[0], mode=_lib.MODE_F32)
+    else:
+        grad_in = torch.zeros_like(features)
     for k, hot in enumerate(nums):
         if hot <= 0:
             continue
@@ -227,5 +239,6 @@ def indice_conv_backward(features, filters, out_bp, indice_pairs, indice_pair_nu
         dst = indice_pairs[k, 0 if inverse else 1, :hot].long()
         go = out_bp[dst]
         grad_w[k] = features[src].t() @ go
-        grad_in.index_add_(0, src, go @ w[k].t())
+        if not use_cuda:
+            grad_in.index_add_(0, src, go @ w[k].t())
     return grad_in, grad_w.view_as(filters)

@@ -539,6 +539,21 @@ def test_module_path_trains():
     assert torch.allclose(gw, w.grad, atol=1e-3, rtol=1e-3)
     assert torch.allclose(gb, b.grad, atol=1e-3, rtol=1e-3)
     assert torch.allclose(gx, f2.grad, atol=1e-3, rtol=1e-3)
+    # strided conv: grad_input runs through fv2p_conv_fwd on the input-major map
+    conv2 = spconv.SparseConv3d(6, 10, 3, stride=2, padding=1, bias=False, indice_key="t2").to(DEV)
+    feats2 = torch.randn(ind.shape[0], 6, device=DEV, requires_grad=True)
+    y2 = conv2(spconv.SparseConvTensor(feats2, cuda(ind), shape, 1))
+    (y2.features ** 2).sum().backward()
+    w2 = conv2.weight.detach().clone().requires_grad_(True)
+    f3 = feats2.detach().clone().requires_grad_(True)
+    dense2 = spconv.scatter_nd(cuda(ind).long(), f3, [1] + shape + [6]).permute(0, 4, 1, 2, 3)
+    out2 = torch.nn.functional.conv3d(dense2, w2.permute(4, 3, 0, 1, 2), None, 2, 1)
+    oi = y2.indices.long()
+    picked2 = out2[oi[:, 0], :, oi[:, 1], oi[:, 2], oi[:, 3]]
+    assert torch.allclose(y2.features, picked2, atol=1e-4, rtol=1e-4)
+    (picked2 ** 2).sum().backward()
+    assert torch.allclose(conv2.weight.grad, w2.grad, atol=1e-3, rtol=1e-3)
+    assert torch.allclose(feats2.grad, f3.grad, atol=1e-3, rtol=1e-3)
 
 
 def test_height_compression_matches_reference_and_oracle():
