@@ -85,6 +85,23 @@ __device__ __forceinline__ uint32_t table_insert(unsigned long long *keys, uint3
   }
 }
 
+// Same for a table that may be too small for the keys offered (its size follows a caller-chosen capacity): gives up
+// with 0xFFFFFFFF once every slot has been looked at instead of probing a full table forever.
+__device__ __forceinline__ uint32_t table_insert_bounded(unsigned long long *keys, uint32_t mask,
+                                                         unsigned long long key) {
+  uint32_t slot = mix64(key) & mask;
+  for (uint32_t probes = 0; probes <= mask; ++probes) {
+    unsigned long long seen = keys[slot];
+    if (seen == key) return slot;
+    if (seen == kEmptyKey) {
+      unsigned long long prev = atomicCAS(&keys[slot], kEmptyKey, key);
+      if (prev == kEmptyKey || prev == key) return slot;
+    }
+    slot = (slot + 1) & mask;
+  }
+  return 0xFFFFFFFFu;
+}
+
 // Returns the slot of `key` or 0xFFFFFFFF.
 __device__ __forceinline__ uint32_t table_find(const unsigned long long *__restrict__ keys,
                                                uint32_t mask, unsigned long long key) {

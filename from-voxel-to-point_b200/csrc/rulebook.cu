@@ -206,7 +206,7 @@ subm_probe_in_kernel(const int4 *__restrict__ indices, const int *n_dev, int64_t
 // Each input inserts its candidate outputs and bids  j*E + e  for them.
 __global__ void __launch_bounds__(kThreads)
 conv_insert_kernel(const int4 *__restrict__ indices, const int *n_dev, int64_t n_cap, Geom g, int64_t out_cap,
-                   unsigned long long *keys, int *vals, int *cand_slot) {
+                   unsigned long long *keys, int *vals, int *cand_slot, int *status) {
   const int n = live_count(n_dev, n_cap);
   int64_t want = (int64_t)n * g.emax;
   if (want > out_cap) want = out_cap;
@@ -221,9 +221,15 @@ conv_insert_kernel(const int4 *__restrict__ indices, const int *n_dev, int64_t n
       if (e < cs.total) {
         int o[3], k;
         if (candidate_at(g, cs, pos, e, o, k)) {
-          uint32_t slot = table_insert(keys, mask, voxel_key(q.x, o[0], o[1], o[2], D, H, W));
-          atomicMin(&vals[slot], j * g.emax + e);
-          slot_out = (int)slot;
+          // the table is sized by out_cap: with more distinct outputs than that it fills up - flag it like the
+          // row overflow (the caller enlarges out_cap and runs the step again) instead of probing forever
+          uint32_t slot = table_insert_bounded(keys, mask, voxel_key(q.x, o[0], o[1], o[2], D, H, W));
+          if (slot != 0xFFFFFFFFu) {
+            atomicMin(&vals[slot], j * g.emax + e);
+            slot_out = (int)slot;
+          } else if (status) {
+            atomicOr(status, FV2P_STATUS_OUT_OVERFLOW);
+          }
         }
       }
       cand_slot[(size_t)j * g.emax + e] = slot_out;
@@ -610,7 +616,8 @@ extern "C" int fv2p_rulebook_conv(const int32_t *indices, int64_t n_cap, const i
     n_live = w.scalars;
   }
   table_clear_kernel<<<grid, kThreads, 0, stream>>>(w.keys, w.vals, n_dev, n_cap, g.emax, out_cap, INT_MAX);
-  conv_insert_kernel<<<grid, kThreads, 0, stream>>>(ind4, n_dev, n_cap, g, out_cap, w.keys, w.vals, w.cand_slot);
+  conv_insert_kernel<<<grid, kThreads, 0, stream>>>(ind4, n_dev, n_cap, g, out_cap, w.keys, w.vals, w.cand_slot,
+                                                    status_dev);
   conv_winner_kernel<<<grid, kThreads, 0, stream>>>(n_dev, n_cap, g.emax, w.vals, w.cand_slot, w.wmask,
                                                     w.win_counts, w.n_chunks);
   launch_scan_chunk_counts(w.win_counts, 1, w.n_chunks, n_live, (int64_t)w.n_chunks * kChunk,

@@ -138,6 +138,11 @@ def trace_backbone(net):
     return steps, list(books.values()), levels
 
 
+class CapacityOverflow(RuntimeError):
+    """A level produced more rows than its arena buffers hold (nothing was written out of bounds).  Raised when the
+    row counts reach the host; `BackboneEngine.grow()` enlarges the bounds, then the step is run again."""
+
+
 class BackboneEngine(object):
     """Runs a traced backbone.  precision: 'fp32' (fp32 storage, fp32-accurate arithmetic) or 'bf16'
     (bf16 storage, fp32 accumulation; the entry layer reads fp32 voxel features)."""
@@ -145,7 +150,7 @@ class BackboneEngine(object):
     SIDE_STREAMS = 4
 
     def __init__(self, net, precision="fp32", materialize_pairs=True, use_tensor_cores=True, sort_rows=True,
-                 concurrent=True):
+                 concurrent=True, cap_growth=2.0):
         traced = trace_backbone(net)
         if traced is None:
             raise NotImplementedError("backbone layout not recognised by the fused engine")
@@ -156,6 +161,11 @@ class BackboneEngine(object):
         self.use_tensor_cores = use_tensor_cores
         self.sort_rows = sort_rows  # mask-sorted row order for the tensor-core layers (same results, fewer stages)
         self.concurrent = concurrent  # geometry and feature pass on forked streams (joined before launch returns)
+        # Row capacity of level l+1 = min(cap_growth * capacity of level l, hard bound).  The hard bound
+        # (fan-out 8 per strided conv, or the dense volume) is 10-100x what LiDAR frames produce - a KITTI batch
+        # of 8 would reserve ~28 GB of rulebooks and feature buffers against ~2 GB at growth 2 - so the arena
+        # starts from the modest bound and grows on CapacityOverflow.  None = hard bound from the start.
+        self.cap_growth = cap_growth
         self._side = None
         self.arena = None
         self.arena_gen = 0
@@ -213,8 +223,19 @@ class BackboneEngine(object):
         for bk in self.books:
             if not bk.subm:
                 vol = int(np.prod(self.level_shapes[bk.out_level])) * int(batch)
-                caps.append(max(1, min(caps[bk.in_level] * bk.fanout, vol)))
+                fan = bk.fanout if not self.cap_growth else min(float(bk.fanout), float(self.cap_growth))
+                caps.append(max(1, min(int(caps[bk.in_level] * fan) + 1024, caps[bk.in_level] * bk.fanout, vol)))
         return caps
+
+    def grow(self):
+        """Enlarges the capacity bounds after a CapacityOverflow (x4, then the hard bound); the next launch
+        allocates a new arena.  Returns False when the bounds are already the hard ones."""
+        if not self.cap_growth:
+            return False
+        self.cap_growth = None if self.cap_growth >= 8 else self.cap_growth * 4.0
+        self.arena = None
+        self.arena_gen += 1  # captured graphs of the old arena are stale
+        return True
 
     def _ensure_arena(self, device, cap0, batch):
         a = self.arena
@@ -430,7 +451,9 @@ class BackboneEngine(object):
         n_levels = len(a["caps"])
         status = host[n_levels]
         if status:
-            raise RuntimeError("fv2p_b200 engine: capacity overflow (status %d); rows exceed the arena bounds" % status)
+            raise CapacityOverflow("fv2p_b200 engine: capacity overflow (status %d): a level has more rows than the "
+                                   "arena bound (cap_growth=%s); call grow() and run the step again" %
+                                   (status, self.cap_growth))
         n = host[:n_levels]
         level_ind = [voxel_coords[:n[0]]] + [t[:n[i + 1]] for i, t in enumerate(a["indices"][1:])]
         indice_dict, nbr_dict = {}, {}
@@ -466,8 +489,13 @@ class BackboneEngine(object):
         return n
 
     def __call__(self, voxel_features, voxel_coords, batch_size):
-        a = self.launch(voxel_features, voxel_coords, batch_size)
-        return self.collect(a, voxel_coords, batch_size)[0]
+        while True:
+            a = self.launch(voxel_features, voxel_coords, batch_size)
+            try:
+                return self.collect(a, voxel_coords, batch_size)[0]
+            except CapacityOverflow:
+                if not self.grow():
+                    raise
 
 
 _TC_FLAG = None

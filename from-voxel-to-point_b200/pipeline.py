@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .engine import BackboneEngine
+from .engine import BackboneEngine, CapacityOverflow
 from .voxel_generator import BatchVoxelizer
 
 
@@ -101,7 +101,7 @@ class HotPath(object):
             e0 = self.engine
             eng = BackboneEngine(self.backbone, precision=e0.precision, materialize_pairs=e0.materialize_pairs,
                                  use_tensor_cores=e0.use_tensor_cores, sort_rows=e0.sort_rows,
-                                 concurrent=e0.concurrent)
+                                 concurrent=e0.concurrent, cap_growth=e0.cap_growth)
             self._lanes.append((eng, BatchVoxelizer(*self._vox_args)))
         return self._lanes[lane]
 
@@ -216,8 +216,14 @@ class HotPath(object):
 
     def __call__(self, frames, device="cuda", fetch="counts"):
         pts, off, mfp, h2d = self.upload(frames, device)
-        handle = self.launch_graph() if self.use_graph else self.launch_resident(pts, off, mfp)
-        outs, info = self.finish(handle, fetch)
+        while True:
+            handle = self.launch_graph() if self.use_graph else self.launch_resident(pts, off, mfp)
+            try:
+                outs, info = self.finish(handle, fetch)
+                break
+            except CapacityOverflow:  # more rows than the arena bound: enlarge every lane's bounds and run again
+                if not any([eng.grow() for eng, _ in self._lanes]):
+                    raise
         info["h2d_bytes"] = h2d
         batch_dict = {
             'batch_size': len(frames),
@@ -314,7 +320,11 @@ class HotPath(object):
         host = snap["counts_host"].tolist()
         n_levels = len(host) - 1
         if host[n_levels]:
-            raise RuntimeError("fv2p_b200: capacity overflow (status %d)" % host[n_levels])
+            for eng, _ in self._lanes:
+                eng.grow()
+            raise CapacityOverflow("fv2p_b200: capacity overflow (status %d) in run_stream; the arena bounds have been "
+                                   "enlarged, restart the stream from this batch (or build the backbone with "
+                                   "CAP_GROWTH: None for the hard bounds)" % host[n_levels])
         rows = host[n_levels - 1]
         hb = self._result_host(("stream", slot), rows, cols, dtype)
         with torch.cuda.stream(copy):

@@ -90,7 +90,8 @@ class _BackboneBase(nn.Module):
         if eng is None or eng.precision != precision:
             eng = BackboneEngine(self, precision=precision,
                                  materialize_pairs=bool(self._cfg('MATERIALIZE_PAIRS', True)),
-                                 sort_rows=bool(self._cfg('SORT_ROWS', True)))
+                                 sort_rows=bool(self._cfg('SORT_ROWS', True)),
+                                 cap_growth=self._cfg('CAP_GROWTH', 2.0))
             object.__setattr__(self, '_engine', eng)  # not a submodule, never in the state_dict
         return eng
 

@@ -591,3 +591,33 @@ def test_height_compression_matches_reference_and_oracle():
         want = O.height_compression(enc.features.cpu().numpy(), enc.indices.cpu().numpy(), enc.spatial_shape, 2)
         assert bd["spatial_features_stride"] == 8
         assert np.array_equal(bd["spatial_features"].cpu().numpy(), want)
+
+
+def test_capacity_overflow_grows_the_arena_and_reruns():
+    """The arena starts from modest row bounds (CAP_GROWTH); a step that overflows them is detected from the status word,
+    the bounds grow and the step runs again - same result as with the hard bounds, eager and from a graph."""
+    g = load_golden("backbone_kitti_VoxelResBackBone8x")
+    want = None
+    for growth in (None, 0.02):
+        net, _ = _load_backbone("VoxelResBackBone8x", 4, g["grid_size"], int(g["seed"]), {"CAP_GROWTH": growth})
+        with torch.no_grad():
+            bd = net({"voxel_features": cuda(g["voxel_features"]), "voxel_coords": cuda(g["voxel_coords"]),
+                      "batch_size": int(g["batch_size"])})
+        enc = bd["encoded_spconv_tensor"]
+        got = (enc.indices.cpu().numpy().copy(), enc.features.cpu().numpy().copy())
+        if want is None:
+            want = got
+        else:
+            assert net.get_engine().cap_growth is None or net.get_engine().cap_growth > 0.02  # it had to grow
+            assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+    cfg = synth.DATASETS["kitti"]
+    frames = [synth.lidar_frame("kitti", seed=400 + i, az_steps=40) for i in range(2)]
+    res = []
+    for growth, use_graph in ((None, False), (0.02, False), (0.02, True)):
+        net, _ = _load_backbone("VoxelResBackBone8x", 4, synth.grid_size(cfg), 4, {"CAP_GROWTH": growth})
+        hp = fv2p_b200.HotPath(net, cfg["voxel_size"], cfg["point_cloud_range"], 5, 16000, use_graph=use_graph)
+        bd, info = hp(frames)
+        enc = bd["encoded_spconv_tensor"]
+        res.append((info["counts"], enc.indices.cpu().numpy().copy(), enc.features.cpu().numpy().copy()))
+    for r in res[1:]:
+        assert r[0] == res[0][0] and np.array_equal(r[1], res[0][1]) and np.array_equal(r[2], res[0][2])
