@@ -127,3 +127,24 @@ def test_candidate_fanout():
     assert f([3, 1, 1], [2, 1, 1], [0, 0, 0], [1, 1, 1]) == 2
     assert f([3, 3, 3], [1, 1, 1], [1, 1, 1], [1, 1, 1]) == 27
     assert f([2, 2, 2], [2, 2, 2], [0, 0, 0], [1, 1, 1]) == 1
+
+
+def test_arena_capacity_bounds_grow_towards_the_hard_bound():
+    """Host logic of the row-capacity bounds (engine._caps / grow): modest bounds first, x4 per overflow, then the
+    hard bound min(fan-out * N, dense volume); never above the hard bound."""
+    import numpy as np
+    import fv2p_b200
+    from fv2p_b200 import synth
+    cfg = synth.DATASETS["kitti"]
+    net = fv2p_b200.VoxelResBackBone8x({"CAP_GROWTH": 2.0}, 4, np.array(synth.grid_size(cfg))).eval()
+    eng = net.get_engine()
+    hard = fv2p_b200.BackboneEngine(net, cap_growth=None)._caps(100000, 8)
+    assert hard == [100000, 800000, 6400000, 1408000, 563200]
+    first = eng._caps(100000, 8)
+    assert first[0] == 100000 and all(a <= b for a, b in zip(first, hard))
+    assert first[1] == 2 * 100000 + 1024 and first[2] == 2 * first[1] + 1024
+    seen = [eng.cap_growth]
+    while eng.grow():
+        seen.append(eng.cap_growth)
+        assert all(a <= b for a, b in zip(eng._caps(100000, 8), hard))
+    assert seen == [2.0, 8.0, None] and eng._caps(100000, 8) == hard and eng.arena is None
