@@ -248,6 +248,10 @@ FV2P_API int fv2p_copy_rows(const void *src, void *dst, int64_t row_bytes, int64
 FV2P_API int fv2p_cast_f32_to_bf16(const float *src, void *dst, int64_t count, fv2p_stream_t stream);
 FV2P_API int fv2p_cast_bf16_to_f32(const void *src, float *dst, int64_t count, fv2p_stream_t stream);
 
+/* The library also exports a few fv2p_debug_* symbols (timing ablations, %globaltimer stamps, role timers in
+ * profiling builds; see profiles/run_layer.py and profiles/timeline.py).  They are profiling hooks, not part of
+ * this interface, and may change without an ABI version bump. */
+
 #ifdef __cplusplus
 }
 #endif
