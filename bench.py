@@ -381,6 +381,61 @@ def cpu_reference(wl, steps, warmup, frames_per_step):
                                         for k, v in timers.items()})
 
 
+def reference_gpu(wl, device, steps=5, warmup=2, frames=None):
+    """The reference's OWN CUDA path on this GPU: oracle/_ref/sparse_conv_ext was
+    built from /root/reference with -DWITH_CUDA for sm_100, so the call sequence of conv.py / spconv_backbone.py on
+    CUDA tensors runs its kernels (src/indice_cuda.cu:30-135 rulebooks on a dense int32 grid + torch::_unique,
+    src/reordering_cuda.cu:31-140 gather / scatter-add, cuBLAS sgemm through torch::mm_out, one host sync per conv)
+    with torch CUDA BatchNorm/ReLU.  Voxels are made on the CPU beforehand (the reference voxelizes in DataLoader
+    workers) and are resident when the timed region starts, so this is the backbone only - the like-for-like bar for
+    our feature + geometry pass.  Timed with CUDA events around each forward."""
+    import torch
+    from oracle import oracle as O
+    from oracle import ref as R
+    import fv2p_b200
+    from fv2p_b200 import synth
+    if not R.have_ext():
+        return {"unavailable": "oracle/_ref/sparse_conv_ext.so not present"}
+    cfg = synth.DATASETS[wl["dataset"]]
+    gs = synth.grid_size(cfg)
+    shape = [int(gs[2]) + 1, int(gs[1]), int(gs[0])]
+    net = getattr(fv2p_b200, wl["backbone"])({}, cfg["num_point_features"], np.array(gs))
+    state = synth.randomize_state(net.state_dict(), seed=0)
+    params = {k: torch.from_numpy(v).to(device) for k, v in state.items()}
+    frames = frames if frames is not None else make_frames(wl, 0, wl["batch"])
+    feats, coords = [], []
+    for b, f in enumerate(frames):
+        v, c, n = O.voxelize(f, cfg["voxel_size"], cfg["point_cloud_range"], cfg["max_points_per_voxel"],
+                             cfg["max_voxels"][wl["split"]])
+        feats.append(O.mean_vfe(v, n))
+        coords.append(np.concatenate([np.full((c.shape[0], 1), b, np.int32), c], 1))
+    feats = torch.from_numpy(np.concatenate(feats)).to(device)
+    coords = torch.from_numpy(np.concatenate(coords)).to(device)
+    try:
+        times = []
+        for i in range(warmup + steps):
+            timers = {}
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            R.ext_backbone_forward(wl["backbone"], params, feats, coords, len(frames), shape, timers=timers,
+                                   device=device)
+            e1.record()
+            torch.cuda.synchronize()
+            if i >= warmup:
+                times.append(e0.elapsed_time(e1))
+    except Exception as e:  # the reference's kernels are not ours to fix
+        return {"unavailable": "reference CUDA path failed on this device: %s" % (str(e).splitlines()[0][:200])}
+    ms = statistics.median(times)
+    return dict(value=round(len(frames) / (ms * 1e-3), 2), unit="frames/s", ms_per_step=round(ms, 3),
+                frames_per_step=len(frames), steps=steps,
+                scope="MeanVFE output resident -> %s forward (rulebooks + convs + BN/ReLU), voxelization not included "
+                      "(the reference voxelizes on the CPU)" % wl["backbone"],
+                kind="reference sparse_conv_ext CUDA kernels (oracle/_ref, sm_100) + cuBLAS + torch CUDA BN/ReLU",
+                host_rulebook_ms=round(1000 * timers.get("rulebook_s", 0.0), 2),
+                host_conv_ms=round(1000 * timers.get("conv_s", 0.0), 2))
+
+
 def run_reference(args, wl, rank, world):
     if rank != 0:
         return None

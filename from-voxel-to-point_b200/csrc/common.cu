@@ -22,17 +22,26 @@ int cuda_status(cudaError_t e, const char *what) {
   return (int)e;
 }
 
+constexpr int kMaxDevices = 64;
+
+int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+  return dev;
+}
+
+// Per device ordinal: one process may drive several GPUs.
 int sm_count() {
-  static int cached = 0;
-  if (cached == 0) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-      cached = n;
+  static int cached[kMaxDevices] = {0};
+  const int dev = current_device();
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      cached[dev] = n;
     else
-      cached = 148;
+      cached[dev] = 148;
   }
-  return cached;
+  return cached[dev];
 }
 
 // Work that is off the caller's dependency chain moves to a second stream: `to` waits for what `from` has enqueued

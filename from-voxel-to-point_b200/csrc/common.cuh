@@ -12,7 +12,8 @@ namespace fv2p {
 // ---------------------------------------------------------------------------------------- errors
 void set_error(const char *fmt, ...);
 int cuda_status(cudaError_t e, const char *what);  // 0 or the cudaError_t, records the message
-int sm_count();                                    // cached per process (current device)
+int sm_count();                                    // of the current device (cached per device ordinal)
+int current_device();                              // ordinal, clamped to [0, 64)
 
 #define FV2P_REQUIRE(cond, ...)       \
   do {                                \

@@ -1029,13 +1029,14 @@ int launch_one(const void *features, int64_t feat_rows, const void *weight, cons
                const int *row_perm, const int *tile_order, int *sched, int kvol, int64_t n_out_cap,
                const int *n_out_dev, int cin, const Epilogue &ep, cudaStream_t stream) {
   using C = Cfg<kTf32, N>;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {false};  // the attribute is per device
+  const int dev = current_device();
+  if (!configured[dev]) {
     int st = cuda_status(cudaFuncSetAttribute(conv_tc_kernel<kTf32, N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               C::kSmemBytes),
                          "conv_fwd(tc) smem attribute");
     if (st) return st;
-    configured = true;
+    configured[dev] = true;
   }
   CUtensorMap map;
   int st = make_feature_map(&map, features, feat_rows, cin, kTf32);

@@ -171,6 +171,7 @@ class BackboneEngine(object):
         self.arena_gen = 0
         self._param_key = None
         self._params = None
+        self._tensors = None
         # liveness of feature buffers: last step reading each one (exports live forever)
         last_read = {}
         for i, st in enumerate(self.steps):
@@ -180,9 +181,20 @@ class BackboneEngine(object):
         self._last_read = last_read
 
     # ------------------------------------------------------------------ parameters
-    def _prepare_params(self, device):
-        key = tuple((p.data_ptr(), p._version) for p in self.net.parameters()) + \
-            tuple((b.data_ptr(), b._version) for b in self.net.buffers()) + (str(device), self.precision)
+    def param_key(self, device):
+        """Cheap identity of everything the packed weights / folded BatchNorm were derived from: (address, version
+        counter) of every parameter and buffer.  In-place updates (load_state_dict, optimizer steps, .copy_) bump
+        the version; replaced tensors change the address.  Recomputed on every launch AND every graph replay."""
+        if self._tensors is None:  # walking the module tree costs ~0.4 ms, the tensors themselves ~30 us
+            self._tensors = list(self.net.parameters()) + list(self.net.buffers())
+        return tuple([t.data_ptr() for t in self._tensors] + [t._version for t in self._tensors]) + \
+            (str(device), self.precision)
+
+    def _prepare_params(self, device, rescan=False):
+        """rescan: walk the module tree again (Parameter objects replaced, not just updated in place)."""
+        if rescan:
+            self._tensors = None
+        key = self.param_key(device)
         if key == self._param_key:
             return self._params
         prm = []
@@ -314,7 +326,7 @@ class BackboneEngine(object):
             raise ValueError("engine expects contiguous inputs")
         cap0 = int(voxel_coords.shape[0] if cap0 is None else cap0)
         a = self._ensure_arena(device, max(cap0, 1), int(batch_size))
-        prm = self._prepare_params(device)
+        prm = self._prepare_params(device, rescan=not torch.cuda.is_current_stream_capturing())
         lib = _lib.load()
         counts = a["counts"]
         caps = a["caps"]

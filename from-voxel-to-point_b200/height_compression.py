@@ -38,6 +38,32 @@ def height_compression(features, indices, spatial_shape, batch_size, out=None, n
     return out
 
 
+class _HeightCompressionFn(torch.autograd.Function):
+    """Differentiable wrapper: the reference's dense() is a scatter_nd (structure.py:5-18,57-66), which autograd
+    follows back to the features; here forward is the CUDA kernel and backward gathers grad[b, :, z, y, x] per row,
+    so the 2D backbone's loss still reaches the sparse convolutions in training mode."""
+
+    @staticmethod
+    def forward(ctx, features, indices, spatial_shape, batch_size):
+        ctx.save_for_backward(indices)
+        ctx.shape5 = (int(batch_size), features.shape[1]) + tuple(int(s) for s in spatial_shape)
+        return height_compression(features.detach(), indices, spatial_shape, batch_size)
+
+    @staticmethod
+    def backward(ctx, grad):
+        (indices,) = ctx.saved_tensors
+        ind = indices.long()
+        g5 = grad.reshape(ctx.shape5)
+        return g5[ind[:, 0], :, ind[:, 1], ind[:, 2], ind[:, 3]].contiguous(), None, None, None
+
+
+def height_compression_autograd(features, indices, spatial_shape, batch_size):
+    """height_compression() that autograd can differentiate with respect to `features`."""
+    if torch.is_grad_enabled() and features.requires_grad:
+        return _HeightCompressionFn.apply(features, indices, spatial_shape, batch_size)
+    return height_compression(features, indices, spatial_shape, batch_size)
+
+
 def _cfg_get(cfg, key):
     return cfg[key] if isinstance(cfg, dict) else getattr(cfg, key)
 
@@ -54,7 +80,8 @@ class HeightCompression(nn.Module):
         enc = batch_dict['encoded_spconv_tensor']
         if enc.features.is_cuda and enc.features.dtype in (torch.float32, torch.bfloat16) and \
                 enc.indices.dtype == torch.int32 and len(enc.spatial_shape) == 3:
-            spatial_features = height_compression(enc.features, enc.indices, enc.spatial_shape, enc.batch_size)
+            spatial_features = height_compression_autograd(enc.features, enc.indices, enc.spatial_shape,
+                                                           enc.batch_size)
         else:
             dense = enc.dense()
             n, c, d, h, w = dense.shape

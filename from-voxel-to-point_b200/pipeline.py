@@ -158,7 +158,9 @@ class HotPath(object):
         key = (s["dev_pts"].data_ptr(), s["dev_off"].data_ptr(), s["pcap"], s["batch"], lane)
         engine, voxelizer = self._lane(lane)
         entry = self._graphs.get(key)
-        if entry is not None and entry[2] != (engine.arena_gen, voxelizer.gen, engine._param_key):
+        # the parameter identity is recomputed here, not read back from the engine: a replay never reaches
+        # _prepare_params, so weights updated after the capture would otherwise keep their stale packed copies
+        if entry is not None and entry[2] != (engine.arena_gen, voxelizer.gen, engine.param_key(s["device"])):
             entry = None  # buffers or parameters behind the captured addresses changed: capture again
         if entry is None:
             cur = torch.cuda.current_stream(s["device"])

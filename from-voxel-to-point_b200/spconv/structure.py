@@ -15,6 +15,28 @@ def scatter_nd(indices, updates, shape):
     return dense
 
 
+class _DenseFn(torch.autograd.Function):
+    """dense() through fv2p_dense_ncdhw, differentiable with respect to the features like the reference's
+    scatter_nd path: backward gathers grad[b, :, z, y, x] for every row."""
+
+    @staticmethod
+    def forward(ctx, features, indices, shape, batch_size):
+        ctx.save_for_backward(indices)
+        f = features.detach().contiguous()
+        out = torch.zeros([batch_size, f.shape[1]] + list(shape), dtype=f.dtype, device=f.device)
+        if f.shape[0]:
+            _lib.check(_lib.load().fv2p_dense_ncdhw(_lib.ptr(f), _lib.ptr(indices), f.shape[0], None, f.shape[1],
+                                                    _lib.i32x3(shape), _lib.ptr(out), _lib.stream_ptr(f.device)),
+                       "dense")
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        (indices,) = ctx.saved_tensors
+        ind = indices.long()
+        return grad[ind[:, 0], :, ind[:, 1], ind[:, 2], ind[:, 3]].contiguous(), None, None, None
+
+
 class SparseConvTensor(object):
     """features [N,C], indices [N,ndim+1] int32 (batch first), spatial_shape, batch_size.
 
@@ -53,14 +75,7 @@ class SparseConvTensor(object):
         if channels_first and len(shape) == 3 and f.is_cuda and f.dtype == torch.float32 and \
                 self.indices.dtype == torch.int32:
             _lib.require_device(f)
-            f = f.contiguous()
-            ind = self.indices.contiguous()
-            out = torch.zeros([self.batch_size, f.shape[1]] + shape, dtype=f.dtype, device=f.device)
-            if f.shape[0]:
-                _lib.check(_lib.load().fv2p_dense_ncdhw(_lib.ptr(f), _lib.ptr(ind), f.shape[0], None, f.shape[1],
-                                                        _lib.i32x3(shape), _lib.ptr(out), _lib.stream_ptr(f.device)),
-                           "dense")
-            return out
+            return _DenseFn.apply(f, self.indices.contiguous(), shape, int(self.batch_size))
         output_shape = [self.batch_size] + shape + [f.shape[1]]
         res = scatter_nd(self.indices.long(), f, output_shape)
         if not channels_first:

@@ -66,6 +66,31 @@ class SparseBasicBlock(spconv.SparseModule):
         return out
 
 
+def _detach_outputs(outs):
+    """Copies of the engine's exported tensors (features, indices, rulebook tensors), sharing one indice_dict /
+    nbr_dict like the originals do."""
+    memo = {}
+
+    def cp(t):
+        if t is None or not isinstance(t, torch.Tensor):
+            return t
+        key = (t.data_ptr(), tuple(t.shape), t.dtype)
+        if key not in memo:
+            memo[key] = t.clone()
+        return memo[key]
+
+    indice_dict = nbr_dict = None
+    res = {}
+    for name, sp in outs.items():
+        if indice_dict is None:
+            indice_dict = {k: (cp(v[0]), cp(v[1]), cp(v[2]), cp(v[3]), v[4]) for k, v in sp.indice_dict.items()}
+            nbr_dict = {k: cp(v) for k, v in sp.nbr_dict.items()}
+        t = spconv.SparseConvTensor(cp(sp.features), cp(sp.indices), sp.spatial_shape, sp.batch_size)
+        t.indice_dict, t.nbr_dict = indice_dict, nbr_dict
+        res[name] = t
+    return res
+
+
 class _BackboneBase(nn.Module):
     """Shared forward: engine in eval mode, module graph otherwise."""
 
@@ -101,10 +126,21 @@ class _BackboneBase(nn.Module):
         voxel_features, voxel_coords = batch_dict['voxel_features'], batch_dict['voxel_coords']
         batch_size = batch_dict['batch_size']
         coords = voxel_coords.int()
-        fused = (not self.training) and bool(self._cfg('FUSED', True)) and voxel_features.is_cuda
+        # The fused engine is an inference transform (BatchNorm folded, no autograd graph): it is used in eval mode
+        # when nothing can ask for gradients, i.e. under torch.no_grad() like the reference's eval loop
+        # (tools/eval_utils/eval_utils.py:58) or when neither the input nor any parameter requires grad.  Eval mode
+        # with gradients enabled (frozen-BN fine-tuning) takes the differentiable module path.
+        wants_grad = torch.is_grad_enabled() and (voxel_features.requires_grad or
+                                                  any(p.requires_grad for p in self.parameters()))
+        fused = (not self.training) and bool(self._cfg('FUSED', True)) and voxel_features.is_cuda and not wants_grad
         if fused:
             with torch.no_grad():
                 outs = self.get_engine()(voxel_features.float().contiguous(), coords.contiguous(), batch_size)
+            if not bool(self._cfg('ALIAS_OUTPUTS', False)):
+                # The engine hands out views into its grow-only arena, which the next forward() overwrites; the
+                # reference returns fresh tensors, so the module API copies them out (11 MB for a KITTI batch of 8).
+                # ALIAS_OUTPUTS: True keeps the zero-copy views (HotPath does, it documents their lifetime).
+                outs = _detach_outputs(outs)
         else:
             input_sp_tensor = spconv.SparseConvTensor(features=voxel_features, indices=coords,
                                                       spatial_shape=self.sparse_shape, batch_size=batch_size)

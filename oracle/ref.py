@@ -64,11 +64,14 @@ def ext_get_indice_pairs(indices, batch, in_shape, ksize, stride, pad, dil, subm
 
 
 def ext_backbone_forward(name, params, voxel_features, voxel_coords, batch_size, sparse_shape, last_pad=0,
-                         timers=None):
-    """Eval forward of VoxelBackBone8x / VoxelResBackBone8x through the reference extension (CPU tensors).
+                         timers=None, device=None):
+    """Eval forward of VoxelBackBone8x / VoxelResBackBone8x through the reference extension.
 
-    params: {state_dict key: torch.Tensor (cpu, fp32)}.  Returns the same structure as
-    oracle.backbone_forward but with torch tensors.
+    params: {state_dict key: torch.Tensor (fp32)}.  Returns the same structure as oracle.backbone_forward but
+    with torch tensors.  device=None: CPU tensors, the reference's CPU functors (the parity target).
+    device='cuda': the same call sequence on CUDA tensors, i.e. the reference's own GPU kernels
+    (src/indice_cuda.cu:30-135, src/reordering_cuda.cu:31-140, cuBLAS through torch::mm_out) - used by
+    bench.py's `reference_gpu` block only; its rulebook ordering differs from the CPU path.
     """
     import time
 
@@ -78,6 +81,8 @@ def ext_backbone_forward(name, params, voxel_features, voxel_coords, batch_size,
     ext = load_ext()
     feats = torch.as_tensor(voxel_features, dtype=torch.float32)
     inds = torch.as_tensor(voxel_coords).int().contiguous()
+    if device is not None:
+        feats, inds = feats.to(device), inds.to(device)
     shape = [int(s) for s in sparse_shape]
     books = {}
     t_rb = t_cv = 0.0

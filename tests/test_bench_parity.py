@@ -1,0 +1,286 @@
+"""Parity at BENCHMARK size (-m gpu): the exact batches bench.py times - kitti_b8 and waymo_b4 - through the code paths it
+times (HotPath with CUDA-graph replay, and run_stream with two lanes), compared with the reference itself (oracle/_ref
+driven per frame, tests/refbatch.py; falls back to the C oracle): voxel coordinates, all five outputs' indices and all
+nine rulebooks bit-exact, features within the stated tolerances (fp32 1e-4 relative, north_star; bf16 see BF16_BAR).
+
+Also here: the reference-shaped C-ABI entries exercised exactly as INTEGRATION.md section 2 binds them (the code block
+is extracted from the document and executed), the conv backward against the reference's own
+indice_conv_backward_fp32, and regression tests for the round-1 advisor findings.
+"""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import fv2p_b200
+from fv2p_b200 import spconv, synth
+from conftest import ROOT, load_golden, rel_err
+from oracle import oracle as O
+from oracle import ref as R
+import refbatch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+FP32_TOL = 1e-4
+# bf16 path: bf16 storage + fp32 accumulation, one rounding per layer, 21 layers.  Measured on B200 (round 2):
+# <= 7e-3 on all five outputs of both benchmark batches; the bar leaves 2x for other seeds.
+BF16_BAR = 1.5e-2
+
+import bench  # noqa: E402  (the workload definitions and frame seeds are bench.py's own)
+
+
+def cuda(a, dtype=None):
+    t = torch.as_tensor(np.ascontiguousarray(a)).to(DEV)
+    return t if dtype is None else t.to(dtype)
+
+
+def _setup(workload, precision):
+    wl = bench.WORKLOADS[workload]
+    net, hp, state, cfg = bench.build_model(wl, torch.device(DEV), precision, use_graph=True)
+    frames = bench.make_frames(wl, 0, wl["batch"])
+    return wl, net, hp, state, frames
+
+
+_EXPECT = {}
+
+
+def _expected(workload):
+    if workload not in _EXPECT:
+        wl = bench.WORKLOADS[workload]
+        import fv2p_b200 as pkg
+        cfg = synth.DATASETS[wl["dataset"]]
+        net = getattr(pkg, wl["backbone"])({}, cfg["num_point_features"], np.array(synth.grid_size(cfg)))
+        state = synth.randomize_state(net.state_dict(), seed=0)
+        frames = bench.make_frames(wl, 0, wl["batch"])
+        _EXPECT[workload] = refbatch.expected_batch(wl["dataset"], wl["backbone"], state, frames, wl["split"])
+    return _EXPECT[workload]
+
+
+def _check_batch_dict(bd, exp, tol, rulebooks=True):
+    assert np.array_equal(bd["voxel_coords"].cpu().numpy(), exp["voxel_coords"])
+    assert rel_err(bd["voxel_features"].cpu().numpy(), exp["voxel_features"]) < 1e-6
+    assert np.array_equal(bd["voxel_num_points"].cpu().numpy(), exp["voxel_num_points"])
+    outs = dict(bd["multi_scale_3d_features"], out=bd["encoded_spconv_tensor"])
+    errs = {}
+    for k in refbatch.EXPORTS:
+        assert np.array_equal(outs[k].indices.cpu().numpy(), exp[k][1]), k
+        errs[k] = rel_err(outs[k].features.float().cpu().numpy(), exp[k][0])
+        assert errs[k] < tol, (k, errs[k])
+    if rulebooks:
+        idict = outs["out"].indice_dict
+        assert set(idict) == set(exp["rulebooks"])
+        for key, (outids, pairs, num) in exp["rulebooks"].items():
+            g_out, g_in, g_pairs, g_num, _ = idict[key]
+            assert np.array_equal(g_out.cpu().numpy(), outids), key
+            assert np.array_equal(g_num.cpu().numpy(), num), key
+            assert np.array_equal(g_pairs.cpu().numpy(), pairs), key
+    return errs
+
+
+@pytest.mark.parametrize("workload", ["kitti_b8", "waymo_b4"])
+def test_benchmark_batch_graph_replay_matches_reference_fp32(workload):
+    """HotPath(use_graph=True) on the benchmark batch: first call captures, second replays; both are checked."""
+    wl, net, hp, state, frames = _setup(workload, "fp32")
+    exp = _expected(workload)
+    for _ in range(2):
+        bd, info = hp(frames, device=DEV)
+        errs = _check_batch_dict(bd, exp, FP32_TOL)
+    print("fp32 %s (%s) rel err per output: %s" % (workload, exp["backend"], errs))
+
+
+@pytest.mark.parametrize("workload", ["kitti_b8", "waymo_b4"])
+def test_benchmark_batch_graph_replay_matches_reference_bf16(workload):
+    wl, net, hp, state, frames = _setup(workload, "bf16")
+    exp = _expected(workload)
+    for _ in range(2):
+        bd, info = hp(frames, device=DEV)
+        errs = _check_batch_dict(bd, exp, BF16_BAR)
+    print("bf16 %s rel err per output: %s" % (workload, errs))
+
+
+@pytest.mark.parametrize("workload", ["kitti_b8", "waymo_b4"])
+def test_benchmark_batch_run_stream_matches_reference(workload):
+    """The pipelined e2e path bench.py reports (two lanes, graph replay, double-buffered copies): every yielded
+    stride-8 result equals the reference's, batch after batch (the lanes alternate)."""
+    wl, net, hp, state, frames = _setup(workload, "fp32")
+    exp = _expected(workload)
+    n = 0
+    for res in hp.run_stream((frames for _ in range(4)), DEV):
+        assert np.array_equal(res["encoded_indices"].numpy(), exp["out"][1])
+        assert rel_err(res["encoded_features"].numpy(), exp["out"][0]) < FP32_TOL
+        assert res["counts"] == [exp["voxel_coords"].shape[0]] + [exp[k][1].shape[0] for k in refbatch.EXPORTS[1:]]
+        n += 1
+    assert n == 4
+
+
+# ------------------------------------------------------------------------------------ INTEGRATION.md stub
+def _integration_stub():
+    """Executes the ctypes binding printed in INTEGRATION.md section 2 verbatim (library path made absolute)."""
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = re.search(r"## 2\..*?```python\n(.*?)```", text, re.S).group(1)
+    block = block.replace('"libfv2p_b200.so"', repr(fv2p_b200._lib.LIB_PATH))
+    ns = {}
+    exec(compile(block, "INTEGRATION.md#2", "exec"), ns)
+    return ns
+
+
+GEOMS = {"subm3": (True, 3, 1, 1), "s2p1": (False, 3, 2, 1), "down311": (False, (3, 1, 1), (2, 1, 1), 0)}
+
+
+@pytest.mark.parametrize("geom", sorted(GEOMS))
+def test_integration_md_stub_binds_and_matches_the_reference(geom):
+    """fv2p_get_indice_pairs_3d and fv2p_indice_conv_fp32 called the way a maintainer would bind them."""
+    ns = _integration_stub()
+    subm, ks, st, pd = GEOMS[geom]
+    tri = lambda v: [int(x) for x in v] if isinstance(v, (tuple, list)) else [int(v)] * 3
+    shape = [9, 40, 36]
+    ind = synth.random_voxels(shape, 1500, 2, seed=11)
+    if subm:
+        ref = O.rulebook_subm(ind, 2, shape, ks, 1)
+        out_shape = shape
+    else:
+        ref = O.rulebook_conv(ind, 2, shape, ks, st, pd, 1)
+        out_shape = ref[3]
+    with torch.cuda.device(0):
+        outids, pairs, num = ns["get_indice_pairs_3d"](cuda(ind), 2, out_shape, shape, tri(ks), tri(st), tri(pd),
+                                                       [1, 1, 1], [0, 0, 0], int(subm), 0)
+        assert np.array_equal(outids.cpu().numpy(), ref[0])
+        assert np.array_equal(pairs.cpu().numpy(), ref[1]) and np.array_equal(num.cpu().numpy(), ref[2])
+        rng = np.random.default_rng(5)
+        for cin, cout in ((16, 32), (5, 16), (64, 64)):
+            feats = rng.standard_normal((ind.shape[0], cin)).astype(np.float32)
+            w = (rng.standard_normal(tuple(tri(ks)) + (cin, cout)) * 0.1).astype(np.float32)
+            got = ns["indice_conv_fp32"](cuda(feats), cuda(w), pairs, num, outids.shape[0], 0, int(subm))
+            exp = O.indice_conv(feats, w, ref[1], ref[2], ref[0].shape[0], False, subm)
+            assert rel_err(got.cpu().numpy(), exp) < FP32_TOL, (cin, cout)
+    # error mapping of the stub: an invalid argument raises ValueError like TV_ASSERT_INVALID_ARG
+    with pytest.raises(ValueError):
+        with torch.cuda.device(0):
+            ns["get_indice_pairs_3d"](cuda(ind), 2, out_shape, shape, [7, 7, 7], tri(st), tri(pd), [1, 1, 1],
+                                      [0, 0, 0], int(subm), 0)
+
+
+# ------------------------------------------------------------------------------------ backward vs the reference
+@pytest.mark.skipif(not R.have_ext(), reason="oracle/_ref (the reference extension) is not built")
+@pytest.mark.parametrize("geom", ["subm3", "s2p1"])
+@pytest.mark.parametrize("ch", [(16, 32), (64, 64), (5, 16)])
+def test_conv_backward_matches_reference_indice_conv_backward(geom, ch):
+    """ops.indice_conv_backward (spconv_ops.h:365-457) against the reference's own indice_conv_backward_fp32 run on
+    the CPU through oracle/_ref: grad_input and grad_filters."""
+    ext = R.load_ext()
+    subm, ks, st, pd = GEOMS[geom]
+    shape = [9, 40, 36]
+    ind = synth.random_voxels(shape, 1200, 2, seed=13)
+    ref = O.rulebook_subm(ind, 2, shape, ks, 1) if subm else O.rulebook_conv(ind, 2, shape, ks, st, pd, 1)
+    outids, pairs, num = ref[0], ref[1], ref[2]
+    rng = np.random.default_rng(7)
+    cin, cout = ch
+    feats = rng.standard_normal((ind.shape[0], cin)).astype(np.float32)
+    w = (rng.standard_normal((3, 3, 3, cin, cout)) * 0.1).astype(np.float32)
+    go = rng.standard_normal((outids.shape[0], cout)).astype(np.float32)
+    e_in, e_w = ext.indice_conv_backward_fp32(torch.from_numpy(feats), torch.from_numpy(w), torch.from_numpy(go),
+                                              torch.from_numpy(pairs), torch.from_numpy(num), 0, int(subm))
+    g_in, g_w = spconv.ops.indice_conv_backward(cuda(feats), cuda(w), cuda(go), cuda(pairs), cuda(num), False, subm)
+    assert rel_err(g_in.cpu().numpy(), e_in.numpy()) < FP32_TOL
+    assert rel_err(g_w.cpu().numpy(), e_w.numpy()) < FP32_TOL
+
+
+# ------------------------------------------------------------------------------------ advisor regressions
+def test_graph_replay_sees_weights_updated_after_capture():
+    """after load_state_dict / an in-place weight update the captured graph must not keep replaying the
+    old packed tensor-core weights and folded BatchNorm."""
+    cfg = synth.DATASETS["kitti"]
+    gs = synth.grid_size(cfg)
+    frames = [synth.lidar_frame("kitti", seed=90 + i, az_steps=80) for i in range(2)]
+
+    def fresh(seed):
+        net = fv2p_b200.VoxelResBackBone8x({}, 4, np.array(gs)).eval()
+        state = synth.randomize_state(net.state_dict(), seed=seed)
+        net.load_state_dict({k: torch.from_numpy(v) for k, v in state.items()}, strict=False)
+        return net.to(DEV), state
+
+    net, _ = fresh(3)
+    hp = fv2p_b200.HotPath(net, cfg["voxel_size"], cfg["point_cloud_range"], 5, 16000, use_graph=True)
+    a = hp(frames, device=DEV)[0]["encoded_spconv_tensor"].features.clone()
+    a2 = hp(frames, device=DEV)[0]["encoded_spconv_tensor"].features.clone()  # replay
+    assert torch.equal(a, a2)
+    _, state2 = fresh(4)
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in state2.items()}, strict=False)  # in place, after capture
+    b = hp(frames, device=DEV)[0]["encoded_spconv_tensor"].features.clone()
+    net2, _ = fresh(4)
+    ref = fv2p_b200.HotPath(net2, cfg["voxel_size"], cfg["point_cloud_range"], 5, 16000, use_graph=False)
+    c = ref(frames, device=DEV)[0]["encoded_spconv_tensor"].features.clone()
+    assert not torch.equal(a, b)
+    assert torch.equal(b, c)
+    with torch.no_grad():  # a single in-place parameter edit is seen as well
+        net.conv_out[0].weight.mul_(0.5)
+        net2.conv_out[0].weight.mul_(0.5)
+    assert torch.equal(hp(frames, device=DEV)[0]["encoded_spconv_tensor"].features,
+                       ref(frames, device=DEV)[0]["encoded_spconv_tensor"].features)
+
+
+def test_dense_and_height_compression_pass_gradients():
+    """SparseConvTensor.dense() and HeightCompression are differentiable like the reference's scatter_nd,
+    so a loss on the BEV map reaches the sparse features."""
+    shape = [2, 12, 10]
+    ind = synth.random_voxels(shape, 90, 2, seed=5)
+    feats = torch.randn(ind.shape[0], 8, device=DEV, requires_grad=True)
+    x = spconv.SparseConvTensor(feats, cuda(ind), shape, 2)
+    wgt = torch.randn(2, 8, 2, 12, 10, device=DEV)
+    (x.dense() * wgt).sum().backward()
+    li = torch.as_tensor(ind).long().to(DEV)
+    exp = wgt[li[:, 0], :, li[:, 1], li[:, 2], li[:, 3]]
+    assert torch.allclose(feats.grad, exp)
+    feats.grad = None
+    hc = fv2p_b200.HeightCompression({"NUM_BEV_FEATURES": 16})
+    bd = hc({"encoded_spconv_tensor": x, "encoded_spconv_tensor_stride": 8})
+    (bd["spatial_features"] * wgt.view(2, 16, 12, 10)).sum().backward()
+    assert torch.allclose(feats.grad, exp)
+
+
+def test_module_outputs_survive_the_next_forward():
+    """tensors returned by backbone.forward() are copies, not views of the engine arena."""
+    g = load_golden("backbone_kitti_VoxelResBackBone8x")
+    net = fv2p_b200.VoxelResBackBone8x({}, 4, np.array(g["grid_size"])).eval()
+    state = synth.randomize_state(net.state_dict(), seed=int(g["seed"]))
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in state.items()}, strict=False)
+    net = net.to(DEV)
+    with torch.no_grad():
+        bd = net({"voxel_features": cuda(g["voxel_features"]), "voxel_coords": cuda(g["voxel_coords"]),
+                  "batch_size": int(g["batch_size"])})
+        keep = bd["encoded_spconv_tensor"]
+        snap = keep.features.clone()
+        half = g["voxel_features"].shape[0] // 2
+        net({"voxel_features": cuda(g["voxel_features"][:half] * 3.0), "voxel_coords": cuda(g["voxel_coords"][:half]),
+             "batch_size": int(g["batch_size"])})
+    assert torch.equal(keep.features, snap)
+    assert rel_err(keep.features.cpu().numpy(), g["out_features"]) < FP32_TOL
+    # eval mode with autograd on (frozen-BN fine-tuning) takes the differentiable module path
+    vf = cuda(g["voxel_features"]).requires_grad_(True)
+    bd = net({"voxel_features": vf, "voxel_coords": cuda(g["voxel_coords"]), "batch_size": int(g["batch_size"])})
+    bd["encoded_spconv_tensor"].features.sum().backward()
+    assert vf.grad is not None and float(vf.grad.abs().sum()) > 0
+
+
+# ------------------------------------------------------------------------------------ a3: the DataProcessor hook
+def test_data_processor_hook_matches_reference_voxelizer_fixture():
+    """DataProcessor.transform_points_to_voxels (data_processor.py:43-81): config keys in, three dict keys out,
+    use_lead_xyz handling - against the reference numba voxelizer's committed outputs."""
+    g = load_golden("voxelize")
+    from fv2p_b200.data_processor import DataProcessor
+    case = [k[:-len("_points")] for k in g.files if k.endswith("_points")][0]
+    cfg = dict(NAME="transform_points_to_voxels", VOXEL_SIZE=g[case + "_voxel_size"].tolist(),
+               MAX_POINTS_PER_VOXEL=int(g[case + "_max_points"]),
+               MAX_NUMBER_OF_VOXELS={"train": int(g[case + "_max_voxels"]), "test": int(g[case + "_max_voxels"])})
+    dp = DataProcessor([cfg], np.array(g[case + "_range"], np.float32), training=False, device=DEV)
+    assert dp.grid_size.tolist() == O.grid_size(cfg["VOXEL_SIZE"], g[case + "_range"]).tolist()
+    dd = dp.forward({"points": g[case + "_points"], "use_lead_xyz": True})
+    assert np.array_equal(dd["voxel_coords"], g[case + "_coors"])
+    assert np.array_equal(dd["voxel_num_points"], g[case + "_num"])
+    assert np.array_equal(dd["voxels"], g[case + "_voxels"])
+    dd = dp.forward({"points": g[case + "_points"], "use_lead_xyz": False})
+    assert np.array_equal(dd["voxels"], g[case + "_voxels"][..., 3:])
+    with pytest.raises(NotImplementedError):
+        DataProcessor([dict(NAME="shuffle_points")], np.array(g[case + "_range"]), training=False)

@@ -104,3 +104,27 @@ def test_height_compression_matches_reference_module():
     got = O.height_compression(g["features"], g["indices"], g["spatial_shape"], int(g["batch_size"]))
     assert got.shape == g["spatial_features"].shape
     assert np.array_equal(got, g["spatial_features"])
+
+
+def test_batch_expectation_stitched_from_frames_equals_a_batched_reference_run():
+    """tests/refbatch.py assembles a batch expectation from per-frame reference runs; here the same batch goes
+    through the oracle in ONE call (batch 3, one empty-ish small frame) and both must agree exactly on every
+    rulebook and row, which is what licenses the per-frame expectation at benchmark size."""
+    import fv2p_b200
+    from fv2p_b200 import synth
+    import refbatch
+    cfg = synth.DATASETS["kitti"]
+    gs = synth.grid_size(cfg)
+    shape = [int(gs[2]) + 1, int(gs[1]), int(gs[0])]
+    frames = [synth.lidar_frame("kitti", seed=300 + i, az_steps=24 + 10 * i) for i in range(3)]
+    net = fv2p_b200.VoxelResBackBone8x({}, 4, np.array(gs))
+    state = synth.randomize_state(net.state_dict(), seed=2)
+    exp = refbatch.expected_batch("kitti", "VoxelResBackBone8x", state, frames, backend="oracle")
+    one = O.backbone_forward("VoxelResBackBone8x", state, exp["voxel_features"], exp["voxel_coords"], 3, shape)
+    for k in refbatch.EXPORTS:
+        assert np.array_equal(exp[k][1], one[k][1]), k
+        assert rel_err(exp[k][0], one[k][0]) < 1e-6, k
+    assert set(exp["rulebooks"]) == set(one["rulebooks"])
+    for key, (outids, pairs, num) in one["rulebooks"].items():
+        e = exp["rulebooks"][key]
+        assert np.array_equal(e[0], outids) and np.array_equal(e[2], num) and np.array_equal(e[1], pairs), key
