@@ -15,6 +15,9 @@ LIB_PATH = os.path.join(_HERE, "lib", "libfv2p_b200.so")
 
 MODE_F32, MODE_BF16_TC, MODE_TF32X3_TC, MODE_BF16_SIMT, MODE_F32_IN_BF16_OUT = 0, 1, 2, 3, 4
 MAX_KVOL = 32
+ABI_VERSION = 2
+FLAG_PREFILLED = 1
+PREFILL_TABLE, PREFILL_NBR_ALL, PREFILL_NBR_MIRROR, PREFILL_CONV_WS, PREFILL_GROUP_WS = 1, 2, 3, 4, 5
 STATUS_OUT_OVERFLOW, STATUS_VOXEL_OVERFLOW = 1, 2
 
 _c_i64, _c_int, _c_sz, _c_vp = ctypes.c_int64, ctypes.c_int, ctypes.c_size_t, ctypes.c_void_p
@@ -30,6 +33,19 @@ PROTOTYPES = {
     "fv2p_voxel_generate": (_c_int, [_c_vp, _c_i64, _c_int, _c_vp, _c_vp, _c_int, _c_int, _c_vp, _c_vp, _c_vp,
                                      _c_vp, _c_i64, _c_vp, _c_vp, _c_sz, _c_vp]),
     "fv2p_mean_vfe": (_c_int, [_c_vp, _c_vp, _c_i64, _c_int, _c_int, _c_vp, _c_vp]),
+    "fv2p_geometry_prefill": (_c_int, [_c_vp, _c_int, _c_vp]),
+    "fv2p_table_bytes": (_c_sz, [_c_i64]),
+    "fv2p_table_build": (_c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_int, _c_vp]),
+    "fv2p_subm_neighbours": (_c_int, [_c_vp, _c_i64, _c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_i64,
+                                      _c_int, _c_vp]),
+    "fv2p_conv_neighbours_workspace_bytes": (_c_sz, [_c_i64, _c_int]),
+    "fv2p_conv_neighbours": (_c_int, [_c_vp, _c_i64, _c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64,
+                                      _c_vp, _c_vp, _c_i64, _c_vp, _c_i64, _c_vp, _c_vp, _c_sz, _c_int, _c_vp]),
+    "fv2p_pairs_workspace_bytes": (_c_sz, [_c_i64, _c_int]),
+    "fv2p_subm_pairs": (_c_int, [_c_vp, _c_i64, _c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_i64, _c_vp,
+                                 _c_i64, _c_vp, _c_vp, _c_sz, _c_vp]),
+    "fv2p_conv_pairs": (_c_int, [_c_vp, _c_i64, _c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp,
+                                 _c_i64, _c_vp, _c_vp, _c_sz, _c_vp]),
     "fv2p_rulebook_workspace_bytes": (_c_sz, [_c_i64, _c_i64, _c_int]),
     "fv2p_rulebook_subm": (_c_int, [_c_vp, _c_i64, _c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp,
                                     _c_i64, _c_vp, _c_sz, _c_vp, _c_vp]),
@@ -41,6 +57,9 @@ PROTOTYPES = {
     "fv2p_pairs_to_nbr": (_c_int, [_c_vp, _c_vp, _c_int, _c_i64, _c_int, _c_i64, _c_vp, _c_i64, _c_vp]),
     "fv2p_conv_fwd": (_c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_int, _c_i64, _c_vp, _c_int,
                                _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_vp, _c_vp]),
+    "fv2p_group_rows_workspace_bytes": (_c_sz, [_c_i64]),
+    "fv2p_group_rows": (_c_int, [_c_vp, _c_i64, _c_int, _c_int, _c_i64, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp, _c_sz,
+                                 _c_int, _c_vp]),
     "fv2p_sort_rows_workspace_bytes": (_c_sz, [_c_i64]),
     "fv2p_sort_rows_by_mask": (_c_int, [_c_vp, _c_i64, _c_int, _c_i64, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp, _c_sz,
                                         _c_vp]),
@@ -76,7 +95,7 @@ def load():
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
-        if lib.fv2p_abi_version() != 1:
+        if lib.fv2p_abi_version() != ABI_VERSION:
             raise RuntimeError("libfv2p_b200.so ABI version mismatch")
         _lib = lib
     return _lib
@@ -108,6 +127,22 @@ def require_device(t):
             check(load().fv2p_device_check(None, None, None), "device check")
         _checked_devices.add(idx)
     return idx
+
+
+class PrefillItem(ctypes.Structure):
+    """fv2p_prefill_item (include/fv2p_b200.h)."""
+    _fields_ = [("kind", ctypes.c_int32), ("reserved", ctypes.c_int32), ("ptr", ctypes.c_void_p),
+                ("a", ctypes.c_int64), ("b", ctypes.c_int64)]
+
+
+def prefill_items(items):
+    """[(kind, tensor_or_ptr, a, b), ...] -> (ctypes array, count)."""
+    arr = (PrefillItem * max(len(items), 1))()
+    for i, (kind, t, a, b) in enumerate(items):
+        arr[i].kind, arr[i].reserved = int(kind), 0
+        arr[i].ptr = t.data_ptr() if isinstance(t, torch.Tensor) else int(t)
+        arr[i].a, arr[i].b = int(a), int(b)
+    return arr, len(items)
 
 
 def ptr(t):

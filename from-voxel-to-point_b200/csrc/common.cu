@@ -57,6 +57,24 @@ cudaStream_t fork_stream(cudaStream_t from, void *to_) {
   return to;
 }
 
+// One launch clears every range of the job (grid-stride over the concatenation of the ranges).
+__global__ void __launch_bounds__(kThreads) fill_ranges_kernel(const FillJob job) {
+  for (int r = 0; r < job.count; ++r) {
+    uint4 *dst = static_cast<uint4 *>(job.r[r].ptr);
+    const unsigned long long n = job.r[r].n16;
+    const uint4 pat = job.r[r].pattern;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x)
+      dst[i] = pat;
+  }
+}
+
+int launch_fill(const FillJob &job, cudaStream_t stream) {
+  if (job.count == 0) return 0;
+  fill_ranges_kernel<<<persistent_grid(8), kThreads, 0, stream>>>(job);
+  return cuda_status(cudaGetLastError(), "fill");
+}
+
 __global__ void set_scalar_kernel(int *dst, int value) { *dst = value; }
 
 void launch_set_scalar(int *dst, int value, cudaStream_t stream) {

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <limits.h>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -118,6 +119,118 @@ __device__ __forceinline__ uint32_t table_find(const unsigned long long *__restr
 __device__ __forceinline__ unsigned long long voxel_key(int b, int z, int y, int x, int D, int H,
                                                         int W) {
   return (((unsigned long long)b * D + z) * H + y) * (unsigned long long)W + x;
+}
+
+// ------------------------------------------------------------------------- coordinate tables (v2)
+// One 16-byte slot per key: the probe of a present key costs ONE 16-byte load (key and value arrive together; the
+// first generation kept keys and values in two arrays = two dependent L2 round trips per hit).  `val` holds, in
+// order: kValEmpty after the clear; for the output table of a strided rulebook the smallest bid (>= 0) while the
+// candidates are being inserted; finally ~row (< 0) of the voxel stored under the key.  Tables are sized by the
+// caller-stated row CAPACITY (host-known), so every kernel of a step agrees on the mask and the clear can run
+// before the live row count exists.
+struct __align__(16) Slot {
+  unsigned long long key;
+  int val;
+  int aux;
+};
+constexpr int kValEmpty = INT_MAX;
+
+__host__ __device__ inline uint32_t table_slots_cap(int64_t row_cap) { return table_slots_for(row_cap); }
+
+// Returns the slot index of `key`, inserting it if absent; 0xFFFFFFFF when the table is full.
+__device__ __forceinline__ uint32_t slot_insert(Slot *t, uint32_t mask, unsigned long long key) {
+  uint32_t s = mix64(key) & mask;
+  for (uint32_t probes = 0; probes <= mask; ++probes) {
+    unsigned long long seen = *reinterpret_cast<volatile unsigned long long *>(&t[s].key);
+    if (seen == key) return s;
+    if (seen == kEmptyKey) {
+      unsigned long long prev = atomicCAS(&t[s].key, kEmptyKey, key);
+      if (prev == kEmptyKey || prev == key) return s;
+    }
+    s = (s + 1) & mask;
+  }
+  return 0xFFFFFFFFu;
+}
+
+// Value stored under `key` (read-only table, one 16-byte load per probe), or kValEmpty when the key is absent.
+__device__ __forceinline__ int slot_lookup(const Slot *__restrict__ t, uint32_t mask, unsigned long long key) {
+  uint32_t s = mix64(key) & mask;
+  while (true) {
+    const uint4 q = __ldg(reinterpret_cast<const uint4 *>(&t[s]));
+    const unsigned long long seen = ((unsigned long long)q.y << 32) | q.x;
+    if (seen == key) return (int)q.z;
+    if (seen == kEmptyKey) return kValEmpty;
+    s = (s + 1) & mask;
+  }
+}
+
+// ------------------------------------------------------------------------- single-pass ordered scan
+// Decoupled look-back over per-chunk totals (Merrill & Garland): chunk c publishes its total, then walks back over
+// its predecessors' words until it meets one that already carries an inclusive prefix.  One 64-bit word per chunk:
+// bits 62-63 = state (0 not ready, 1 total only, 2 inclusive prefix), low 32 bits = value; the words must be zero
+// when the kernel starts.  Chunks are handed out through an atomic ticket, so every predecessor of a chunk has
+// already been taken by a CTA that never waits on a later chunk: forward progress does not depend on the whole grid
+// being resident (the geometry kernels share the SMs with persistent conv kernels).  Call with the whole CTA;
+// returns the exclusive prefix of chunk `c` to every thread.  `smem_word` = one int of shared memory.
+__device__ __forceinline__ int lookback_exclusive(unsigned long long *state, int c, int total, int *smem_word) {
+  constexpr unsigned long long kAgg = 1ull << 62, kPre = 2ull << 62;
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    volatile unsigned long long *vs = state;
+    int exclusive = 0;
+    if (c == 0) {
+      if (lane == 0) vs[0] = kPre | (unsigned int)total;
+    } else {
+      if (lane == 0) vs[c] = kAgg | (unsigned int)total;
+      int idx = c - 1;
+      while (true) {
+        const int mine = idx - lane;
+        unsigned long long w;
+        do {
+          w = mine >= 0 ? vs[mine] : kPre;  // the virtual chunk before chunk 0 has prefix 0
+        } while (__any_sync(0xFFFFFFFFu, (w >> 62) == 0));
+        const unsigned has_pre = __ballot_sync(0xFFFFFFFFu, (w >> 62) == 2);
+        const int first = has_pre ? __ffs(has_pre) - 1 : 31;
+        int v = lane <= first ? (int)(unsigned int)(w & 0xFFFFFFFFu) : 0;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
+        exclusive += v;
+        if (has_pre) break;
+        idx -= 32;
+      }
+      if (lane == 0) vs[c] = kPre | (unsigned int)(exclusive + total);
+    }
+    if (lane == 0) *smem_word = exclusive;
+  }
+  __syncthreads();
+  const int r = *smem_word;
+  __syncthreads();
+  return r;
+}
+
+// Ranges cleared by ONE launch at the start of a geometry pass (tables, scan states, -1 fills).
+struct FillRange {
+  void *ptr;
+  unsigned long long n16;  // 16-byte units
+  uint4 pattern;
+};
+constexpr int kMaxFillRanges = 40;
+struct FillJob {
+  int count;
+  FillRange r[kMaxFillRanges];
+};
+int launch_fill(const FillJob &job, cudaStream_t stream);
+// region of the row-grouping workspace (sort.cu) that must be zero when fv2p_group_rows starts
+void group_rows_zero_region(int64_t n_cap, size_t *off, size_t *bytes);
+inline void add_fill(FillJob &job, void *ptr, size_t bytes, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  if (!ptr || bytes == 0 || job.count >= kMaxFillRanges) return;
+  FillRange &r = job.r[job.count++];
+  r.ptr = ptr;
+  r.n16 = (bytes + 15) / 16;
+  r.pattern = make_uint4(a, b, c, d);
+}
+inline void add_fill_table(FillJob &job, void *table, int64_t row_cap) {
+  add_fill(job, table, (size_t)table_slots_cap(row_cap) * sizeof(Slot), 0xFFFFFFFFu, 0xFFFFFFFFu, (uint32_t)kValEmpty, 0u);
 }
 
 // ------------------------------------------------------------------------------ block-level scan

@@ -1,163 +1,176 @@
-// Row ordering for the tensor-core conv: sort output rows by their neighbour mask.
+// Row grouping for the tensor-core conv: output rows with similar neighbour masks share a tile.
 //
 // The fused conv processes 128 output rows per tile and one kernel offset per pipeline stage; an offset is skipped
 // only if NO row of the tile has that neighbour.  In point-cloud geometry a row has 4-13 of the 27 neighbours, so
 // tiles cut from the rulebook's native row order need almost all 27 stages and 60-75 % of the gathered rows are
-// zero fill.  Grouping rows with equal / similar masks (the mask-sort of spconv v2's implicit GEMM) roughly halves
-// the stages per tile (KITTI: 17.8->7.7, 25.9->12.9, 26.9->14.8, 26.9->15.7 at strides 1/2/4/8) and doubles the
-// density of the rest.  The reference has no counterpart: its gather-GEMM-scatter (spconv_ops.h:308-357) works on
-// compacted per-offset pair lists instead.
+// zero fill.  The reference has no counterpart: its gather-GEMM-scatter (spconv_ops.h:308-357) works on compacted
+// per-offset pair lists instead.
 //
-// Results do not change: every output row still accumulates its offsets in ascending k, only the assignment of
-// rows to tiles moves.  The order is a stable LSD radix sort (9-bit digits, ascending mask, ties by row), hence
-// deterministic.  Outputs: perm[t] = output row processed at sorted position t, and the neighbour map permuted the
-// same way (nbr_sorted[k][t] = nbr[k][perm[t]]) so the conv reads it coalesced.
+// Round 1 sorted the rows by their full 27-bit mask (stable LSD radix sort, 3 passes x 3 launches + 4 more).  Round
+// 2 groups them by a 12-bit DIGEST of the mask in ONE counting pass (2 launches):
+//
+//     digest = [ which x-offsets occur anywhere | which (z,y) lines of the kernel have any neighbour ]
+//
+// (kx + kz*ky bits: 3 + 9 for 3x3x3, 1 + 3 for (3,1,1)).  Rows of a tile then agree on the lines they touch, which
+// is what decides the tile's active offsets; on the synthetic KITTI / Waymo frames this needs FEWER stages per tile
+// than the exact sort (e.g. 9.4 vs 10.7, 6.8 vs 8.2, 12.2 vs 15.2, 10.6 vs 14.7 at the first four rulebooks of a
+// KITTI frame; unsorted: 18.8 / 23.1 / 25.6 / 26.4), because the exact sort splits rows that differ only in
+// low-order bits across distant tiles.
+//
+// Results do not change: every output row still accumulates its offsets in ascending k, only the assignment of rows
+// to tiles moves - so the position of a row INSIDE its group may come from an atomic cursor (no ordered scan, no
+// stability needed).  Outputs: perm[t] = output row processed at position t, the neighbour map permuted the same way
+// (nbr_sorted[k][t] = nbr[k][perm[t]]), and the tile list (tile, OR of its rows' masks) by descending number of
+// active offsets - the conv's longest-processing-time-first schedule.
 #include "common.cuh"
 
 namespace fv2p {
 namespace {
 
-constexpr int kDigitBits = 9;
-constexpr int kBins = 1 << kDigitBits;
+constexpr int kDigestBits = 12;
+constexpr int kBins = 1 << kDigestBits;
+constexpr int kConvTile = 128;
 
 __device__ __forceinline__ int live_n(const int *n_dev, int64_t n_cap) {
   int n = n_dev ? *n_dev : (int)n_cap;
   return n < 0 ? 0 : (n > n_cap ? (int)n_cap : n);
 }
 
+// kx = extent of the fastest kernel axis, lines = kvol / kx.  kvol <= 12: the mask itself.
+__device__ __forceinline__ uint32_t mask_digest(uint32_t m, int kvol, int kx, int lines) {
+  if (kvol <= kDigestBits) return m;
+  uint32_t line_bits = 0, x_bits = 0;
+  const uint32_t xm = (1u << kx) - 1u;
+  for (int l = 0; l < lines; ++l) {
+    const uint32_t seg = (m >> (l * kx)) & xm;
+    x_bits |= seg;
+    line_bits |= (seg != 0u ? 1u : 0u) << l;
+  }
+  uint32_t d = (x_bits << lines) | line_bits;
+  if (kx + lines > kDigestBits) d = (d ^ (d >> kDigestBits)) & (kBins - 1);  // exotic kernels: fold
+  return d;
+}
+
+struct GroupWs {
+  uint32_t *masks;
+  uint16_t *digests;
+  int *bin_base;             // [kBins] exclusive scan of the bins (written by the last CTA of the histogram)
+  int *bins, *cursor;        // [kBins] each, zero on entry
+  uint32_t *tile_masks;      // [tiles], zero on entry
+  int *done;                 // [4], zero on entry: CTAs finished per kernel
+  size_t zero_off, zero_bytes, bytes;
+};
+
+GroupWs carve(void *ws, int64_t n_cap) {
+  GroupWs w;
+  Carver c(ws);
+  const size_t n = (size_t)(n_cap > 0 ? n_cap : 1);
+  w.masks = c.take<uint32_t>(n);
+  w.digests = c.take<uint16_t>(n);
+  w.bin_base = c.take<int>(kBins);
+  w.bins = c.take<int>(kBins);
+  w.zero_off = (size_t)(reinterpret_cast<char *>(w.bins) - static_cast<char *>(ws));
+  w.cursor = c.take<int>(kBins);
+  w.tile_masks = c.take<uint32_t>(n / kConvTile + 2);
+  w.done = c.take<int>(64);
+  w.zero_bytes = c.used - w.zero_off;
+  w.bytes = c.used + 256;
+  return w;
+}
+
+// masks, digests and the digest histogram; the last CTA to finish turns the bins into their exclusive scan.
 __global__ void __launch_bounds__(kThreads)
-nbr_mask_kernel(const int *__restrict__ nbr, int64_t nbr_stride, int kvol, const int *n_dev, int64_t n_cap,
-                uint32_t *keys, int *vals) {
+group_hist_kernel(const int *__restrict__ nbr, int64_t nbr_stride, int kvol, int kx, int lines, const int *n_dev,
+                  int64_t n_cap, uint32_t *masks, uint16_t *digests, int *bins, int *bin_base, int *done) {
+  __shared__ int hist[kBins];
+  __shared__ int scan_smem[kThreads / 32 + 1];
+  __shared__ int s_last;
   const int n = live_n(n_dev, n_cap);
+  for (int b = threadIdx.x; b < kBins; b += kThreads) hist[b] = 0;
+  __syncthreads();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     uint32_t m = 0;
     for (int k = 0; k < kvol; ++k) m |= (__ldg(&nbr[(size_t)k * nbr_stride + i]) >= 0 ? 1u : 0u) << k;
-    keys[i] = m;
-    vals[i] = i;
-  }
-}
-
-// counts[bin][chunk] = items of the chunk whose digit is `bin`
-__global__ void __launch_bounds__(kThreads)
-sort_hist_kernel(const uint32_t *__restrict__ keys, const int *n_dev, int64_t n_cap, int shift, int *counts,
-                 int n_chunks) {
-  __shared__ int hist[kBins];
-  const int n = live_n(n_dev, n_cap);
-  for (int c = blockIdx.x; c < live_chunks(n); c += gridDim.x) {
-    for (int b = threadIdx.x; b < kBins; b += kThreads) hist[b] = 0;
-    __syncthreads();
-    for (int p = 0; p < kItemsPerThread; ++p) {
-      const int i = c * kChunk + p * kThreads + threadIdx.x;
-      if (i < n) atomicAdd(&hist[(keys[i] >> shift) & (kBins - 1)], 1);
-    }
-    __syncthreads();
-    for (int b = threadIdx.x; b < kBins; b += kThreads) counts[(size_t)b * n_chunks + c] = hist[b];
-    __syncthreads();
-  }
-}
-
-// Stable scatter: destination = (items in smaller bins) + (items of this bin in earlier chunks) + (earlier items of
-// this bin inside the chunk).  `chunk_prefix` holds the per-bin exclusive scan over chunks, `bin_totals` the per-bin
-// totals (both from launch_scan_chunk_counts).  Inside a chunk the 32-item slices ("virtual warps", in row order)
-// publish their per-bin counts as bytes; an item's rank is the sum over earlier slices plus its position among the
-// equal-digit lanes of its own slice (__match_any_sync), so a chunk costs two block barriers.
-__global__ void __launch_bounds__(kThreads)
-sort_scatter_kernel(const uint32_t *__restrict__ keys_in, const int *__restrict__ vals_in, const int *n_dev,
-                    int64_t n_cap, int shift, const int *__restrict__ chunk_prefix,
-                    const int *__restrict__ bin_totals, int n_chunks, uint32_t *keys_out, int *vals_out) {
-  constexpr int kSlices = kChunk / 32;
-  __shared__ int bin_base[kBins];
-  __shared__ __align__(16) uint8_t slice_cnt[kSlices][kBins];
-  __shared__ int scan_smem[kThreads / 32 + 1];
-  const int n = live_n(n_dev, n_cap);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  {  // exclusive scan of the 512 bin totals (two per thread)
-    const int a = bin_totals[2 * threadIdx.x], b = bin_totals[2 * threadIdx.x + 1];
-    int total;
-    const int ex = block_exclusive_scan(a + b, scan_smem, total);
-    bin_base[2 * threadIdx.x] = ex;
-    bin_base[2 * threadIdx.x + 1] = ex + a;
+    const uint32_t d = mask_digest(m, kvol, kx, lines);
+    masks[i] = m;
+    digests[i] = (uint16_t)d;
+    atomicAdd(&hist[d], 1);
   }
   __syncthreads();
-  for (int c = blockIdx.x; c < live_chunks(n); c += gridDim.x) {
-    uint32_t *zero = reinterpret_cast<uint32_t *>(&slice_cnt[0][0]);
-    for (int e = threadIdx.x; e < kSlices * kBins / 4; e += kThreads) zero[e] = 0u;
-    __syncthreads();
-    uint32_t key[kItemsPerThread];
-    int val[kItemsPerThread], dig[kItemsPerThread], rank[kItemsPerThread];
+  for (int b = threadIdx.x; b < kBins; b += kThreads)
+    if (hist[b]) atomicAdd(&bins[b], hist[b]);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(&done[0], 1) == (int)gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  constexpr int kPer = kBins / kThreads;  // consecutive bins per thread
+  int local[kPer];
+  int sum = 0;
 #pragma unroll
-    for (int p = 0; p < kItemsPerThread; ++p) {
-      const int i = c * kChunk + p * kThreads + threadIdx.x;
-      const bool live = i < n;
-      key[p] = live ? keys_in[i] : 0u;
-      val[p] = live ? vals_in[i] : 0;
-      dig[p] = live ? (int)((key[p] >> shift) & (kBins - 1)) : -1;
-      const unsigned peers = __match_any_sync(0xFFFFFFFFu, live ? dig[p] : kBins + lane);
-      rank[p] = __popc(peers & ((1u << lane) - 1u));
-      if (live && lane == __ffs(peers) - 1) slice_cnt[p * (kThreads / 32) + warp][dig[p]] = (uint8_t)__popc(peers);
-    }
-    __syncthreads();
+  for (int q = 0; q < kPer; ++q) {
+    local[q] = *reinterpret_cast<volatile int *>(&bins[threadIdx.x * kPer + q]);
+    sum += local[q];
+  }
+  int total;
+  int run = block_exclusive_scan(sum, scan_smem, total);
 #pragma unroll
-    for (int p = 0; p < kItemsPerThread; ++p) {
-      if (dig[p] < 0) continue;
-      const int slice = p * (kThreads / 32) + warp;
-      int before = 0;
-      for (int q = 0; q < slice; ++q) before += slice_cnt[q][dig[p]];
-      const int dst = bin_base[dig[p]] + chunk_prefix[(size_t)dig[p] * n_chunks + c] + before + rank[p];
-      keys_out[dst] = key[p];
-      vals_out[dst] = val[p];
-    }
-    __syncthreads();
+  for (int q = 0; q < kPer; ++q) {
+    bin_base[threadIdx.x * kPer + q] = run;
+    run += local[q];
   }
 }
 
+// Scatter: position = start of the row's bin + a ticket from the bin's cursor (one atomic per distinct digest per
+// warp).  Writes perm, the permuted neighbour map and ORs the row's mask into its tile's mask; the last CTA to
+// finish ranks the tiles.
 __global__ void __launch_bounds__(kThreads)
-permute_nbr_kernel(const int *__restrict__ nbr, int64_t nbr_stride, int kvol, const int *__restrict__ perm,
-                   const int *n_dev, int64_t n_cap, int *nbr_sorted, int64_t sorted_stride) {
-  const int n = live_n(n_dev, n_cap);
-  const int64_t total = (int64_t)n * kvol;
-  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const int k = (int)(e / n), t = (int)(e - (int64_t)k * n);
-    nbr_sorted[(size_t)k * sorted_stride + t] = __ldg(&nbr[(size_t)k * nbr_stride + __ldg(&perm[t])]);
-  }
-}
-
-// Tile masks for the conv's tile scheduler: masks[t] = OR of the neighbour masks of sorted rows [128 t, 128 t + 128);
-// its population count = pipeline stages (per 128-byte slice) the conv spends on the tile.  One warp per tile.
-constexpr int kConvTile = 128;
-
-__global__ void __launch_bounds__(kThreads)
-tile_mask_kernel(const uint32_t *__restrict__ keys_sorted, const int *n_dev, int64_t n_cap, uint32_t *masks) {
-  const int n = live_n(n_dev, n_cap);
-  const int n_tiles = (n + kConvTile - 1) / kConvTile;
-  const int lane = threadIdx.x & 31;
-  const int warps = (gridDim.x * blockDim.x) >> 5;
-  for (int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < n_tiles; t += warps) {
-    uint32_t m = 0;
-#pragma unroll
-    for (int q = 0; q < kConvTile / 32; ++q) {
-      const int i = t * kConvTile + q * 32 + lane;
-      if (i < n) m |= keys_sorted[i];
-    }
-    m = __reduce_or_sync(0xFFFFFFFFu, m);
-    if (lane == 0) masks[t] = m;
-  }
-}
-
-// tile_order = (tile, mask) pairs by descending weight = popcount(mask) (counting sort over the 33 possible weights,
-// one CTA).  The conv hands tiles to its CTAs in this order, i.e. longest-processing-time-first list scheduling, and
-// takes the tile's active offsets from the mask.  Ties are placed in tile order (per-warp ballots under a
-// block-ordered cursor), so the order is deterministic.
-__global__ void __launch_bounds__(1024)
-tile_rank_kernel(const uint32_t *__restrict__ masks, const int *n_dev, int64_t n_cap, int2 *tile_order) {
+group_scatter_kernel(const int *__restrict__ nbr, int64_t nbr_stride, int kvol, const int *n_dev, int64_t n_cap,
+                     const uint32_t *__restrict__ masks, const uint16_t *__restrict__ digests,
+                     const int *__restrict__ bin_base, int *cursor, int *perm, int *nbr_sorted,
+                     int64_t sorted_stride, uint32_t *tile_masks, int *done, int2 *tile_order) {
+  __shared__ int s_last;
   __shared__ int hist[33], base[33];
-  __shared__ int warp_cnt[32][33];
+  __shared__ int warp_cnt[kThreads / 32][33];
   const int n = live_n(n_dev, n_cap);
-  const int n_tiles = (n + kConvTile - 1) / kConvTile;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n_round = (n + 31) & ~31;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+    const bool live = i < n;
+    const int d = live ? (int)digests[i] : kBins + lane;
+    const unsigned peers = __match_any_sync(0xFFFFFFFFu, d);
+    const int leader = __ffs(peers) - 1;
+    int start = 0;
+    if (live && lane == leader) start = __ldg(&bin_base[d]) + atomicAdd(&cursor[d], __popc(peers));
+    start = __shfl_sync(0xFFFFFFFFu, start, leader);
+    const int pos = start + __popc(peers & ((1u << lane) - 1u));
+    const uint32_t m = live ? masks[i] : 0u;
+    const int tile = live ? pos / kConvTile : -1 - lane;
+    const unsigned tpeers = __match_any_sync(0xFFFFFFFFu, tile);
+    const uint32_t tm = __reduce_or_sync(tpeers, m);
+    if (live) {
+      perm[pos] = i;
+      if (nbr_sorted)
+        for (int k = 0; k < kvol; ++k)
+          nbr_sorted[(size_t)k * sorted_stride + pos] = __ldg(&nbr[(size_t)k * nbr_stride + i]);
+      if (tile_order && lane == __ffs(tpeers) - 1) atomicOr(&tile_masks[tile], tm);
+    }
+  }
+  if (!tile_order) return;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(&done[1], 1) == (int)gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // tile_order = (tile, mask) pairs by descending weight = popcount(mask) (counting sort over the 33 possible
+  // weights), ties in tile order (per-warp ballots under a block-ordered cursor).
+  const volatile uint32_t *tmv = tile_masks;
+  const int n_tiles = (n + kConvTile - 1) / kConvTile;
   if (threadIdx.x < 33) hist[threadIdx.x] = 0;
   __syncthreads();
-  for (int t = threadIdx.x; t < n_tiles; t += blockDim.x) atomicAdd(&hist[__popc(masks[t])], 1);
+  for (int t = threadIdx.x; t < n_tiles; t += blockDim.x) atomicAdd(&hist[__popc(tmv[t])], 1);
   __syncthreads();
   if (threadIdx.x == 0) {
     int run = 0;
@@ -169,7 +182,7 @@ tile_rank_kernel(const uint32_t *__restrict__ masks, const int *n_dev, int64_t n
   __syncthreads();
   for (int t0 = 0; t0 < n_tiles; t0 += blockDim.x) {
     const int t = t0 + threadIdx.x;
-    const uint32_t m = t < n_tiles ? masks[t] : 0u;
+    const uint32_t m = t < n_tiles ? tmv[t] : 0u;
     const int w = t < n_tiles ? __popc(m) : -1;
     const unsigned peers = __match_any_sync(0xFFFFFFFFu, w);
     for (int b = lane; b < 33; b += 32) warp_cnt[warp][b] = 0;
@@ -184,91 +197,71 @@ tile_rank_kernel(const uint32_t *__restrict__ masks, const int *n_dev, int64_t n
     __syncthreads();
     if (threadIdx.x < 33) {
       int add = 0;
-      for (int q = 0; q < 32; ++q) add += warp_cnt[q][threadIdx.x];
+      for (int q = 0; q < kThreads / 32; ++q) add += warp_cnt[q][threadIdx.x];
       base[threadIdx.x] += add;
     }
     __syncthreads();
   }
 }
 
-struct SortWorkspace {
-  uint32_t *keys_a, *keys_b;
-  int *vals_b, *counts, *totals;
-  uint32_t *tile_masks;
-  int n_chunks;
-  size_t bytes;
-};
+}  // namespace
 
-SortWorkspace carve(void *ws, int64_t n_cap) {
-  SortWorkspace w;
-  Carver c(ws);
-  const size_t n = (size_t)(n_cap > 0 ? n_cap : 1);
-  w.n_chunks = (int)((n_cap + kChunk - 1) / kChunk);
-  if (w.n_chunks < 1) w.n_chunks = 1;
-  w.keys_a = c.take<uint32_t>(n);
-  w.keys_b = c.take<uint32_t>(n);
-  w.vals_b = c.take<int>(n);
-  w.counts = c.take<int>((size_t)kBins * w.n_chunks);
-  w.totals = c.take<int>(kBins);
-  w.tile_masks = c.take<uint32_t>(n / kConvTile + 1);
-  w.bytes = c.used + 256;
-  return w;
+void group_rows_zero_region(int64_t n_cap, size_t *off, size_t *bytes) {
+  // offsets do not depend on the base pointer
+  GroupWs w = carve(reinterpret_cast<void *>(uintptr_t(4096)), n_cap);
+  *off = w.zero_off;
+  *bytes = w.zero_bytes;
 }
 
-}  // namespace
 }  // namespace fv2p
 
 using namespace fv2p;
 
-extern "C" size_t fv2p_sort_rows_workspace_bytes(int64_t n_cap) {
+extern "C" size_t fv2p_group_rows_workspace_bytes(int64_t n_cap) {
   if (n_cap < 0) return 0;
   return carve(nullptr, n_cap).bytes;
 }
 
+extern "C" size_t fv2p_sort_rows_workspace_bytes(int64_t n_cap) { return fv2p_group_rows_workspace_bytes(n_cap); }
+
+extern "C" int fv2p_group_rows(const int32_t *nbr, int64_t nbr_stride, int kvol, int kx, int64_t n_cap,
+                               const int32_t *n_dev, int32_t *perm, int32_t *nbr_sorted, int64_t sorted_stride,
+                               int32_t *tile_order, void *workspace, size_t workspace_bytes, int flags,
+                               fv2p_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  FV2P_REQUIRE(kvol >= 1 && kvol <= FV2P_MAX_KVOL, "group_rows: kernel volume %d out of range", kvol);
+  if (kx < 1 || kvol % kx != 0) kx = 1;
+  FV2P_REQUIRE(n_cap >= 0 && n_cap < (1ll << 26) && nbr_stride >= n_cap, "group_rows: bad sizes");
+  FV2P_REQUIRE(!nbr_sorted || sorted_stride >= n_cap, "group_rows: sorted_stride < row capacity");
+  if (n_cap == 0) return FV2P_OK;
+  FV2P_REQUIRE(nbr && perm, "group_rows: null pointer argument");
+  GroupWs w = carve(workspace, n_cap);
+  if (!workspace || workspace_bytes < w.bytes) {
+    set_error("group_rows: workspace too small (%zu < %zu)", workspace_bytes, w.bytes);
+    return FV2P_ERR_WORKSPACE;
+  }
+  if (!(flags & FV2P_FLAG_PREFILLED)) {
+    int st = cuda_status(cudaMemsetAsync(static_cast<char *>(workspace) + w.zero_off, 0, w.zero_bytes, stream),
+                         "group_rows");
+    if (st) return st;
+  }
+  const int grid = persistent_grid();
+  group_hist_kernel<<<grid, kThreads, 0, stream>>>(nbr, nbr_stride, kvol, kx, kvol / kx, n_dev, n_cap, w.masks,
+                                                   w.digests, w.bins, w.bin_base, w.done);
+  group_scatter_kernel<<<grid, kThreads, 0, stream>>>(nbr, nbr_stride, kvol, n_dev, n_cap, w.masks, w.digests,
+                                                      w.bin_base, w.cursor, perm, nbr_sorted, sorted_stride,
+                                                      w.tile_masks, w.done, reinterpret_cast<int2 *>(tile_order));
+  FV2P_LAUNCH_CHECK("group_rows");
+  return FV2P_OK;
+}
+
+// First-generation name and signature (3x3x3-style kernels: the fastest axis has extent 3 when kvol is a multiple
+// of 9, else the mask is short enough to be its own digest).
 extern "C" int fv2p_sort_rows_by_mask(const int32_t *nbr, int64_t nbr_stride, int kvol, int64_t n_cap,
                                       const int32_t *n_dev, int32_t *perm, int32_t *nbr_sorted,
                                       int64_t sorted_stride, int32_t *tile_order, void *workspace,
-                                      size_t workspace_bytes,
-                                      fv2p_stream_t stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  FV2P_REQUIRE(kvol >= 1 && kvol <= FV2P_MAX_KVOL, "sort_rows: kernel volume %d out of range", kvol);
-  FV2P_REQUIRE(n_cap >= 0 && n_cap < (1ll << 26) && nbr_stride >= n_cap, "sort_rows: bad sizes");
-  FV2P_REQUIRE(!nbr_sorted || sorted_stride >= n_cap, "sort_rows: sorted_stride < row capacity");
-  if (n_cap == 0) return FV2P_OK;
-  FV2P_REQUIRE(nbr && perm, "sort_rows: null pointer argument");
-  SortWorkspace w = carve(workspace, n_cap);
-  if (!workspace || workspace_bytes < w.bytes) {
-    set_error("sort_rows: workspace too small (%zu < %zu)", workspace_bytes, w.bytes);
-    return FV2P_ERR_WORKSPACE;
-  }
-  const int grid = persistent_grid();
-  const int passes = (kvol + kDigitBits - 1) / kDigitBits;
-  // ping-pong (keys_a, perm) <-> (keys_b, vals_b), arranged so that the last pass lands in `perm`
-  uint32_t *k_src = w.keys_a, *k_dst = w.keys_b;
-  int *v_src = (passes % 2 == 0) ? perm : w.vals_b;
-  int *v_dst = (passes % 2 == 0) ? w.vals_b : perm;
-  nbr_mask_kernel<<<grid, kThreads, 0, stream>>>(nbr, nbr_stride, kvol, n_dev, n_cap, k_src, v_src);
-  for (int p = 0; p < passes; ++p) {
-    const int shift = p * kDigitBits;
-    sort_hist_kernel<<<grid, kThreads, 0, stream>>>(k_src, n_dev, n_cap, shift, w.counts, w.n_chunks);
-    launch_scan_chunk_counts(w.counts, kBins, w.n_chunks, n_dev, n_cap, w.totals, stream);
-    sort_scatter_kernel<<<grid, kThreads, 0, stream>>>(k_src, v_src, n_dev, n_cap, shift, w.counts, w.totals,
-                                                       w.n_chunks, k_dst, v_dst);
-    uint32_t *tk = k_src;
-    k_src = k_dst;
-    k_dst = tk;
-    int *tv = v_src;
-    v_src = v_dst;
-    v_dst = tv;
-  }
-  // v_src now holds the sorted rows and, by construction, is `perm`
-  if (nbr_sorted)
-    permute_nbr_kernel<<<grid, kThreads, 0, stream>>>(nbr, nbr_stride, kvol, perm, n_dev, n_cap, nbr_sorted,
-                                                      sorted_stride);
-  if (tile_order) {  // k_src holds the sorted masks
-    tile_mask_kernel<<<grid, kThreads, 0, stream>>>(k_src, n_dev, n_cap, w.tile_masks);
-    tile_rank_kernel<<<1, 1024, 0, stream>>>(w.tile_masks, n_dev, n_cap, reinterpret_cast<int2 *>(tile_order));
-  }
-  FV2P_LAUNCH_CHECK("sort_rows_by_mask");
-  return FV2P_OK;
+                                      size_t workspace_bytes, fv2p_stream_t stream_) {
+  const int kx = kvol == 27 ? 3 : (kvol == 8 ? 2 : (kvol == 125 ? 5 : 1));
+  return fv2p_group_rows(nbr, nbr_stride, kvol, kx, n_cap, n_dev, perm, nbr_sorted, sorted_stride, tile_order,
+                         workspace, workspace_bytes, 0, stream_);
 }

@@ -138,6 +138,39 @@ def trace_backbone(net):
     return steps, list(books.values()), levels
 
 
+class _LazyIndiceDict(dict):
+    """indice_dict whose values are produced on first access (the reference-layout pair tensors are not needed by
+    anything on the hot path; consumers that read them - `find_indice_pair`, `indice_dict[key]` - get them built then)."""
+
+    def defer(self, key, thunk):
+        dict.__setitem__(self, key, _Deferred(thunk))
+
+    def _resolve(self, key, value):
+        if isinstance(value, _Deferred):
+            value = value.thunk()
+            dict.__setitem__(self, key, value)
+        return value
+
+    def __getitem__(self, key):
+        return self._resolve(key, dict.__getitem__(self, key))
+
+    def get(self, key, default=None):
+        return self[key] if key in self else default
+
+    def items(self):
+        return [(k, self[k]) for k in self.keys()]
+
+    def values(self):
+        return [self[k] for k in self.keys()]
+
+
+class _Deferred(object):
+    __slots__ = ("thunk",)
+
+    def __init__(self, thunk):
+        self.thunk = thunk
+
+
 class CapacityOverflow(RuntimeError):
     """A level produced more rows than its arena buffers hold (nothing was written out of bounds).  Raised when the
     row counts reach the host; `BackboneEngine.grow()` enlarges the bounds, then the step is run again."""
@@ -150,13 +183,15 @@ class BackboneEngine(object):
     SIDE_STREAMS = 4
 
     def __init__(self, net, precision="fp32", materialize_pairs=True, use_tensor_cores=True, sort_rows=True,
-                 concurrent=True, cap_growth=2.0):
+                 concurrent=True, cap_growth='auto'):
         traced = trace_backbone(net)
         if traced is None:
             raise NotImplementedError("backbone layout not recognised by the fused engine")
         self.steps, self.books, self.level_shapes = traced
         self.net = net
         self.precision = precision
+        # True: the reference-layout pair tensors are built with every step (on a side stream); 'lazy': when
+        # indice_dict[key] is first read; False: never (indice_dict stays empty)
         self.materialize_pairs = materialize_pairs
         self.use_tensor_cores = use_tensor_cores
         self.sort_rows = sort_rows  # mask-sorted row order for the tensor-core layers (same results, fewer stages)
@@ -230,24 +265,45 @@ class BackboneEngine(object):
         return _lib.MODE_TF32X3_TC if (tc_ok and not first) else _lib.MODE_F32
 
     # ------------------------------------------------------------------ arena
+    # Row capacity of a level relative to the level it is built from, when cap_growth == 'auto': what LiDAR-like
+    # frames produce (x1.06-1.13 at the first stride-2 conv, then x0.45-0.57, x0.40, x0.85) with 30-100 %
+    # head room.  A step that overflows sets a status bit, the bounds grow and the step runs again.
+    AUTO_GROWTH_FIRST, AUTO_GROWTH_DEEPER, AUTO_GROWTH_NARROW = 1.5, 0.6, 1.0
+
+    def _growth(self, bk):
+        if not self.cap_growth:
+            return float(bk.fanout)
+        if self.cap_growth == 'auto':
+            if bk.fanout <= 2:
+                return min(float(bk.fanout), self.AUTO_GROWTH_NARROW)
+            return self.AUTO_GROWTH_FIRST if bk.in_level == 0 else min(float(bk.fanout), self.AUTO_GROWTH_DEEPER)
+        return min(float(bk.fanout), float(self.cap_growth))
+
     def _caps(self, cap0, batch):
         caps = [int(cap0)]
         for bk in self.books:
             if not bk.subm:
                 vol = int(np.prod(self.level_shapes[bk.out_level])) * int(batch)
-                fan = bk.fanout if not self.cap_growth else min(float(bk.fanout), float(self.cap_growth))
-                caps.append(max(1, min(int(caps[bk.in_level] * fan) + 1024, caps[bk.in_level] * bk.fanout, vol)))
+                caps.append(max(1, min(int(caps[bk.in_level] * self._growth(bk)) + 1024,
+                                       caps[bk.in_level] * bk.fanout, vol)))
         return caps
 
     def grow(self):
-        """Enlarges the capacity bounds after a CapacityOverflow (x4, then the hard bound); the next launch
-        allocates a new arena.  Returns False when the bounds are already the hard ones."""
+        """Enlarges the capacity bounds after a CapacityOverflow ('auto' -> x2 per level -> x8 -> the hard bound); the
+        next launch allocates a new arena.  Returns False when the bounds are already the hard ones."""
         if not self.cap_growth:
             return False
-        self.cap_growth = None if self.cap_growth >= 8 else self.cap_growth * 4.0
+        if self.cap_growth == 'auto':
+            self.cap_growth = 2.0
+        else:
+            self.cap_growth = None if self.cap_growth >= 8 else self.cap_growth * 4.0
         self.arena = None
         self.arena_gen += 1  # captured graphs of the old arena are stale
         return True
+
+    @staticmethod
+    def _geo_key(bk):
+        return (bool(bk.subm), bk.in_level, tuple(bk.ksize), tuple(bk.stride), tuple(bk.pad), tuple(bk.dil))
 
     def _ensure_arena(self, device, cap0, batch):
         a = self.arena
@@ -261,32 +317,52 @@ class BackboneEngine(object):
         a["counts"] = torch.zeros((len(caps) + 1,), dtype=torch.int32, device=device)  # [levels..., status]
         a["counts_host"] = torch.zeros((len(caps) + 1,), dtype=torch.int32).pin_memory()
         a["indices"] = [None] + [torch.empty((c, 4), dtype=torch.int32, device=device) for c in caps[1:]]
-        books = {}
-        ws_bytes = 0
+        # one coordinate table per level: level 0 is built from the voxel coordinates, level l+1 is the output table of
+        # the strided rulebook l -> l+1 and then serves the submanifold rulebooks of level l+1
+        a["tables"] = [torch.empty(lib.fv2p_table_bytes(c) + 16, dtype=torch.uint8, device=device) for c in caps]
+        tc_modes = (_lib.MODE_BF16_TC, _lib.MODE_TF32X3_TC)
+        tc_books = {st.key for st in self.steps if self._mode_for(st) in tc_modes}
+        books, geo = {}, {}
         for bk in self.books:
-            cin_cap, cout_cap = caps[bk.in_level], caps[bk.out_level]
-            # neighbour-map rows padded to whole 128-row tiles: the conv's bulk copies need 16-byte aligned rows
-            cols = (cout_cap + 127) // 128 * 128
-            d = dict(nbr=torch.empty((bk.kvol, cols), dtype=torch.int32, device=device),
-                     pair_num=torch.zeros((bk.kvol,), dtype=torch.int32, device=device),
-                     pairs=(torch.empty((bk.kvol, 2, cin_cap), dtype=torch.int32, device=device)
-                            if self.materialize_pairs else None))
-            if self.sort_rows:
+            gk = self._geo_key(bk)
+            d = geo.get(gk)
+            if d is None:
+                cin_cap, cout_cap = caps[bk.in_level], caps[bk.out_level]
+                # neighbour-map rows padded to whole 128-row tiles: the conv's bulk copies need 16-byte aligned rows
+                cols = (cout_cap + 127) // 128 * 128
+                d = dict(geo=gk, book=bk, keys=[], nbr=torch.empty((bk.kvol, cols), dtype=torch.int32, device=device),
+                         sorted=False, pairs=None, pair_num=None, pair_ws=None)
+                if not bk.subm:
+                    d["ws"] = torch.empty(lib.fv2p_conv_neighbours_workspace_bytes(cin_cap, bk.kvol) + 256,
+                                          dtype=torch.uint8, device=device)
+                geo[gk] = d
+            d["keys"].append(bk.key)
+            if self.sort_rows and bk.key in tc_books and not d["sorted"]:
+                cout_cap = caps[bk.out_level]
+                cols = d["nbr"].shape[1]
+                d["sorted"] = True
                 d["perm"] = torch.empty((cout_cap,), dtype=torch.int32, device=device)
                 d["nbr_sorted"] = torch.empty((bk.kvol, cols), dtype=torch.int32, device=device)
-                d["tile_order"] = torch.empty((cout_cap // 128 + 1, 2), dtype=torch.int32, device=device)
-                ws_bytes = max(ws_bytes, lib.fv2p_sort_rows_workspace_bytes(cout_cap))
-            # own scratch per book: the pair compaction runs on a stream of its own and keeps reading it while the
-            # next book is already being built
-            d["ws"] = torch.empty(lib.fv2p_rulebook_workspace_bytes(cin_cap, cout_cap, bk.kvol) + 1024,
-                                  dtype=torch.uint8, device=device)
+                d["tile_order"] = torch.empty((cout_cap // 128 + 2, 2), dtype=torch.int32, device=device)
+                d["group_ws"] = torch.empty(lib.fv2p_group_rows_workspace_bytes(cout_cap) + 256, dtype=torch.uint8,
+                                            device=device)
             books[bk.key] = d
-        a["books"] = books
+        a["books"], a["geo"] = books, list(geo.values())
+        # everything the geometry pass wants cleared / zeroed / set to -1 before it starts: ONE launch per step
+        items = [(_lib.PREFILL_TABLE, t, c, 0) for t, c in zip(a["tables"], caps)]
+        for d in a["geo"]:
+            bk = d["book"]
+            if bk.subm:
+                if all(k % 2 == 1 for k in bk.ksize) and all(x == 1 for x in bk.dil) and bk.kvol > 1:
+                    items.append((_lib.PREFILL_NBR_MIRROR, d["nbr"], bk.kvol, d["nbr"].shape[1]))
+            else:
+                items.append((_lib.PREFILL_NBR_ALL, d["nbr"], bk.kvol, d["nbr"].shape[1]))
+                items.append((_lib.PREFILL_CONV_WS, d["ws"], caps[bk.in_level], bk.kvol))
+            if d["sorted"]:
+                items.append((_lib.PREFILL_GROUP_WS, d["group_ws"], caps[bk.out_level], 0))
+        a["prefill"] = _lib.prefill_items(items)
         # two scheduler words per conv step (tile counter, CTAs done); zero between launches, the kernel re-arms them
         a["sched"] = torch.zeros((len(self.steps), 2), dtype=torch.int32, device=device)
-        # mask sorts: one workspace per side stream
-        a["ws_side"] = [torch.empty(ws_bytes + 1024, dtype=torch.uint8, device=device)
-                        for _ in range(self.SIDE_STREAMS)]
         # feature buffers with liveness-based reuse
         bufs, free, owner = {}, [], {}
         for i, st in enumerate(self.steps):
@@ -310,6 +386,26 @@ class BackboneEngine(object):
         self.arena_gen += 1  # captured CUDA graphs hold arena addresses: a new arena invalidates them
         return a
 
+    def arena_bytes(self):
+        """Device bytes held by the current arena (rulebooks, tables, feature buffers)."""
+        a = self.arena
+        if a is None:
+            return 0
+        seen, total = set(), 0
+
+        def add(t):
+            nonlocal total
+            if isinstance(t, torch.Tensor) and t.is_cuda and t.data_ptr() not in seen:
+                seen.add(t.data_ptr())
+                total += t.numel() * t.element_size()
+
+        for t in a["indices"] + a["tables"] + list(a["bufs"].values()) + [a["counts"], a["sched"]]:
+            add(t)
+        for d in a["geo"]:
+            for v in d.values():
+                add(v)
+        return total
+
     # ------------------------------------------------------------------ run
     def launch(self, voxel_features, voxel_coords, batch_size, n0_dev=None, cap0=None, features_ready=None):
         """Enqueues geometry + feature passes on the current stream.  No host sync.
@@ -330,6 +426,7 @@ class BackboneEngine(object):
         lib = _lib.load()
         counts = a["counts"]
         caps = a["caps"]
+        PRE = _lib.FLAG_PREFILLED
         with torch.cuda.device(dev):
             main = torch.cuda.current_stream(device)
             if self.concurrent:
@@ -338,7 +435,6 @@ class BackboneEngine(object):
                 side, s_pairs, s_conv = self._side[:-2], self._side[-2], self._side[-1]
             else:
                 side, s_pairs, s_conv = [main], main, main
-            pairs_ptr = _lib.ctypes.c_void_p(s_pairs.cuda_stream)
             counts[len(caps):].zero_()
             if n0_dev is None:
                 counts[0:1].fill_(cap0)
@@ -349,82 +445,113 @@ class BackboneEngine(object):
             level_cap = [cap0] + caps[1:]
             n_ptr = [_lib.ctypes.c_void_p(counts.data_ptr() + 4 * i) for i in range(len(caps))]
             status_ptr = _lib.ctypes.c_void_p(counts.data_ptr() + 4 * len(caps))
-            tc_modes = (_lib.MODE_BF16_TC, _lib.MODE_TF32X3_TC)
-            tc_books = {st_.key for st_, p in zip(self.steps, prm) if p["mode"] in tc_modes}
 
             # Dependency chains, forked from and joined back into the caller's stream (so the whole thing is still one
             # stream-ordered step, and one CUDA graph when captured):
-            #   main   the strided rulebooks, level by level (each needs the previous level's output coordinates)
-            #   side   the submanifold rulebooks and every mask sort: leaves of that chain, independent of each
-            #          other, dealt round-robin to SIDE_STREAMS streams (each with its own workspace)
-            #   s_pairs the compaction of the reference-layout pair lists (forked inside the rulebook calls once the
-            #          neighbour map is complete; nothing in the step waits for it but the final join)
-            #   s_conv the feature pass, each layer waiting only for what it reads (the sorted set for the
+            #   main   ONE prefill launch, the level-0 table, then the strided rulebooks level by level (each needs
+            #          the previous level's output coordinates)
+            #   side   the submanifold rulebooks and every row grouping: leaves of that chain, independent of each
+            #          other, dealt round-robin to SIDE_STREAMS streams
+            #   s_pairs the reference-layout pair lists when they are materialised eagerly (nothing in the step waits
+            #          for them but the final join)
+            #   s_conv the feature pass, each layer waiting only for what it reads (the grouped set for the
             #          tensor-core kernels, the plain neighbour map otherwise)
-            # The geometry kernels are small and latency bound, so they hide behind the conv kernels.
             def mark(stream):
                 ev = torch.cuda.Event()
                 ev.record(stream)
                 return ev
 
+            items, n_items = a["prefill"]
+            _lib.check(lib.fv2p_geometry_prefill(items, n_items, _lib.stream_ptr(device)), "geometry_prefill")
+            _lib.check(lib.fv2p_table_build(_lib.ptr(voxel_coords), cap0, n_ptr[0], _lib.i32x3(self.level_shapes[0]),
+                                            _lib.ptr(a["tables"][0]), caps[0], status_ptr, PRE,
+                                            _lib.stream_ptr(device)), "table_build")
             level_ready = {0: mark(main)}
-            book_built, book_sorted = {}, {}
-            for j, bk in enumerate(self.books):
-                d = a["books"][bk.key]
-                pairs = d["pairs"]
+            built, grouped = {}, {}
+            for j, d in enumerate(a["geo"]):
+                bk = d["book"]
                 s_side = side[j % len(side)]
-                ws_side = a["ws_side"][j % len(side)]
                 if bk.subm:
                     s_side.wait_event(level_ready[bk.in_level])
                     with torch.cuda.stream(s_side):
-                        st = lib.fv2p_rulebook_subm(_lib.ptr(level_ind[bk.in_level]), level_cap[bk.in_level],
-                                                    n_ptr[bk.in_level], int(batch_size),
-                                                    _lib.i32x3(self.level_shapes[bk.in_level]), _lib.i32x3(bk.ksize),
-                                                    _lib.i32x3(bk.dil), _lib.ptr(pairs),
-                                                    pairs.shape[2] if pairs is not None else 0,
-                                                    _lib.ptr(d["pair_num"]) if pairs is not None else None,
-                                                    _lib.ptr(d["nbr"]), d["nbr"].shape[1], _lib.ptr(d["ws"]),
-                                                    d["ws"].numel(), _lib.stream_ptr(device), pairs_ptr)
-                    book_built[bk.key] = mark(s_side)
+                        st = lib.fv2p_subm_neighbours(_lib.ptr(level_ind[bk.in_level]), level_cap[bk.in_level],
+                                                      n_ptr[bk.in_level], int(batch_size),
+                                                      _lib.i32x3(self.level_shapes[bk.in_level]), _lib.i32x3(bk.ksize),
+                                                      _lib.i32x3(bk.dil), _lib.ptr(a["tables"][bk.in_level]),
+                                                      caps[bk.in_level], _lib.ptr(d["nbr"]), d["nbr"].shape[1], PRE,
+                                                      _lib.stream_ptr(device))
+                    built[id(d)] = mark(s_side)
                 else:
                     with torch.cuda.stream(main):
-                        st = lib.fv2p_rulebook_conv(_lib.ptr(level_ind[bk.in_level]), level_cap[bk.in_level],
-                                                    n_ptr[bk.in_level], int(batch_size),
-                                                    _lib.i32x3(self.level_shapes[bk.out_level]),
-                                                    _lib.i32x3(bk.ksize), _lib.i32x3(bk.stride), _lib.i32x3(bk.pad),
-                                                    _lib.i32x3(bk.dil), _lib.ptr(level_ind[bk.out_level]),
-                                                    level_cap[bk.out_level], n_ptr[bk.out_level], _lib.ptr(pairs),
-                                                    pairs.shape[2] if pairs is not None else 0,
-                                                    _lib.ptr(d["pair_num"]) if pairs is not None else None,
-                                                    _lib.ptr(d["nbr"]), d["nbr"].shape[1], status_ptr,
-                                                    _lib.ptr(d["ws"]), d["ws"].numel(), _lib.stream_ptr(device),
-                                                    pairs_ptr)
-                    level_ready[bk.out_level] = book_built[bk.key] = mark(main)
-                    s_side.wait_event(book_built[bk.key])
+                        st = lib.fv2p_conv_neighbours(_lib.ptr(level_ind[bk.in_level]), level_cap[bk.in_level],
+                                                      n_ptr[bk.in_level], int(batch_size),
+                                                      _lib.i32x3(self.level_shapes[bk.out_level]),
+                                                      _lib.i32x3(bk.ksize), _lib.i32x3(bk.stride), _lib.i32x3(bk.pad),
+                                                      _lib.i32x3(bk.dil), _lib.ptr(level_ind[bk.out_level]),
+                                                      level_cap[bk.out_level], n_ptr[bk.out_level],
+                                                      _lib.ptr(a["tables"][bk.out_level]), caps[bk.out_level],
+                                                      _lib.ptr(d["nbr"]), d["nbr"].shape[1], status_ptr,
+                                                      _lib.ptr(d["ws"]), d["ws"].numel(), PRE, _lib.stream_ptr(device))
+                    level_ready[bk.out_level] = built[id(d)] = mark(main)
+                    s_side.wait_event(built[id(d)])
                 _lib.check(st, "rulebook[%s]" % bk.key)
-                if self.sort_rows and bk.key in tc_books:
+                if d["sorted"]:
                     with torch.cuda.stream(s_side):
-                        st = lib.fv2p_sort_rows_by_mask(_lib.ptr(d["nbr"]), d["nbr"].shape[1], bk.kvol,
-                                                        level_cap[bk.out_level], n_ptr[bk.out_level],
-                                                        _lib.ptr(d["perm"]), _lib.ptr(d["nbr_sorted"]),
-                                                        d["nbr_sorted"].shape[1], _lib.ptr(d["tile_order"]),
-                                                        _lib.ptr(ws_side), ws_side.numel(), _lib.stream_ptr(device))
-                    _lib.check(st, "sort_rows[%s]" % bk.key)
-                    book_sorted[bk.key] = mark(s_side)
+                        st = lib.fv2p_group_rows(_lib.ptr(d["nbr"]), d["nbr"].shape[1], bk.kvol, int(bk.ksize[2]),
+                                                 level_cap[bk.out_level], n_ptr[bk.out_level], _lib.ptr(d["perm"]),
+                                                 _lib.ptr(d["nbr_sorted"]), d["nbr_sorted"].shape[1],
+                                                 _lib.ptr(d["tile_order"]), _lib.ptr(d["group_ws"]),
+                                                 d["group_ws"].numel(), PRE, _lib.stream_ptr(device))
+                    _lib.check(st, "group_rows[%s]" % bk.key)
+                    grouped[id(d)] = mark(s_side)
+                if self.materialize_pairs is True:
+                    s_pairs.wait_event(built[id(d)])
+                    with torch.cuda.stream(s_pairs):
+                        self._pairs_call(a, d, level_ind, level_cap, n_ptr, batch_size)
             waited = set()
             if features_ready is not None:
                 s_conv.wait_event(features_ready)
             for i, (st_, p) in enumerate(zip(self.steps, prm)):
-                needs = book_sorted if self.conv_operands(a, st_, p)[1] is not None else book_built
-                if (st_.key, id(needs)) not in waited:
-                    s_conv.wait_event(needs[st_.key])
-                    waited.add((st_.key, id(needs)))
+                d = a["books"][st_.key]
+                ev = grouped[id(d)] if self.conv_operands(a, st_, p)[1] is not None else built[id(d)]
+                if id(ev) not in waited:
+                    s_conv.wait_event(ev)
+                    waited.add(id(ev))
                 with torch.cuda.stream(s_conv):
                     self.run_conv_step(a, i, p, voxel_features, cap0)
             if self.concurrent:  # join: everything this step enqueued is ordered before what the caller does next
                 for s_ in side + [s_pairs, s_conv]:
                     main.wait_event(mark(s_))
+        a["level_cap"] = level_cap
+        a["step"] = a.get("step", 0) + 1
         return a
+
+    def _pairs_call(self, a, d, level_ind, level_cap, n_ptr, batch_size):
+        """Enqueues the reference-layout pair lists of one geometry on the current stream (buffers on first use)."""
+        lib = _lib.load()
+        bk = d["book"]
+        device = a["device"]
+        cin_cap = a["caps"][bk.in_level]
+        if d["pairs"] is None:
+            d["pairs"] = torch.empty((bk.kvol, 2, cin_cap), dtype=torch.int32, device=device)
+            d["pair_num"] = torch.zeros((bk.kvol,), dtype=torch.int32, device=device)
+            d["pair_ws"] = torch.empty(lib.fv2p_pairs_workspace_bytes(cin_cap, bk.kvol) + 256, dtype=torch.uint8,
+                                       device=device)
+        if bk.subm:
+            st = lib.fv2p_subm_pairs(_lib.ptr(level_ind[bk.in_level]), level_cap[bk.in_level], n_ptr[bk.in_level],
+                                     int(batch_size), _lib.i32x3(self.level_shapes[bk.in_level]), _lib.i32x3(bk.ksize),
+                                     _lib.i32x3(bk.dil), _lib.ptr(a["tables"][bk.in_level]), a["caps"][bk.in_level],
+                                     _lib.ptr(d["nbr"]), d["nbr"].shape[1], _lib.ptr(d["pairs"]), d["pairs"].shape[2],
+                                     _lib.ptr(d["pair_num"]), _lib.ptr(d["pair_ws"]), d["pair_ws"].numel(),
+                                     _lib.stream_ptr(device))
+        else:
+            st = lib.fv2p_conv_pairs(_lib.ptr(level_ind[bk.in_level]), level_cap[bk.in_level], n_ptr[bk.in_level],
+                                     int(batch_size), _lib.i32x3(self.level_shapes[bk.out_level]),
+                                     _lib.i32x3(bk.ksize), _lib.i32x3(bk.stride), _lib.i32x3(bk.pad),
+                                     _lib.i32x3(bk.dil), _lib.ptr(a["tables"][bk.out_level]), a["caps"][bk.out_level],
+                                     _lib.ptr(d["pairs"]), d["pairs"].shape[2], _lib.ptr(d["pair_num"]),
+                                     _lib.ptr(d["pair_ws"]), d["pair_ws"].numel(), _lib.stream_ptr(device))
+        _lib.check(st, "pairs[%s]" % bk.key)
 
     def conv_operands(self, a, step, prm):
         """(neighbour map, row order, tile order) a conv step reads: the mask-sorted set for the tensor-core modes."""
@@ -468,14 +595,13 @@ class BackboneEngine(object):
                                    (status, self.cap_growth))
         n = host[:n_levels]
         level_ind = [voxel_coords[:n[0]]] + [t[:n[i + 1]] for i, t in enumerate(a["indices"][1:])]
-        indice_dict, nbr_dict = {}, {}
+        nbr_dict = {}
+        indice_dict = _LazyIndiceDict() if self.materialize_pairs else {}
         for bk in self.books:
             d = a["books"][bk.key]
-            n_in, n_out = n[bk.in_level], n[bk.out_level]
-            nbr_dict[bk.key] = d["nbr"][:, :n_out]
-            if d["pairs"] is not None:
-                indice_dict[bk.key] = (level_ind[bk.out_level], level_ind[bk.in_level], d["pairs"][:, :, :n_in],
-                                       d["pair_num"], self.level_shapes[bk.in_level])
+            nbr_dict[bk.key] = d["nbr"][:, :n[bk.out_level]]
+            if self.materialize_pairs:
+                indice_dict.defer(bk.key, self._pairs_thunk(a, d, bk, level_ind, n, voxel_coords, batch_size))
         outs = {}
         for st in self.steps:
             if st.export is None:
@@ -486,18 +612,49 @@ class BackboneEngine(object):
             outs[st.export] = t
         return outs, n
 
+    def _pairs_thunk(self, a, d, bk, level_ind, n, voxel_coords, batch_size):
+        """indice_dict[key] = the reference's 5-tuple (conv.py:180-183).  With materialize_pairs=True the pair lists were
+        enqueued with the step; with 'lazy' they are built from the neighbour map / the level's table when the entry is
+        first read (valid, like every view, until the next launch)."""
+        gen = self.arena_gen
+
+        def make():
+            if self.materialize_pairs is not True or d["pairs"] is None:
+                if gen != self.arena_gen:
+                    raise RuntimeError("indice_dict entry read after the arena it pointed into was replaced")
+                if d.get("pairs_step") != a["step"]:  # two indice_keys over one geometry share the tensors
+                    d["pairs_step"] = a["step"]
+                    counts = a["counts"]
+                    n_ptr = [_lib.ctypes.c_void_p(counts.data_ptr() + 4 * i) for i in range(len(a["caps"]))]
+                    with torch.cuda.device(a["device"]):
+                        self._pairs_call(a, d, [voxel_coords] + a["indices"][1:], a["level_cap"], n_ptr, batch_size)
+            return (level_ind[bk.out_level], level_ind[bk.in_level], d["pairs"][:, :, :n[bk.in_level]], d["pair_num"],
+                    self.level_shapes[bk.in_level])
+        return make
+
     def launch_count(self):
-        """Kernels of libfv2p_b200 enqueued by one launch(): rulebook chains + one fused conv per layer."""
-        n = len(self.steps)
-        tc_modes = (_lib.MODE_BF16_TC, _lib.MODE_TF32X3_TC)
-        tc_books = {st.key for st in self.steps if self._mode_for(st) in tc_modes}
-        for bk in self.books:
-            if bk.subm:
-                n += 5 if self.materialize_pairs else 3  # clear, insert, probe (+ scan, compact)
-            else:
-                n += 9 if self.materialize_pairs else 7  # clear, insert, winners, scan, assign, fill, pairs (+2)
-            if self.sort_rows and bk.key in tc_books:  # mask, 3 per 9-bit radix pass, permute, tile masks, ranking
-                n += 4 + 3 * ((bk.kvol + 8) // 9)
+        """Kernels of libfv2p_b200 enqueued by one launch(): one prefill, the level-0 table, 1 launch per submanifold
+        and 3 per strided rulebook, 2 per row grouping, one fused conv per layer (+ the pair lists when they are
+        materialised with the step: counts, scan, compaction, and the input-side probe for strided rulebooks)."""
+        n = len(self.steps) + 2
+        a = self.arena
+        geo = a["geo"] if a is not None else None
+        if geo is None:
+            seen, geo = set(), []
+            tc_modes = (_lib.MODE_BF16_TC, _lib.MODE_TF32X3_TC)
+            tc_books = {st.key for st in self.steps if self._mode_for(st) in tc_modes}
+            for bk in self.books:
+                gk = self._geo_key(bk)
+                if gk not in seen:
+                    seen.add(gk)
+                    geo.append(dict(book=bk, sorted=False))
+                if self.sort_rows and bk.key in tc_books:
+                    [g for g in geo if self._geo_key(g["book"]) == gk][0]["sorted"] = True
+        for d in geo:
+            n += 1 if d["book"].subm else 3
+            n += 2 if d["sorted"] else 0
+            if self.materialize_pairs is True:
+                n += 3 if d["book"].subm else 4
         return n
 
     def __call__(self, voxel_features, voxel_coords, batch_size):

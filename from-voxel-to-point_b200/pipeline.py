@@ -32,7 +32,9 @@ class HotPath(object):
                 backbone.model_cfg['PRECISION'] = precision
             except TypeError:
                 setattr(backbone.model_cfg, 'PRECISION', precision)
-        self.engine = backbone.get_engine()
+        # own engine(s): the pair tensors of indice_dict are built only when somebody reads them (the module API keeps
+        # building them with every step unless MATERIALIZE_PAIRS says otherwise)
+        self.engine = backbone.make_engine(materialize_pairs='lazy')
         self.voxelizer = BatchVoxelizer(voxel_size, point_cloud_range, max_points_per_voxel, max_voxels)
         # lane 0 is the engine the backbone module itself uses; further lanes are built on first use by run_stream
         self._vox_args = (voxel_size, point_cloud_range, max_points_per_voxel, max_voxels)

@@ -8,7 +8,7 @@ Two execution paths, same numbers:
     reference op for op (separate BatchNorm1d / ReLU modules on ``.features``).
 
 Extra, optional model_cfg keys (absent in the reference's YAML, defaults keep its behaviour):
-  PRECISION: 'fp32' (default) | 'bf16';  FUSED: True;  MATERIALIZE_PAIRS: True (fill indice_dict with the
+  PRECISION: 'fp32' (default) | 'bf16';  FUSED: True;  MATERIALIZE_PAIRS: True | 'lazy' | False (fill indice_dict with the
   reference-layout pair tensors; the fused kernels themselves only need the neighbour map);  SORT_ROWS: True
   (process output rows in neighbour-mask order inside the tensor-core kernels; results are unchanged).
 """
@@ -109,14 +109,20 @@ class _BackboneBase(nn.Module):
         out = self.conv_out(x_conv4)
         return dict(x_conv1=x_conv1, x_conv2=x_conv2, x_conv3=x_conv3, x_conv4=x_conv4, out=out)
 
+    def make_engine(self, materialize_pairs=None):
+        """A new BackboneEngine over this module tree with the options of model_cfg (PRECISION, MATERIALIZE_PAIRS,
+        SORT_ROWS, CAP_GROWTH).  materialize_pairs overrides the config when the config does not set it."""
+        mp = self._cfg('MATERIALIZE_PAIRS', True if materialize_pairs is None else materialize_pairs)
+        return BackboneEngine(self, precision=self._cfg('PRECISION', 'fp32'),
+                              materialize_pairs=mp if mp in (True, False, 'lazy') else bool(mp),
+                              sort_rows=bool(self._cfg('SORT_ROWS', True)),
+                              cap_growth=self._cfg('CAP_GROWTH', 'auto'))
+
     def get_engine(self):
         precision = self._cfg('PRECISION', 'fp32')
         eng = getattr(self, '_engine', None)
         if eng is None or eng.precision != precision:
-            eng = BackboneEngine(self, precision=precision,
-                                 materialize_pairs=bool(self._cfg('MATERIALIZE_PAIRS', True)),
-                                 sort_rows=bool(self._cfg('SORT_ROWS', True)),
-                                 cap_growth=self._cfg('CAP_GROWTH', 2.0))
+            eng = self.make_engine()
             object.__setattr__(self, '_engine', eng)  # not a submodule, never in the state_dict
         return eng
 

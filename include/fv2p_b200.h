@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define FV2P_ABI_VERSION 1
+#define FV2P_ABI_VERSION 2
 #define FV2P_MAX_KVOL 32
 
 #define FV2P_OK 0
@@ -114,10 +114,72 @@ FV2P_API int fv2p_mean_vfe(const float *voxels, const int32_t *num_points, int64
                   int num_features, float *out, fv2p_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
- * Rulebooks (indice pairs).  Replace getIndicePair<3> (include/spconv/spconv_ops.h:28-141) and its
- * functors (src/indice.cc, src/indice_cuda.cu, include/spconv/indice.cu.h, geometry.h:25-297).
- * Results are bit-identical to the reference's CPU path (the deterministic one): submanifold pairs
- * ascending by input row inside each offset; strided outputs in first-touch order.
+ * Rulebooks, second generation (round 2): what the convolution reads is the output-major neighbour map
+ * nbr [K, nbr_stride]; the reference-layout pair tensors are built on demand (fv2p_subm_pairs / fv2p_conv_pairs).
+ * Replace getIndicePair<3> (include/spconv/spconv_ops.h:28-141) and its functors (src/indice.cc,
+ * src/indice_cuda.cu, include/spconv/indice.cu.h, geometry.h:25-297).  Results are bit-identical to the reference's
+ * CPU path (the deterministic one).
+ *
+ * A "table" is a caller-owned open-addressing map (b,z,y,x) -> row of fv2p_table_bytes(row_cap) bytes.  The table a
+ * strided rulebook fills for its OUTPUT coordinates is the input table of the next level's submanifold rulebook, so
+ * a backbone builds one table per level.  Calls with FV2P_FLAG_PREFILLED expect their buffers to have been prepared
+ * by ONE fv2p_geometry_prefill launch at the start of the pass (tables cleared, scan states zeroed, -1 fills);
+ * without the flag each call prepares its own buffers first.
+ *   subm_neighbours: odd kernels with dilation 1 probe only offsets k <= K/2 (a hit (i,k)->j is also the pair
+ *                    (j,K-1-k)->i); rows K/2+1..K-1 of `nbr` must hold -1 on entry (FV2P_PREFILL_NBR_MIRROR).
+ *   conv_neighbours: candidates in getValidOutPos order, atomicMin bids, ONE decoupled look-back scan ranks the
+ *                    winners = first-touch output rows (geometry.h:181-187); `nbr` must hold -1 on entry.
+ * ------------------------------------------------------------------------------------------- */
+#define FV2P_FLAG_PREFILLED 1
+
+#define FV2P_PREFILL_TABLE 1      /* ptr = table, a = row_cap                                   */
+#define FV2P_PREFILL_NBR_ALL 2    /* ptr = nbr, a = kvol, b = nbr_stride (multiple of 4): all -1 */
+#define FV2P_PREFILL_NBR_MIRROR 3 /* ptr = nbr, a = kvol, b = nbr_stride: rows K/2+1..K-1 = -1   */
+#define FV2P_PREFILL_CONV_WS 4    /* ptr = conv_neighbours workspace, a = n_in_cap, b = kvol     */
+#define FV2P_PREFILL_GROUP_WS 5   /* ptr = group_rows workspace, a = n_cap                       */
+typedef struct {
+  int32_t kind;
+  int32_t reserved;
+  void *ptr; /* device, 16-byte aligned */
+  int64_t a, b;
+} fv2p_prefill_item;
+
+FV2P_API int fv2p_geometry_prefill(const fv2p_prefill_item *items, int count, fv2p_stream_t stream);
+
+FV2P_API size_t fv2p_table_bytes(int64_t row_cap);
+/* Inserts rows [0, n) of `indices` (level-0 coordinates) into a cleared table. */
+FV2P_API int fv2p_table_build(const int32_t *indices, int64_t n_cap, const int32_t *n_dev, const int32_t *shape3,
+                              void *table, int64_t table_row_cap, int32_t *status_dev, int flags,
+                              fv2p_stream_t stream);
+FV2P_API int fv2p_subm_neighbours(const int32_t *indices, int64_t n_cap, const int32_t *n_dev, int batch,
+                                  const int32_t *shape3, const int32_t *ksize3, const int32_t *dilation3,
+                                  const void *table, int64_t table_row_cap, int32_t *nbr, int64_t nbr_stride,
+                                  int flags, fv2p_stream_t stream);
+FV2P_API size_t fv2p_conv_neighbours_workspace_bytes(int64_t n_in_cap, int kvol);
+FV2P_API int fv2p_conv_neighbours(const int32_t *indices, int64_t n_cap, const int32_t *n_dev, int batch,
+                                  const int32_t *out_shape3, const int32_t *ksize3, const int32_t *stride3,
+                                  const int32_t *pad3, const int32_t *dilation3, int32_t *out_indices,
+                                  int64_t out_cap, int32_t *n_out_dev, void *table, int64_t table_row_cap,
+                                  int32_t *nbr, int64_t nbr_stride, int32_t *status_dev, void *workspace,
+                                  size_t workspace_bytes, int flags, fv2p_stream_t stream);
+/* Reference-layout pair lists on demand: pairs [K,2,pair_stride] (-1 tail up to the live row count), pair_num [K].
+ * subm_pairs reads the neighbour map (mirror-symmetric kernels) or indices + table (other geometries); conv_pairs
+ * reads the input coordinates and the OUTPUT table of the strided rulebook. */
+FV2P_API size_t fv2p_pairs_workspace_bytes(int64_t n_in_cap, int kvol);
+FV2P_API int fv2p_subm_pairs(const int32_t *indices, int64_t n_cap, const int32_t *n_dev, int batch,
+                             const int32_t *shape3, const int32_t *ksize3, const int32_t *dilation3,
+                             const void *table, int64_t table_row_cap, const int32_t *nbr, int64_t nbr_stride,
+                             int32_t *pairs, int64_t pair_stride, int32_t *pair_num, void *workspace,
+                             size_t workspace_bytes, fv2p_stream_t stream);
+FV2P_API int fv2p_conv_pairs(const int32_t *indices, int64_t n_cap, const int32_t *n_dev, int batch,
+                             const int32_t *out_shape3, const int32_t *ksize3, const int32_t *stride3,
+                             const int32_t *pad3, const int32_t *dilation3, const void *table,
+                             int64_t table_row_cap, int32_t *pairs, int64_t pair_stride, int32_t *pair_num,
+                             void *workspace, size_t workspace_bytes, fv2p_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Rulebooks, first-generation entry points (kept; same kernels underneath, each call builds its own table inside
+ * `workspace` and, when asked for them, the pair lists).
  *
  *   indices   device [n_cap,4] int32;  the live row count is *n_dev if n_dev != NULL, else n_cap
  *   pairs     device [K,2,pair_stride] int32 out or NULL; rows >= the live count are not touched
@@ -188,12 +250,19 @@ FV2P_API int fv2p_conv_fwd(const void *features, int64_t n_in_cap, const void *w
                   const int32_t *n_out_dev, int cin, int cout, const float *bias, const float *scale,
                   const float *shift, const void *residual, int relu, int mode, void *out, fv2p_stream_t stream);
 
-/* Row order for the tensor-core conv: stable sort of the output rows by their neighbour mask (bit k = offset k has
- * a neighbour).  perm[t] = output row at sorted position t; nbr_sorted[k][t] = nbr[k][perm[t]] (optional).  Tiles
- * cut from this order need about half the pipeline stages (rows of a tile share their active offsets); the conv
- * result does not change.  tile_order (optional, 2 * ceil(n_cap / 128) int32): (tile, OR of the tile's masks) pairs by
- * descending population count, ties by tile.  No reference counterpart (spconv_ops.h:308-357 works on per-offset
- * pair lists). */
+/* Row order for the tensor-core conv: output rows grouped by a 12-bit digest of their neighbour mask (bit k = offset
+ * k has a neighbour; digest = which x-offsets occur | which (z,y) lines of the kernel have a neighbour; `kx` = extent
+ * of the fastest kernel axis).  perm[t] = output row at position t; nbr_sorted[k][t] = nbr[k][perm[t]] (optional).
+ * Tiles cut from this order need less than half the pipeline stages (rows of a tile share their active offsets); the
+ * conv result does not change, and the order inside a group is whatever the atomic cursors hand out (any permutation
+ * gives bit-identical conv results).  tile_order (optional, 2 * (ceil(n_cap / 128) + 1) int32): (tile, OR of the
+ * tile's masks) pairs by descending population count, ties by tile.  No reference counterpart (spconv_ops.h:308-357
+ * works on per-offset pair lists).  fv2p_sort_rows_by_mask is the first-generation name (kx inferred from kvol). */
+FV2P_API size_t fv2p_group_rows_workspace_bytes(int64_t n_cap);
+FV2P_API int fv2p_group_rows(const int32_t *nbr, int64_t nbr_stride, int kvol, int kx, int64_t n_cap,
+                             const int32_t *n_dev, int32_t *perm, int32_t *nbr_sorted, int64_t sorted_stride,
+                             int32_t *tile_order, void *workspace, size_t workspace_bytes, int flags,
+                             fv2p_stream_t stream);
 FV2P_API size_t fv2p_sort_rows_workspace_bytes(int64_t n_cap);
 FV2P_API int fv2p_sort_rows_by_mask(const int32_t *nbr, int64_t nbr_stride, int kvol, int64_t n_cap,
                                     const int32_t *n_dev, int32_t *perm, int32_t *nbr_sorted,

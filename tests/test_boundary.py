@@ -29,7 +29,7 @@ def test_library_exports_every_header_symbol():
     for s in syms:
         assert hasattr(lib, s), s
     assert sorted(_lib.PROTOTYPES) == syms  # the ctypes table binds exactly the header
-    assert lib.fv2p_abi_version() == 1
+    assert lib.fv2p_abi_version() == 2
 
 
 def test_size_queries_need_no_gpu():

@@ -406,9 +406,21 @@ def test_dense_matches_reference_scatter():
     assert torch.equal(x.dense(), ref)
 
 
+def _digest(masks, kvol=27, kx=3):
+    """The 12-bit grouping key of csrc/sort.cu: [x-offsets that occur | (z,y) lines with a neighbour]."""
+    lines = kvol // kx
+    x_bits = np.zeros_like(masks)
+    line_bits = np.zeros_like(masks)
+    for l in range(lines):
+        seg = (masks >> (l * kx)) & ((1 << kx) - 1)
+        x_bits |= seg
+        line_bits |= (seg != 0).astype(masks.dtype) << l
+    return (x_bits << lines) | line_bits
+
+
 def test_mask_sorted_row_order_gives_identical_results():
-    """fv2p_sort_rows_by_mask only changes which rows share a tile: the conv output must be bit-identical, the
-    order a stable ascending sort of the neighbour masks."""
+    """fv2p_group_rows / fv2p_sort_rows_by_mask only change which rows share a tile: the conv output must be
+    bit-identical.  The order is a grouping by the mask digest (ascending digest, any order inside a group)."""
     rng = np.random.default_rng(3)
     shape = [9, 40, 40]
     ind = synth.random_voxels(shape, 3000, 2, seed=5)
@@ -422,12 +434,14 @@ def test_mask_sorted_row_order_gives_identical_results():
         perm, nbr_sorted, order = spconv.ops.sort_rows_by_mask(nbr, n_out, return_tile_order=True)
         m = nbr.cpu().numpy()
         masks = ((m >= 0).astype(np.int64) << np.arange(27)[:, None]).sum(0)
-        expect = np.argsort(masks, kind="stable")
-        assert np.array_equal(perm.cpu().numpy(), expect)
-        assert np.array_equal(nbr_sorted.cpu().numpy(), m[:, expect])
+        got = perm.cpu().numpy()
+        assert np.array_equal(np.sort(got), np.arange(n_out))  # a permutation of the rows
+        dg = _digest(masks)[got]
+        assert np.all(np.diff(dg) >= 0)  # grouped: ascending digest
+        assert np.array_equal(nbr_sorted.cpu().numpy(), m[:, got])
         # tile list: every 128-row tile once with the OR of its rows' masks, by descending number of active offsets,
         # ties in tile order
-        sm = masks[expect]
+        sm = masks[got]
         tmask = np.array([int(np.bitwise_or.reduce(sm[t:t + 128])) for t in range(0, n_out, 128)])
         weight = np.array([bin(m_).count("1") for m_ in tmask])
         by_weight = np.argsort(-weight, kind="stable")
