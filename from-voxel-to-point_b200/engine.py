@@ -468,9 +468,12 @@ class BackboneEngine(object):
                                             _lib.stream_ptr(device)), "table_build")
             level_ready = {0: mark(main)}
             built, grouped = {}, {}
+            forked = []  # streams that joined this step (a captured step may only be joined by streams it forked)
             for j, d in enumerate(a["geo"]):
                 bk = d["book"]
                 s_side = side[j % len(side)]
+                if s_side not in forked:
+                    forked.append(s_side)
                 if bk.subm:
                     s_side.wait_event(level_ready[bk.in_level])
                     with torch.cuda.stream(s_side):
@@ -505,10 +508,14 @@ class BackboneEngine(object):
                     _lib.check(st, "group_rows[%s]" % bk.key)
                     grouped[id(d)] = mark(s_side)
                 if self.materialize_pairs is True:
+                    if s_pairs not in forked:
+                        forked.append(s_pairs)
                     s_pairs.wait_event(built[id(d)])
                     with torch.cuda.stream(s_pairs):
                         self._pairs_call(a, d, level_ind, level_cap, n_ptr, batch_size)
             waited = set()
+            forked.append(s_conv)
+            s_conv.wait_event(level_ready[0])
             if features_ready is not None:
                 s_conv.wait_event(features_ready)
             for i, (st_, p) in enumerate(zip(self.steps, prm)):
@@ -520,8 +527,9 @@ class BackboneEngine(object):
                 with torch.cuda.stream(s_conv):
                     self.run_conv_step(a, i, p, voxel_features, cap0)
             if self.concurrent:  # join: everything this step enqueued is ordered before what the caller does next
-                for s_ in side + [s_pairs, s_conv]:
-                    main.wait_event(mark(s_))
+                for s_ in forked:
+                    if s_ is not main:
+                        main.wait_event(mark(s_))
         a["level_cap"] = level_cap
         a["step"] = a.get("step", 0) + 1
         return a

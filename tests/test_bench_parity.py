@@ -272,7 +272,7 @@ def test_data_processor_hook_matches_reference_voxelizer_fixture():
     from fv2p_b200.data_processor import DataProcessor
     case = [k[:-len("_points")] for k in g.files if k.endswith("_points")][0]
     cfg = dict(NAME="transform_points_to_voxels", VOXEL_SIZE=g[case + "_voxel_size"].tolist(),
-               MAX_POINTS_PER_VOXEL=int(g[case + "_max_points"]),
+               MAX_POINTS_PER_VOXEL=int(g[case + "_T"]),
                MAX_NUMBER_OF_VOXELS={"train": int(g[case + "_max_voxels"]), "test": int(g[case + "_max_voxels"])})
     dp = DataProcessor([cfg], np.array(g[case + "_range"], np.float32), training=False, device=DEV)
     assert dp.grid_size.tolist() == O.grid_size(cfg["VOXEL_SIZE"], g[case + "_range"]).tolist()
