@@ -198,6 +198,23 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// Split form for software pipelining: the load is issued into `r` without waiting; tmem_ld_wait makes every register
+// of `r` depend on the tcgen05.wait::ld (in/out operands), so no consumer can be scheduled above it.
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t *r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t *r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
+
 // UMMA shared-memory descriptor, K-major, swizzled (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
 // [0,14) start>>4, [16,30) leading byte offset>>4 (1 for swizzled K-major), [32,46) stride byte offset>>4
 // (distance between 8-row groups = 8 * row_bytes), [46,48) version=1, [61,64) layout: 2/4/6 = 128B/64B/32B swizzle.
@@ -241,7 +258,14 @@ __device__ __forceinline__ unsigned long long global_timer() {
 int g_tc_gather_mode = -1;
 int g_tc_pdl = 1;  // programmatic dependent launch of the tensor-core conv kernels (debug switch: fv2p_debug_pdl)
 
-template <bool kTf32, int N>
+// kPacked: rows narrower than 128 bytes (bf16 cin 16/32, fp32 cin 16).  The first generation spent one pipeline stage
+// per kernel offset whatever the row width, and the narrow layers ran at the issue loop's fixed cost per stage
+// (~320 cycles of MMA-thread time + barrier round trips for 8-32 cycles of tensor work; role timers in
+// profiles/r2_notes.md).  Packed stages put G = 128 / row_bytes offsets side by side in ONE 128-byte-swizzled A tile
+// - row r = [x(k0) | x(k1) | ...] - and issue one MMA per 32 bytes of it against that offset's weight image, which for
+// these widths is small enough (<= 108 KB for all 27 offsets) to stay RESIDENT in shared memory: no weight ring, no
+// weight traffic per stage, and 2-4x fewer stages, barriers and commits per tile.
+template <bool kTf32, int N, bool kPacked = false>
 struct Cfg {
   static constexpr int kABytes = kTileM * 128;  // one (up to) 128-byte slice per row
   static constexpr int kWBytes = N * 128;
@@ -252,9 +276,12 @@ struct Cfg {
   // memory is better spent on the A ring: 0.080 ms with 5 A slots, 0.073 with 6, 0.070 with 8).  (One ring of A+W
   // slots was 4 deep at N = 128.)
   static constexpr int kWSlotBytes = (kTf32 ? 2 : 1) * kWBytes;
-  static constexpr int kWStages = (kTf32 && N == 128) ? 2 : 3;
+  static constexpr int kWStages = kPacked ? 0 : ((kTf32 && N == 128) ? 2 : 3);
+  // packed: all (<= 27) offsets' images, sized for the widest packed row (64 bytes: bf16 cin 32 / fp32 cin 16)
+  static constexpr int kMaxPackedKvol = 27;
+  static constexpr int kWResBytes = kPacked ? kMaxPackedKvol * (kTf32 ? 2 : 1) * N * 64 : 0;
   // The scheduler warp streams neighbour-map tiles into a ring of kNbrBufs buffers ahead of the producers.
-  static constexpr int kNbrBufs = N == 128 ? 2 : (N == 64 ? 3 : 4);
+  static constexpr int kNbrBufs = kPacked ? (kWResBytes > 100000 ? 2 : 3) : (N == 128 ? 2 : (N == 64 ? 3 : 4));
   static constexpr int kNbrBytes = kNbrBufs * kNbrBufInts * 4;
   // fp32: the hi product reads the landed fp32 tile straight from shared memory (kind::tf32 ignores the low 13
   // mantissa bits, i.e. hi = trunc(x)); only the correction operand goes through the transform warps and TMEM,
@@ -264,11 +291,13 @@ struct Cfg {
   // gets onto an SM if the conv CTA leaves it some shared memory.  The fp32 128-wide layers come last, when little
   // geometry is left, and take it all.
   static constexpr int kSmemAvail = kSmemLimit - ((kTf32 && N == 128) ? 0 : kSmemGuest);
-  static constexpr int kStagesSmem = (kSmemAvail - kSmemMisc - kNbrBytes - kWStages * kWSlotBytes) / kABytes;
+  static constexpr int kStagesSmem =
+      (kSmemAvail - kSmemMisc - kNbrBytes - kWStages * kWSlotBytes - kWResBytes) / kABytes;
   static constexpr int kStagesTmem = kTf32 ? (512 - 2 * N) / kAColsPerStage : kMaxStages;
   static constexpr int kStagesRaw = kStagesSmem < kStagesTmem ? kStagesSmem : kStagesTmem;
   static constexpr int kStages = kStagesRaw > kMaxStages ? kMaxStages : kStagesRaw;
-  static constexpr int kSmemBytes = kStages * kABytes + kWStages * kWSlotBytes + kNbrBytes + kSmemMisc;
+  static constexpr int kWRegion = kPacked ? kWResBytes : kWStages * kWSlotBytes;
+  static constexpr int kSmemBytes = kStages * kABytes + kWRegion + kNbrBytes + kSmemMisc;
   static constexpr int kTmemCols = kTf32 ? 512 : (2 * N < 32 ? 32 : 2 * N);  // power of two
   static constexpr int kThreads = kTcThreadsBase + (kTf32 ? kXformThreads : 0);
   // Register cap: leaves >= 10 K of the 64 K registers so that one 256-thread geometry CTA (<= 40 registers per
@@ -290,31 +319,33 @@ struct Epilogue {
   int relu;
 };
 
-template <bool kTf32, int N>
-__global__ void __launch_bounds__((Cfg<kTf32, N>::kThreads)) __maxnreg__((Cfg<kTf32, N>::kMaxRegs))
+template <bool kTf32, int N, bool kPacked>
+__global__ void __launch_bounds__((Cfg<kTf32, N, kPacked>::kThreads)) __maxnreg__((Cfg<kTf32, N, kPacked>::kMaxRegs))
 conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restrict__ feat_ptr,
                const uint8_t *__restrict__ wpacked,
                const int *__restrict__ nbr, int64_t nbr_stride, const int *__restrict__ row_perm,
                const int *__restrict__ tile_order, int *sched, int kvol, int64_t n_out_cap,
                const int *__restrict__ n_out_dev, int cin, int oob_row, int use_tma_arg, Epilogue ep) {
-  using C = Cfg<kTf32, N>;
+  using C = Cfg<kTf32, N, kPacked>;
   constexpr int kElem = kTf32 ? 4 : 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t *stage_base = smem;                               // A ring
-  uint8_t *w_base = smem + C::kStages * C::kABytes;         // W ring
-  int *nbr_s = reinterpret_cast<int *>(w_base + C::kWStages * C::kWSlotBytes);
+  uint8_t *w_base = smem + C::kStages * C::kABytes;         // W ring, or the resident images (packed)
+  int *nbr_s = reinterpret_cast<int *>(w_base + C::kWRegion);
   uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(nbr_s) + C::kNbrBytes);
   // barrier layout: full[kStages], empty[kStages], landed[kStages] (fp32 only), tmem_full[2], tmem_empty[2],
-  // nbr_full[kNbrBufs], nbr_empty[kNbrBufs], w_full[kWStages], w_empty[kWStages]
+  // nbr_full[kNbrBufs], nbr_empty[kNbrBufs], w_full[max(kWStages, 1)] (packed: [0] = the resident images have landed)
+  constexpr int kWBars = C::kWStages > 0 ? C::kWStages : 1;
   const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * C::kStages;
   const uint32_t bar_landed = bar_empty + 8 * C::kStages;
   const uint32_t bar_tfull = bar_landed + 8 * C::kStages, bar_tempty = bar_tfull + 16;
   const uint32_t bar_nfull = bar_tempty + 16, bar_nempty = bar_nfull + 8 * C::kNbrBufs;
-  const uint32_t bar_wfull = bar_nempty + 8 * C::kNbrBufs, bar_wempty = bar_wfull + 8 * C::kWStages;
+  const uint32_t bar_wfull = bar_nempty + 8 * C::kNbrBufs;
   volatile int *stage_flags =
-      reinterpret_cast<volatile int *>(bars + 3 * C::kStages + 4 + 2 * C::kNbrBufs + 2 * C::kWStages);  // [kStages]
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(const_cast<int *>(stage_flags + C::kStages));
+      reinterpret_cast<volatile int *>(bars + 3 * C::kStages + 4 + 2 * C::kNbrBufs + kWBars);  // [kStages]
+  volatile int *stage_ks = stage_flags + C::kStages;  // [kStages] packed: the stage's offsets, one byte each (0xFF = none)
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(const_cast<int *>(stage_ks + C::kStages));
   volatile int *tile_ring = reinterpret_cast<volatile int *>(tmem_slot + 1);  // [kTileRing] tile id per sequence no.
   volatile int *tile_info = tile_ring + kTileRing;                            // [kNbrBufs][2]: tile id, offset mask
 
@@ -335,10 +366,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
   int n_out = n_out_dev ? *n_out_dev : (int)n_out_cap;
   if (n_out > n_out_cap) n_out = (int)n_out_cap;
   const int n_tiles = (n_out + kTileM - 1) / kTileM;
-  const int row_bytes = min(cin * kElem, 128);   // bytes of one row consumed per stage (= TMA box width)
-  const int slices = (cin * kElem) / row_bytes;  // stages per kernel offset
+  // w_row_bytes: bytes of one input row consumed per MMA group = row pitch of a weight image (= TMA box width);
+  // row_bytes: row pitch of the A tile - the same, except packed stages, whose 128-byte rows hold kGroup offsets.
+  const int w_row_bytes = min(cin * kElem, 128);
+  const int row_bytes = kPacked ? 128 : w_row_bytes;
+  const int slices = kPacked ? 1 : (cin * kElem) / w_row_bytes;  // stages per kernel offset
+  const int group = kPacked ? 128 / w_row_bytes : 1;             // offsets per stage
   const uint32_t a_stage_bytes = (uint32_t)kTileM * row_bytes;
-  const uint32_t w_stage_bytes = (uint32_t)N * row_bytes;
+  const uint32_t w_stage_bytes = (uint32_t)N * w_row_bytes;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::kStages; ++s) {
@@ -350,17 +385,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
       mbar_init(bar_empty + 8 * s, 1);
       mbar_init(bar_landed + 8 * s, a_arrivals);
     }
-    for (int w = 0; w < C::kWStages; ++w) {
-      mbar_init(bar_wfull + 8 * w, 1);   // the expect_tx arrive of the warp that issues the bulk copy
-      mbar_init(bar_wempty + 8 * w, 1);  // tcgen05.commit
-    }
+    // W slots are released by the same tcgen05.commit as the A slot of the stage that used them (bar_empty): one
+    // commit per stage instead of two
+    for (int w = 0; w < kWBars; ++w) mbar_init(bar_wfull + 8 * w, 1);  // the expect_tx arrive of the bulk copy's issuer
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
       mbar_init(bar_tempty + 8 * a, kEpiThreads);
     }
     for (int b = 0; b < C::kNbrBufs; ++b) {
       mbar_init(bar_nfull + 8 * b, 1);            // the scheduler's (expect_tx) arrive; bulk copies complete the bytes
-      mbar_init(bar_nempty + 8 * b, kProdWarps + 1);  // every producer warp and the W loader are done with the buffer
+      // every producer warp and (with a weight ring) the W loader are done with the buffer
+      mbar_init(bar_nempty + 8 * b, kProdWarps + (kPacked ? 0 : 1));
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&feat_map) : "memory");
@@ -429,6 +464,68 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
       tm_tiles += 1;
 #endif
       if (mask == 0u) mask = 1u;  // a tile nothing feeds still has to produce (zero) accumulators
+      if constexpr (kPacked) {
+        // `group` offsets per stage, side by side in the 128-byte rows of the A tile: 16-byte chunk c of row r holds
+        // chunk c % cpo of the input row that feeds r through the (c / cpo)-th offset of the stage.
+        const int cpo = w_row_bytes >> 4;  // chunks per offset: 2 or 4
+        const int my_q = my_chunk / cpo;
+        const uint8_t *src_base = feat + (size_t)(my_chunk % cpo) * 16;
+        const int n_st = (__popc(mask) + group - 1) / group;
+        for (int g = 0; g < n_st; ++g, ++issued) {
+          uint32_t ks = 0xFFFFFFFFu;
+          int my_k = -1;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (q < group && mask) {
+              const int k = __ffs(mask) - 1;
+              mask &= mask - 1;
+              ks = (ks & ~(0xFFu << (8 * q))) | ((uint32_t)k << (8 * q));
+              if (q == my_q) my_k = k;
+            }
+          }
+          const uint32_t s = issued % C::kStages;
+          if ((int)s != my_slot || my_part >= 2) continue;
+          const int rows_here = (s + C::kStages < kProdWarps) ? kTileM / 2 : kTileM;  // rows this warp gathers
+          const int row_base = my_part * rows_here;
+          {
+            TC_T0();
+            mbar_wait(bar_empty + 8 * s, ((issued / C::kStages) & 1) ^ 1);
+            TC_ACC(tm_pwait);
+          }
+          TC_T0();
+          const uint32_t a_u32 = smem_u32(stage_base + (size_t)s * C::kABytes);
+          const uint32_t a_bar = kTf32 ? bar_landed + 8 * s : bar_full + 8 * s;
+          if (lane == 0 && my_part == 0) {
+            stage_flags[s] = (g == 0 ? kFlagFirst : 0) | (g == n_st - 1 ? kFlagLast : 0);
+            stage_ks[s] = (int)ks;
+            mbar_arrive(a_bar);
+          }
+          __syncwarp();
+          if (my_k >= 0) {  // lanes of an unused slot of the last group copy nothing (no MMA reads those columns)
+            const int rpg = rows_here >> 2;  // rows per 8-lane group
+            const int r_first = row_base + (lane >> 3) * rpg;
+            const int4 *idx4 = reinterpret_cast<const int4 *>(nbr_b + my_k * kTileM + r_first);
+            const uint32_t dst0 = a_u32 + (uint32_t)r_first * 128u;
+            for (int q4 = 0; q4 < (rpg >> 2); ++q4) {
+              const int4 v = idx4[q4];
+              const int srcs[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int r = r_first + 4 * q4 + u;
+                const uint32_t swz = (uint32_t)(my_chunk ^ (r & 7));
+                const int src = srcs[u];
+                cp_async16(dst0 + (uint32_t)(4 * q4 + u) * 128u + (swz << 4),
+                           src_base + (src >= 0 ? (size_t)src * feat_row_bytes : 0), src >= 0 ? 16u : 0u);
+              }
+            }
+          }
+          cp_async_arrive(a_bar);
+          TC_ACC(tm_pissue);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_nempty + 8 * nb);  // this warp no longer reads the tile's neighbour rows
+        continue;
+      }
       const uint32_t first_k = __ffs(mask) - 1;
       const uint32_t last_k = 31 - __clz(mask);
       while (mask) {
@@ -614,14 +711,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
     (void)idesc_corr;
     const uint32_t sbo = 8u * (uint32_t)row_bytes;
     const uint32_t layout = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
+    const uint32_t w_sbo = 8u * (uint32_t)w_row_bytes;
+    const uint32_t w_layout = w_row_bytes == 128 ? 2u : (w_row_bytes == 64 ? 4u : 6u);
     const int ksteps = row_bytes >> 5;  // 32 bytes of K per MMA (16 bf16 / 8 tf32)
     // This loop is a single thread's instruction stream, so it is kept short: the descriptor of a slot is the
     // descriptor of slot 0 plus a constant in the 16-byte start-address field (no carry: smem is < 256 KB).
     const uint64_t a_desc0 = smem_desc(smem_u32(stage_base), sbo, layout);
-    const uint64_t w_desc0 = smem_desc(smem_u32(w_base), sbo, layout);
+    const uint64_t w_desc0 = smem_desc(smem_u32(w_base), w_sbo, w_layout);
     constexpr uint64_t kStageStep = (uint64_t)(C::kABytes >> 4);
     constexpr uint64_t kWSlotStep = (uint64_t)(C::kWSlotBytes >> 4);
     const uint64_t w_lo_off = (uint64_t)(w_stage_bytes >> 4);
+    const uint64_t w_img_step = (uint64_t)((w_stage_bytes * (kTf32 ? 2u : 1u)) >> 4);  // packed: one offset's image(s)
+    const int kpo_shift = (w_row_bytes >> 5) - 1;  // packed: MMA K steps per offset = 1 << kpo_shift (1 or 2)
+    (void)w_img_step, (void)kpo_shift, (void)kWSlotStep;
     const uint32_t a_tmem0 = tmem_base + 2u * (uint32_t)N;  // fp32: TMEM ring of split A tiles behind the accumulators
     // One elected thread runs the whole loop on its own (waits included).  Re-electing per stage with the warp
     // waiting and re-synchronising around the issue costs ~300 cycles per stage and ~50 per tcgen05.mma
@@ -634,6 +736,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
       TC_TIMER_DECL(tm_mfull);
       TC_TIMER_DECL(tm_mtmem);
       TC_TIMER_DECL(tm_missue);
+      if constexpr (kPacked) mbar_wait(bar_wfull, 0);  // the resident weight images
       for (;;) {
         {
           TC_T0();
@@ -657,33 +760,56 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
 #endif
           break;
         }
-        {
-          TC_T0();
-          mbar_wait(bar_wfull + 8 * ws, wphase);  // the stage's weight slice
-          TC_ACC(tm_mfull);
-        }
-        tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * (uint32_t)N;
         uint32_t accumulate = (flags & kFlagFirst) ? 0u : 1u;
-        if (dbg != 4) {
+        if constexpr (kPacked) {
+          // one MMA per 32 bytes of the A row: K step t belongs to the (t >> kpo_shift)-th offset of the stage and
+          // reads that offset's resident weight image
+          const uint32_t ks = (uint32_t)stage_ks[s];
+          if (dbg != 4) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (j < ksteps) {
-              const uint64_t adv = (uint64_t)(2 * j);  // 32 bytes of K
-              if constexpr (kTf32) {
-                // 8 input channels per step: hi*hi as tf32, both correction terms as one bf16 MMA of K = 16
-                const uint32_t a_cols = a_tmem0 + s * (uint32_t)C::kAColsPerStage + 8u * (uint32_t)j;
-                tc_mma_ts_f16(d_tmem, a_cols, b_desc + w_lo_off + adv, idesc_corr, accumulate);
-                tc_mma<true>(d_tmem, a_desc + adv, b_desc + adv, idesc, 1u);
-              } else {
-                tc_mma<false>(d_tmem, a_desc + adv, b_desc + adv, idesc, accumulate);
+            for (int t = 0; t < 4; ++t) {
+              const uint32_t k = (ks >> (8 * (t >> kpo_shift))) & 0xFFu;
+              if (k != 0xFFu) {
+                const uint64_t b = w_desc0 + (uint64_t)k * w_img_step + (uint64_t)(2 * (t & ((1 << kpo_shift) - 1)));
+                const uint64_t adv = (uint64_t)(2 * t);
+                if constexpr (kTf32) {
+                  const uint32_t a_cols = a_tmem0 + s * (uint32_t)C::kAColsPerStage + 8u * (uint32_t)t;
+                  tc_mma_ts_f16(d_tmem, a_cols, b + w_lo_off, idesc_corr, accumulate);
+                  tc_mma<true>(d_tmem, a_desc + adv, b, idesc, 1u);
+                } else {
+                  tc_mma<false>(d_tmem, a_desc + adv, b, idesc, accumulate);
+                }
+                accumulate = 1u;
               }
-              accumulate = 1u;
+            }
+          }
+        } else {
+          {
+            TC_T0();
+            mbar_wait(bar_wfull + 8 * ws, wphase);  // the stage's weight slice
+            TC_ACC(tm_mfull);
+          }
+          tc_fence_after();
+          if (dbg != 4) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (j < ksteps) {
+                const uint64_t adv = (uint64_t)(2 * j);  // 32 bytes of K
+                if constexpr (kTf32) {
+                  // 8 input channels per step: hi*hi as tf32, both correction terms as one bf16 MMA of K = 16
+                  const uint32_t a_cols = a_tmem0 + s * (uint32_t)C::kAColsPerStage + 8u * (uint32_t)j;
+                  tc_mma_ts_f16(d_tmem, a_cols, b_desc + w_lo_off + adv, idesc_corr, accumulate);
+                  tc_mma<true>(d_tmem, a_desc + adv, b_desc + adv, idesc, 1u);
+                } else {
+                  tc_mma<false>(d_tmem, a_desc + adv, b_desc + adv, idesc, accumulate);
+                }
+                accumulate = 1u;
+              }
             }
           }
         }
-        tc_commit(bar_empty + 8 * s);    // both ring slots are reusable once these MMAs retire
-        tc_commit(bar_wempty + 8 * ws);
+        tc_commit(bar_empty + 8 * s);  // the A slot AND the W slot of this stage are reusable once these MMAs retire
         if (flags & kFlagLast) {
           tc_commit(bar_tfull + 8 * acc);  // accumulator complete
           acc ^= 1u;
@@ -695,11 +821,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
           phase ^= 1;
           a_desc = a_desc0;
         }
-        b_desc += kWSlotStep;
-        if (++ws == (uint32_t)C::kWStages) {
-          ws = 0;
-          wphase ^= 1;
-          b_desc = w_desc0;
+        if constexpr (!kPacked) {
+          b_desc += kWSlotStep;
+          if (++ws == (uint32_t)C::kWStages) {
+            ws = 0;
+            wphase ^= 1;
+            b_desc = w_desc0;
+          }
         }
         TC_ACC(tm_missue);
       }
@@ -712,27 +840,41 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
     // barrier, so the W ring may be shallower than the A ring without a parity wait ever being two phases ahead.
     if (elect_one_sync()) {
       const uint32_t wb = w_stage_bytes * (kTf32 ? 2 : 1);
-      uint32_t n = 0;
-      for (uint32_t seq = 0;; ++seq) {
-        const uint32_t nb = seq % C::kNbrBufs;
-        mbar_wait(bar_nfull + 8 * nb, (seq / C::kNbrBufs) & 1);
-        const int tile = tile_info[2 * nb];
-        uint32_t mask = (uint32_t)tile_info[2 * nb + 1];
-        if (tile < 0) break;
-        if (mask == 0u) mask = 1u;
-        while (mask) {
-          const int k = __ffs(mask) - 1;
-          mask &= mask - 1;
-          for (int sl = 0; sl < slices; ++sl, ++n) {
-            const uint32_t w = n % C::kWStages;
-            mbar_wait(bar_wempty + 8 * w, ((n / C::kWStages) & 1) ^ 1);
-            mbar_arrive_expect_tx(bar_wfull + 8 * w, dbg == 3 ? 0u : wb);  // dbg 3: no weight copy
-            if (dbg != 3)
-              bulk_g2s(smem_u32(w_base + (size_t)w * C::kWSlotBytes), wpacked + ((size_t)k * slices + sl) * wb, wb,
-                       bar_wfull + 8 * w);
+      if constexpr (kPacked) {
+        // every offset's image once, resident for the whole kernel (weights do not depend on the previous layer, so
+        // this does not wait for it either)
+        mbar_arrive_expect_tx(bar_wfull, dbg == 3 ? 0u : wb * (uint32_t)kvol);
+        if (dbg != 3)
+          for (int k = 0; k < kvol; ++k)
+            bulk_g2s(smem_u32(w_base + (size_t)k * wb), wpacked + (size_t)k * wb, wb, bar_wfull);
+      } else {
+        uint32_t n = 0;
+        for (uint32_t seq = 0;; ++seq) {
+          const uint32_t nb = seq % C::kNbrBufs;
+          mbar_wait(bar_nfull + 8 * nb, (seq / C::kNbrBufs) & 1);
+          const int tile = tile_info[2 * nb];
+          uint32_t mask = (uint32_t)tile_info[2 * nb + 1];
+          if (tile < 0) break;
+          if (mask == 0u) mask = 1u;
+          while (mask) {
+            const int k = __ffs(mask) - 1;
+            mask &= mask - 1;
+            for (int sl = 0; sl < slices; ++sl, ++n) {
+              const uint32_t w = n % C::kWStages;
+              if (n >= (uint32_t)C::kWStages) {
+                // slot w was last read by stage n - kWStages; that stage's commit (bar_empty of ITS A slot) frees it.
+                // kWStages <= kStages, so the barrier cannot complete another phase before stage n has its weights.
+                const uint32_t m = n - (uint32_t)C::kWStages;
+                mbar_wait(bar_empty + 8 * (m % C::kStages), (m / C::kStages) & 1);
+              }
+              mbar_arrive_expect_tx(bar_wfull + 8 * w, dbg == 3 ? 0u : wb);  // dbg 3: no weight copy
+              if (dbg != 3)
+                bulk_g2s(smem_u32(w_base + (size_t)w * C::kWSlotBytes), wpacked + ((size_t)k * slices + sl) * wb, wb,
+                         bar_wfull + 8 * w);
+            }
           }
+          mbar_arrive(bar_nempty + 8 * nb);
         }
-        mbar_arrive(bar_nempty + 8 * nb);
       }
     }
     __syncwarp();
@@ -839,45 +981,65 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
       const int srow = tile * kTileM + warp * 32 + lane;
       const int row = srow < n_out ? (row_perm ? __ldg(&row_perm[srow]) : srow) : n_out;
       const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * N);
-#pragma unroll 1
-      for (int c0 = 0; c0 < N; c0 += 16) {
-        float v[16];
-        tmem_ld16(taddr + c0, v);  // warp-collective: executed by all lanes even for rows past the end
-        if (row < n_out && dbg != 6) {
+      // Software pipeline over 16-column chunks: while chunk c is scaled and stored, the tcgen05.ld of chunk c+1 and
+      // the residual of chunk c+1 are already in flight.  (Round 1 did load -> wait -> residual load -> store chunk by
+      // chunk: 18-29 k cycles per 128-wide tile, all of it exposed on the last tile of every CTA.)
+      constexpr int kChunks = N / 16;
+      constexpr int kResVecs = kTf32 ? 4 : 2;  // 16-byte vectors of residual per chunk
+      const bool live = row < n_out && dbg != 6;
+      const uint8_t *res_row = static_cast<const uint8_t *>(ep.residual) + (size_t)row * N * kElem;
+      uint8_t *out_row = static_cast<uint8_t *>(ep.out) + (size_t)row * N * kElem;
+      uint32_t acc_regs[2][16];
+      uint4 res_regs[2][kResVecs];
+      tmem_ld16_issue(taddr, acc_regs[0]);  // warp-collective: executed by all lanes even for rows past the end
+      if (live && ep.residual) {
+#pragma unroll
+        for (int q = 0; q < kResVecs; ++q) res_regs[0][q] = __ldg(reinterpret_cast<const uint4 *>(res_row) + q);
+      }
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) {
+        const int c0 = c * 16;
+        uint32_t *cur = acc_regs[c & 1];
+        const uint4 *rcur = res_regs[c & 1];
+        tmem_ld_wait(cur);
+        if (c + 1 < kChunks) {
+          tmem_ld16_issue(taddr + c0 + 16, acc_regs[(c + 1) & 1]);
+          if (live && ep.residual) {
+#pragma unroll
+            for (int q = 0; q < kResVecs; ++q)
+              res_regs[(c + 1) & 1][q] = __ldg(reinterpret_cast<const uint4 *>(res_row + (size_t)(c0 + 16) * kElem) + q);
+          }
+        }
+        if (live) {
+          float v[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            float x = v[i];
+            float x = __uint_as_float(cur[i]);
             if (ep.bias) x += __ldg(&ep.bias[c0 + i]);
             if (ep.scale) x = fmaf(x, __ldg(&ep.scale[c0 + i]), __ldg(&ep.shift[c0 + i]));
             v[i] = x;
           }
           if constexpr (kTf32) {
-            float *o = static_cast<float *>(ep.out) + (size_t)row * N + c0;
             if (ep.residual) {
-              const float4 *rs = reinterpret_cast<const float4 *>(static_cast<const float *>(ep.residual) +
-                                                                 (size_t)row * N + c0);
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
-                float4 t = __ldg(rs + q);
-                v[4 * q] += t.x, v[4 * q + 1] += t.y, v[4 * q + 2] += t.z, v[4 * q + 3] += t.w;
+                v[4 * q] += __uint_as_float(rcur[q].x), v[4 * q + 1] += __uint_as_float(rcur[q].y);
+                v[4 * q + 2] += __uint_as_float(rcur[q].z), v[4 * q + 3] += __uint_as_float(rcur[q].w);
               }
             }
+            float4 *o = reinterpret_cast<float4 *>(out_row + (size_t)c0 * 4);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               float4 t;
               t.x = v[4 * q], t.y = v[4 * q + 1], t.z = v[4 * q + 2], t.w = v[4 * q + 3];
               if (ep.relu) t.x = fmaxf(t.x, 0.f), t.y = fmaxf(t.y, 0.f), t.z = fmaxf(t.z, 0.f), t.w = fmaxf(t.w, 0.f);
-              reinterpret_cast<float4 *>(o)[q] = t;
+              o[q] = t;
             }
           } else {
-            __nv_bfloat16 *o = static_cast<__nv_bfloat16 *>(ep.out) + (size_t)row * N + c0;
             if (ep.residual) {
-              const uint4 *rs = reinterpret_cast<const uint4 *>(static_cast<const __nv_bfloat16 *>(ep.residual) +
-                                                               (size_t)row * N + c0);
 #pragma unroll
               for (int q = 0; q < 2; ++q) {
-                uint4 t = __ldg(rs + q);
-                const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&t);
+                const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&rcur[q]);
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                   float2 f = __bfloat1622float2(h[e]);
@@ -886,6 +1048,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
                 }
               }
             }
+            uint4 *o = reinterpret_cast<uint4 *>(out_row + (size_t)c0 * 2);
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
               uint4 t;
@@ -896,7 +1059,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
                 if (ep.relu) a = fmaxf(a, 0.f), b = fmaxf(b, 0.f);
                 h[e] = __floats2bfloat162_rn(a, b);
               }
-              reinterpret_cast<uint4 *>(o)[q] = t;
+              o[q] = t;
             }
           }
         }
@@ -1024,16 +1187,18 @@ int make_feature_map(CUtensorMap *map, const void *features, int64_t rows, int c
   return 0;
 }
 
-template <bool kTf32, int N>
+int g_tc_packed = 1;  // packed stages for narrow rows (debug switch: fv2p_debug_packed)
+
+template <bool kTf32, int N, bool kPacked>
 int launch_one(const void *features, int64_t feat_rows, const void *weight, const int *nbr, int64_t nbr_stride,
                const int *row_perm, const int *tile_order, int *sched, int kvol, int64_t n_out_cap,
                const int *n_out_dev, int cin, const Epilogue &ep, cudaStream_t stream) {
-  using C = Cfg<kTf32, N>;
+  using C = Cfg<kTf32, N, kPacked>;
   static bool configured[64] = {false};  // the attribute is per device
   const int dev = current_device();
   if (!configured[dev]) {
-    int st = cuda_status(cudaFuncSetAttribute(conv_tc_kernel<kTf32, N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              C::kSmemBytes),
+    int st = cuda_status(cudaFuncSetAttribute(conv_tc_kernel<kTf32, N, kPacked>,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes),
                          "conv_fwd(tc) smem attribute");
     if (st) return st;
     configured[dev] = true;
@@ -1041,11 +1206,11 @@ int launch_one(const void *features, int64_t feat_rows, const void *weight, cons
   CUtensorMap map;
   int st = make_feature_map(&map, features, feat_rows, cin, kTf32);
   if (st) return st;
-  // Measured on B200 (profiles/r1_notes.md): the TMA gather wins for fp32 rows of 128 bytes and more (the LSU
-  // path also has to feed the transform warps there), the swizzled cp.async gather everywhere else.  (A third
-  // producer, LDG + hi/lo split in registers + STS without transform warps, never won and was removed:
-  // 0.182 vs 0.172 ms on 64->64, 0.248 vs 0.221 ms on 128->128.)
-  const int use_tma = g_tc_gather_mode >= 0 ? g_tc_gather_mode : 0;
+  // A-tile producer.  fv2p_tc_gather_mode(1) selects the TMA gather (cp.async.bulk.tensor tile::gather4), which was
+  // measured faster only for fp32 rows of 128 bytes and more on KITTI-sized layers and slower everywhere else
+  // (profiles/r1_notes.md); the default for every shape is the swizzled cp.async gather.  Packed stages always use
+  // the cp.async gather (their rows interleave several offsets).
+  const int use_tma = (!kPacked && g_tc_gather_mode > 0) ? 1 : 0;
   int64_t tiles = (n_out_cap + kTileM - 1) / kTileM;
   int grid = (int)(tiles < sm_count() ? tiles : sm_count());
   if (grid < 1) grid = 1;
@@ -1065,8 +1230,8 @@ int launch_one(const void *features, int64_t feat_rows, const void *weight, cons
   cfg.numAttrs = 1;
   const uint8_t *wp = static_cast<const uint8_t *>(weight);
   const int oob = (int)feat_rows;
-  return cuda_status(cudaLaunchKernelEx(&cfg, conv_tc_kernel<kTf32, N>, map, features, wp, nbr, nbr_stride, row_perm,
-                                        tile_order, sched, kvol, n_out_cap, n_out_dev, cin, oob, use_tma, ep),
+  return cuda_status(cudaLaunchKernelEx(&cfg, conv_tc_kernel<kTf32, N, kPacked>, map, features, wp, nbr, nbr_stride,
+                                        row_perm, tile_order, sched, kvol, n_out_cap, n_out_dev, cin, oob, use_tma, ep),
                      "conv_fwd(tc)");
 }
 
@@ -1087,17 +1252,28 @@ int launch_conv_tc(const void *features, int64_t feat_rows, const void *weight, 
   }
   Epilogue ep{bias, scale, shift, residual, out, relu};
   const bool tf32 = mode == FV2P_MODE_TF32X3_TC;
-#define FV2P_TC(NN)                                                                                            \
-  return tf32 ? launch_one<true, NN>(features, feat_rows, weight, nbr, nbr_stride, row_perm, tile_order, sched,  \
-                                     kvol, n_out_cap, n_out_dev, cin, ep, stream)                                \
-              : launch_one<false, NN>(features, feat_rows, weight, nbr, nbr_stride, row_perm, tile_order, sched, \
-                                      kvol, n_out_cap, n_out_dev, cin, ep, stream)
+  // packed stages: rows narrower than 128 bytes whose 27 weight images fit the resident area
+  const int row_bytes_in = cin * (tf32 ? 4 : 2);
+  const bool packed = g_tc_packed && row_bytes_in < 128 && kvol <= 27 && (tf32 ? cout <= 32 : cout <= 64);
+#define FV2P_TC_ARGS features, feat_rows, weight, nbr, nbr_stride, row_perm, tile_order, sched, kvol, n_out_cap, n_out_dev, cin, ep, stream
+#define FV2P_TC(NN) return tf32 ? launch_one<true, NN, false>(FV2P_TC_ARGS) : launch_one<false, NN, false>(FV2P_TC_ARGS)
+#define FV2P_TCP(NN) return tf32 ? launch_one<true, NN, true>(FV2P_TC_ARGS) : launch_one<false, NN, true>(FV2P_TC_ARGS)
+  if (packed) {
+    switch (cout) {
+      case 16: FV2P_TCP(16);
+      case 32: FV2P_TCP(32);
+      default:  // 64, bf16 only
+        return launch_one<false, 64, true>(FV2P_TC_ARGS);
+    }
+  }
   switch (cout) {
     case 16: FV2P_TC(16);
     case 32: FV2P_TC(32);
     case 64: FV2P_TC(64);
     default: FV2P_TC(128);
   }
+#undef FV2P_TCP
+#undef FV2P_TC_ARGS
 #undef FV2P_TC
 }
 
@@ -1108,6 +1284,11 @@ using namespace fv2p;
 extern "C" int fv2p_tc_gather_mode(int mode) {
   g_tc_gather_mode = mode < 0 ? -1 : (mode > 1 ? 1 : mode);
   return FV2P_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int fv2p_debug_packed(int v) {
+  g_tc_packed = v ? 1 : 0;
+  return 0;
 }
 
 extern "C" __attribute__((visibility("default"))) int fv2p_debug_pdl(int v) {

@@ -243,6 +243,11 @@ class BackboneEngine(object):
             scale = shift = None
             if st.bn is not None:
                 scale, shift = fold_bn(st.bn)
+                if bias is not None:
+                    # (acc + bias) * scale + shift == acc * scale + (bias * scale + shift): one fused multiply-add and
+                    # two parameter loads per output element in the epilogue instead of three
+                    shift = (bias * scale + shift).contiguous()
+                    bias = None
             mode = self._mode_for(st)
             packed = None
             if mode in (_lib.MODE_BF16_TC, _lib.MODE_TF32X3_TC):
