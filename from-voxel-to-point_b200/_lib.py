@@ -73,6 +73,11 @@ PROTOTYPES = {
     "fv2p_height_compression_workspace_bytes": (_c_sz, [_c_int, _c_vp]),
     "fv2p_height_compression": (_c_int, [_c_vp, _c_vp, _c_i64, _c_vp, _c_int, _c_int, _c_vp, _c_int, _c_vp, _c_vp, _c_sz,
                                          _c_vp]),
+    "fv2p_voxel_three_nn_workspace_bytes": (_c_sz, [_c_int, _c_i64]),
+    "fv2p_voxel_three_nn": (_c_int, [_c_vp, _c_i64, _c_vp, _c_i64, _c_vp, _c_int, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp,
+                                     _c_vp, _c_vp, _c_vp, _c_int, _c_vp, _c_vp, _c_sz, _c_vp]),
+    "fv2p_voxel_query": (_c_int, [_c_i64, _c_vp, _c_int, ctypes.c_float, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64,
+                                  _c_vp, _c_vp]),
     "fv2p_copy_rows": (_c_int, [_c_vp, _c_vp, _c_i64, _c_i64, _c_vp, _c_vp]),
     "fv2p_cast_f32_to_bf16": (_c_int, [_c_vp, _c_vp, _c_i64, _c_vp]),
     "fv2p_cast_bf16_to_f32": (_c_int, [_c_vp, _c_vp, _c_i64, _c_vp]),

@@ -622,6 +622,8 @@ class BackboneEngine(object):
             t = SparseConvTensor(a["bufs"][st.out_buf][:n[st.out_level]], level_ind[st.out_level],
                                  self.level_shapes[st.out_level], batch_size)
             t.indice_dict, t.nbr_dict = indice_dict, nbr_dict
+            # the level's coordinate table (rows of t.indices), for pointops.voxel_three_nn / voxel_query
+            t.fv2p_table = (a["tables"][st.out_level], a["caps"][st.out_level])
             outs[st.export] = t
         return outs, n
 

@@ -308,6 +308,41 @@ FV2P_API int fv2p_height_compression(const void *features, const int32_t *indice
                             int elem_bytes, void *spatial_features, void *workspace, size_t workspace_bytes,
                             fv2p_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Consumers of the sparse outputs, on the level's coordinate table instead of dense grids.
+ *
+ * fv2p_voxel_three_nn: front end of ResidualVoxelToPointDecoder.forward
+ * (pcdet/models/backbones_3d/pfe/residual_v2p_decoder.py:86-116): for every query point the three nearest voxel
+ * CENTRES of its own frame (get_voxel_centers, pcdet/utils/common_utils.py:76-92; three_nn,
+ * pcdet/ops/pointnet2/pointnet2_batch/src/interpolate_gpu.cu:16-58, which scans every voxel per query), and
+ * optionally the inverse-distance interpolation of the voxel features (top3_interpolate,
+ * pointnet2_batch/pointnet2_utils.py:292-326; three_interpolate, interpolate_gpu.cu:78-100).
+ *   point_coords  device [P,4] fp32 (batch, x, y, z)        (bottom_point_coords)
+ *   voxel_indices device [n_cap,4] int32 (batch, z, y, x), frames contiguous; live rows *n_dev or n_cap
+ *   table         the level's table (rows of voxel_indices), shape3 = the level's (D,H,W)
+ *   voxel_size3   host fp32 (x,y,z), ALREADY multiplied by the level's downsample factor; range_min3 host fp32 (x,y,z)
+ *   dist [P,3] fp32 (sqrt of the squared distance, like ThreeNN.forward), idx [P,3] int32 = row inside the point's
+ *   frame (the reference searches one frame at a time); either may be NULL
+ *   interpolated [P,channels] fp32 out or NULL; features [n_cap,channels] fp32
+ * Indices and distances are bit-identical to the reference kernel (ties by lowest row).
+ *
+ * fv2p_voxel_query: voxel_query_kernel_stack (pcdet/ops/pointnet2/pointnet2_stack/src/voxel_query_gpu.cu:10-88) with
+ * the dense point_indices grid of generate_voxel2pinds (pcdet/utils/spconv_utils.py:13-21) replaced by the table:
+ * same cells in the same order, first nsample hits within `radius`, idx[0] = -1 for an empty ball.
+ *   shape3 = (Z,Y,X) of the grid; range3 = (z_range, y_range, x_range); new_xyz [M,3], xyz [N,3] fp32;
+ *   new_coords [M,4] int32 (batch,z,y,x); idx [M,nsample] int32 out (every entry is written)
+ * ------------------------------------------------------------------------------------------- */
+FV2P_API size_t fv2p_voxel_three_nn_workspace_bytes(int batch, int64_t n_points);
+FV2P_API int fv2p_voxel_three_nn(const float *point_coords, int64_t n_points, const int32_t *voxel_indices,
+                                 int64_t n_cap, const int32_t *n_dev, int batch, const int32_t *shape3,
+                                 const void *table, int64_t table_row_cap, const float *voxel_size3,
+                                 const float *range_min3, float *dist, int32_t *idx, const float *features,
+                                 int channels, float *interpolated, void *workspace, size_t workspace_bytes,
+                                 fv2p_stream_t stream);
+FV2P_API int fv2p_voxel_query(int64_t m, const int32_t *shape3, int nsample, float radius, const int32_t *range3,
+                              const float *new_xyz, const float *xyz, const int32_t *new_coords, const void *table,
+                              int64_t table_row_cap, int32_t *idx, fv2p_stream_t stream);
+
 /* Copies the live rows (count on the device) of a capacity-sized row buffer; row_bytes must be a multiple of 16.
  * Used to snapshot a step's result so that its D2H copy overlaps the next step. */
 FV2P_API int fv2p_copy_rows(const void *src, void *dst, int64_t row_bytes, int64_t n_cap, const int32_t *n_dev,

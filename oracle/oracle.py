@@ -327,3 +327,124 @@ def backbone_forward(name, params, voxel_features, voxel_coords, batch_size, spa
             outs[tag] = (x.features, x.indices, list(x.shape))
     outs["rulebooks"] = {k: v[:3] for k, v in rulebooks.items()}
     return outs
+
+
+# --------------------------------------------------------------------------------------------
+# consumers of the sparse outputs: voxel -> point 3-NN interpolation, voxel query
+# --------------------------------------------------------------------------------------------
+def voxel_centers(voxel_coords_zyx, downsample_times, voxel_size, point_cloud_range):
+    """get_voxel_centers (pcdet/utils/common_utils.py:76-92): fp32, (idx + 0.5) * (voxel_size * ds) + range_min."""
+    c = np.asarray(voxel_coords_zyx)[:, [2, 1, 0]].astype(np.float32)
+    vs = (np.asarray(voxel_size, np.float32) * np.float32(downsample_times)).astype(np.float32)
+    lo = np.asarray(point_cloud_range[0:3], np.float32)
+    return ((c + np.float32(0.5)) * vs + lo).astype(np.float32)
+
+
+def three_nn(unknown, known, chunk=2048):
+    """three_nn_kernel_fast (pcdet/ops/pointnet2/pointnet2_batch/src/interpolate_gpu.cu:16-58) + the sqrt of
+    ThreeNN.forward: for every `unknown` row the three `known` rows with the smallest squared distance, ties by
+    lowest index (the kernel scans ascending with strict <).  The differences are rounded to fp32 like the kernel's;
+    squares and sum are carried in float64 (the kernel's fp32 FMA chain differs from this by <= 2 ulp, which only
+    matters for candidates closer than that to a tie).  Fewer than three known rows: distance inf, index 0.
+    Returns (dist [n,3] fp32, idx [n,3] int32, dist2 [n,3] float64)."""
+    unknown = _f32(unknown).reshape(-1, 3)
+    known = _f32(known).reshape(-1, 3)
+    n, m = unknown.shape[0], known.shape[0]
+    d2 = np.full((n, 3), np.inf, np.float64)
+    idx = np.zeros((n, 3), np.int32)
+    if m:
+        for s in range(0, n, chunk):
+            diff = (unknown[s:s + chunk, None, :] - known[None, :, :]).astype(np.float32).astype(np.float64)
+            d = (diff * diff).sum(-1)
+            order = np.argsort(d, axis=1, kind="stable")[:, :3]
+            k = order.shape[1]
+            d2[s:s + chunk, :k] = np.take_along_axis(d, order, 1)
+            idx[s:s + chunk, :k] = order
+    return np.sqrt(d2).astype(np.float32), idx, d2
+
+
+def top3_interpolate(xyz, new_xyz, feats):
+    """top3_interpolate (pcdet/ops/pointnet2/pointnet2_batch/pointnet2_utils.py:292-326): inverse-distance weights
+    over the three nearest `xyz` of every `new_xyz`, weighted sum of `feats` (three_interpolate,
+    interpolate_gpu.cu:78-100).  Returns (interpolated [M,C] fp32, dist, idx)."""
+    dist, idx, _ = three_nn(new_xyz, xyz)
+    recip = (np.float32(1.0) / (dist + np.float32(1e-8))).astype(np.float32)
+    norm = recip.sum(1, keepdims=True, dtype=np.float32)
+    w = (recip / norm).astype(np.float32)
+    feats = _f32(feats)
+    if feats.shape[0] == 0:
+        return np.zeros((dist.shape[0], feats.shape[1]), np.float32), dist, idx
+    out = (w[:, 0:1] * feats[idx[:, 0]] + w[:, 1:2] * feats[idx[:, 1]] + w[:, 2:3] * feats[idx[:, 2]])
+    return out.astype(np.float32), dist, idx
+
+
+def voxel_to_point_interpolate(voxel_indices, voxel_feats, point_coords, batch_size, voxel_size, point_cloud_range,
+                               downsample_times):
+    """Steps 1-3 of ResidualVoxelToPointDecoder.forward (residual_v2p_decoder.py:86-116): per frame, centres of the
+    frame's voxels, 3-NN of the frame's points, interpolation.  voxel_indices [N,4] (b,z,y,x), point_coords [P,4]
+    (b,x,y,z).  Returns (feats [P,C], dist [P,3], idx [P,3] frame-local)."""
+    voxel_indices = _i32(voxel_indices)
+    point_coords = _f32(point_coords)
+    voxel_feats = _f32(voxel_feats)
+    out = np.zeros((point_coords.shape[0], voxel_feats.shape[1]), np.float32)
+    dist = np.zeros((point_coords.shape[0], 3), np.float32)
+    idx = np.zeros((point_coords.shape[0], 3), np.int32)
+    for b in range(int(batch_size)):
+        vm = voxel_indices[:, 0] == b
+        pm = point_coords[:, 0].astype(np.int64) == b
+        xyz = voxel_centers(voxel_indices[vm][:, 1:4], downsample_times, voxel_size, point_cloud_range)
+        o, d, i = top3_interpolate(xyz, point_coords[pm][:, 1:4], voxel_feats[vm])
+        out[pm], dist[pm], idx[pm] = o, d, i
+    return out, dist, idx
+
+
+def voxel2pinds(indices, spatial_shape, batch_size):
+    """generate_voxel2pinds (pcdet/utils/spconv_utils.py:13-21): dense [B,Z,Y,X] int32 grid of row ids, -1 elsewhere."""
+    indices = _i32(indices)
+    grid = -np.ones([int(batch_size)] + [int(s) for s in spatial_shape], np.int32)
+    grid[indices[:, 0], indices[:, 1], indices[:, 2], indices[:, 3]] = np.arange(indices.shape[0], dtype=np.int32)
+    return grid
+
+
+def voxel_query(max_range, radius, nsample, xyz, new_xyz, new_coords, point_indices):
+    """voxel_query_kernel_stack (pcdet/ops/pointnet2/pointnet2_stack/src/voxel_query_gpu.cu:10-88) + the empty-ball
+    handling of VoxelQuery.forward (voxel_query_utils.py:33-42).  Pure-python loops: small cases only.
+    Returns (idx [M,nsample] int32, empty_ball_mask [M] bool)."""
+    xyz, new_xyz = _f32(xyz), _f32(new_xyz)
+    new_coords = _i32(new_coords)
+    B, R1, R2, R3 = point_indices.shape
+    zr, yr, xr = (int(v) for v in max_range)
+    M = new_coords.shape[0]
+    idx = np.zeros((M, int(nsample)), np.int32)
+    r2 = np.float32(radius) * np.float32(radius)
+    for pt in range(M):
+        b, cz, cy, cx = (int(v) for v in new_coords[pt])
+        cnt = 0
+        for dz in range(-zr, zr + 1):
+            z = cz + dz
+            if z < 0 or z >= R1:
+                continue
+            for dy in range(-yr, yr + 1):
+                y = cy + dy
+                if y < 0 or y >= R2:
+                    continue
+                for dx in range(-xr, xr + 1):
+                    x = cx + dx
+                    if x < 0 or x >= R3:
+                        continue
+                    nb = int(point_indices[b, z, y, x])
+                    if nb < 0:
+                        continue
+                    diff = (xyz[nb] - new_xyz[pt]).astype(np.float32).astype(np.float64)
+                    if float((diff * diff).sum()) > float(r2):
+                        continue
+                    if cnt < nsample:
+                        if cnt == 0:
+                            idx[pt, :] = nb
+                        idx[pt, cnt] = nb
+                        cnt += 1
+        if cnt == 0:
+            idx[pt, 0] = -1
+    empty = idx[:, 0] == -1
+    idx[empty] = 0
+    return idx, empty

@@ -204,3 +204,91 @@ def _namespace():
 
 def to_numpy_params(state_dict):
     return {k: v.detach().cpu().numpy() for k, v in state_dict.items() if v.dtype.is_floating_point}
+
+
+# --------------------------------------------------------------------------------------------
+# reference pointnet2 CUDA kernels (oracle/_ref/libref_pointnet2.so): GPU box only
+# --------------------------------------------------------------------------------------------
+_pn2 = None
+
+
+def have_pointnet2():
+    return build_ref.pointnet2_path() is not None
+
+
+def load_pointnet2():
+    """ctypes handle on the reference's own kernel launchers (C++ mangled names; built by
+    oracle/build_ref.py:build_pointnet2 from pointnet2_batch/src/interpolate_gpu.cu and
+    pointnet2_stack/src/voxel_query_gpu.cu).  They launch on the legacy default stream."""
+    global _pn2
+    if _pn2 is None:
+        import ctypes
+        path = build_ref.pointnet2_path()
+        if path is None:
+            raise FileNotFoundError("oracle/_ref/libref_pointnet2.so missing: run `python oracle/build_ref.py`")
+        lib = ctypes.CDLL(path)
+        vp, ci, cf = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+        lib.three_nn = getattr(lib, "_Z29three_nn_kernel_launcher_fastiiiPKfS0_PfPi")
+        lib.three_nn.argtypes = [ci, ci, ci, vp, vp, vp, vp]
+        lib.three_nn.restype = None
+        lib.three_interpolate = getattr(lib, "_Z38three_interpolate_kernel_launcher_fastiiiiPKfPKiS0_Pf")
+        lib.three_interpolate.argtypes = [ci, ci, ci, ci, vp, vp, vp, vp]
+        lib.three_interpolate.restype = None
+        lib.voxel_query = getattr(lib, "_Z33voxel_query_kernel_launcher_stackiiiiifiiiPKfS0_PKiS2_Pi")
+        lib.voxel_query.argtypes = [ci, ci, ci, ci, ci, cf, ci, ci, ci, vp, vp, vp, vp, vp]
+        lib.voxel_query.restype = None
+        _pn2 = lib
+    return _pn2
+
+
+def ref_three_nn(unknown, known):
+    """ThreeNN.forward (pointnet2_batch/pointnet2_utils.py:107-129) on CUDA tensors [n,3], [m,3] (batch of one, as
+    top3_interpolate calls it).  Returns (dist [n,3] = sqrt(dist2), idx [n,3] int32)."""
+    import torch
+    lib = load_pointnet2()
+    unknown, known = unknown.contiguous(), known.contiguous()
+    n, m = unknown.shape[0], known.shape[0]
+    dist2 = torch.empty((1, n, 3), dtype=torch.float32, device=unknown.device)
+    idx = torch.empty((1, n, 3), dtype=torch.int32, device=unknown.device)
+    torch.cuda.synchronize()
+    lib.three_nn(1, n, m, unknown.data_ptr(), known.data_ptr(), dist2.data_ptr(), idx.data_ptr())
+    torch.cuda.synchronize()
+    return torch.sqrt(dist2)[0], idx[0]
+
+
+def ref_top3_interpolate(xyz, new_xyz, feats):
+    """top3_interpolate (pointnet2_utils.py:292-326) with the reference's kernels: returns [M, Cf]."""
+    import torch
+    lib = load_pointnet2()
+    dist, idx = ref_three_nn(new_xyz, xyz)
+    dist_recip = 1.0 / (dist + 1e-8)
+    norm = torch.sum(dist_recip, dim=1, keepdim=True)
+    weight = (dist_recip / norm).contiguous()
+    feats_b = feats.t().contiguous()  # (Cf, N)
+    c, m = feats_b.shape
+    n = new_xyz.shape[0]
+    out = torch.empty((c, n), dtype=torch.float32, device=feats.device)
+    torch.cuda.synchronize()
+    lib.three_interpolate(1, c, m, n, feats_b.data_ptr(), idx.contiguous().data_ptr(), weight.data_ptr(),
+                          out.data_ptr())
+    torch.cuda.synchronize()
+    return out.t().contiguous(), dist, idx
+
+
+def ref_voxel_query(max_range, radius, nsample, xyz, new_xyz, new_coords, point_indices):
+    """VoxelQuery.forward (pointnet2_stack/voxel_query_utils.py:12-42) with the reference's kernel and its dense
+    [B,Z,Y,X] int32 grid."""
+    import torch
+    lib = load_pointnet2()
+    m = new_coords.shape[0]
+    _, z, y, x = point_indices.shape
+    idx = torch.zeros((m, int(nsample)), dtype=torch.int32, device=xyz.device)
+    zr, yr, xr = max_range
+    torch.cuda.synchronize()
+    lib.voxel_query(m, z, y, x, int(nsample), float(radius), int(zr), int(yr), int(xr),
+                    new_xyz.contiguous().data_ptr(), xyz.contiguous().data_ptr(), new_coords.contiguous().data_ptr(),
+                    point_indices.contiguous().data_ptr(), idx.data_ptr())
+    torch.cuda.synchronize()
+    empty = idx[:, 0] == -1
+    idx[empty] = 0
+    return idx, empty
