@@ -63,8 +63,12 @@ constexpr int kXformThreads = 128;                           // warps 15-18, fp3
 constexpr int kTcThreadsBase = kEpiThreads + kProdThreads + 96;
 constexpr int kMaxStages = 8;
 constexpr int kSmemLimit = 232448;                 // 227 KB of dynamic shared memory per CTA
-constexpr int kSmemGuest = 12288;                  // left free so that a geometry CTA (rulebook, sort) can co-reside
+constexpr int kSmemGuest = 2048;                   // left free so that a geometry CTA (rulebook, grouping) can co-reside
 constexpr int kSmemMisc = 2048;                    // barriers and small rings + 1024-byte alignment slack
+// Epilogue staging: each of the four epilogue warps transposes 16-column chunks of its 32 accumulator rows through
+// shared memory, so that its global accesses are whole contiguous row segments instead of one row per lane.
+constexpr int kEpiRowPitch = 80;                   // 64 bytes of fp32 + 16: 16-byte accesses of 8 rows hit 8 bank groups
+constexpr int kEpiStageBytes = 4 * 32 * kEpiRowPitch;
 constexpr int kNbrBufInts = FV2P_MAX_KVOL * 128;   // one tile of the neighbour map: [offset][128 rows]
 constexpr int kTileRing = 16;  // > kMaxStages + 2: how far the producers can run ahead of the epilogue, in tiles
 constexpr int kFlagFirst = 1, kFlagLast = 2, kFlagStop = 4;
@@ -292,12 +296,12 @@ struct Cfg {
   // geometry is left, and take it all.
   static constexpr int kSmemAvail = kSmemLimit - ((kTf32 && N == 128) ? 0 : kSmemGuest);
   static constexpr int kStagesSmem =
-      (kSmemAvail - kSmemMisc - kNbrBytes - kWStages * kWSlotBytes - kWResBytes) / kABytes;
+      (kSmemAvail - kSmemMisc - kEpiStageBytes - kNbrBytes - kWStages * kWSlotBytes - kWResBytes) / kABytes;
   static constexpr int kStagesTmem = kTf32 ? (512 - 2 * N) / kAColsPerStage : kMaxStages;
   static constexpr int kStagesRaw = kStagesSmem < kStagesTmem ? kStagesSmem : kStagesTmem;
   static constexpr int kStages = kStagesRaw > kMaxStages ? kMaxStages : kStagesRaw;
   static constexpr int kWRegion = kPacked ? kWResBytes : kWStages * kWSlotBytes;
-  static constexpr int kSmemBytes = kStages * kABytes + kWRegion + kNbrBytes + kSmemMisc;
+  static constexpr int kSmemBytes = kStages * kABytes + kWRegion + kNbrBytes + kEpiStageBytes + kSmemMisc;
   static constexpr int kTmemCols = kTf32 ? 512 : (2 * N < 32 ? 32 : 2 * N);  // power of two
   static constexpr int kThreads = kTcThreadsBase + (kTf32 ? kXformThreads : 0);
   // Register cap: leaves >= 10 K of the 64 K registers so that one 256-thread geometry CTA (<= 40 registers per
@@ -333,7 +337,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
   uint8_t *stage_base = smem;                               // A ring
   uint8_t *w_base = smem + C::kStages * C::kABytes;         // W ring, or the resident images (packed)
   int *nbr_s = reinterpret_cast<int *>(w_base + C::kWRegion);
-  uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(nbr_s) + C::kNbrBytes);
+  uint8_t *epi_stage = reinterpret_cast<uint8_t *>(nbr_s) + C::kNbrBytes;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(epi_stage + kEpiStageBytes);
   // barrier layout: full[kStages], empty[kStages], landed[kStages] (fp32 only), tmem_full[2], tmem_empty[2],
   // nbr_full[kNbrBufs], nbr_empty[kNbrBufs], w_full[max(kWStages, 1)] (packed: [0] = the resident images have landed)
   constexpr int kWBars = C::kWStages > 0 ? C::kWStages : 1;
@@ -981,86 +986,107 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
       const int srow = tile * kTileM + warp * 32 + lane;
       const int row = srow < n_out ? (row_perm ? __ldg(&row_perm[srow]) : srow) : n_out;
       const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * N);
-      // Software pipeline over 16-column chunks: while chunk c is scaled and stored, the tcgen05.ld of chunk c+1 and
-      // the residual of chunk c+1 are already in flight.  (Round 1 did load -> wait -> residual load -> store chunk by
-      // chunk: 18-29 k cycles per 128-wide tile, all of it exposed on the last tile of every CTA.)
+      // Per 16-column chunk: tcgen05.ld hands every lane ITS row (32 rows x 16 fp32 per warp); the warp writes them to
+      // its staging buffer and reads them back transposed - lanes side by side along a row - so that every global
+      // access below covers whole contiguous row segments (fp32: 4 lanes x 16 B = the 64 bytes of the chunk, 8 rows per
+      // instruction; bf16: 2 lanes x 16 B, 16 rows per instruction) and a lane needs the folded BatchNorm parameters of
+      // 4 / 8 columns only (2-4 vector loads per chunk instead of 32 scalar ones).  Round 1 had one row per lane all
+      // the way: 32 half-used sectors per load / store instruction and 40 memory instructions per lane and chunk -
+      // the epilogue (18-40 k cycles per 128-wide tile) was busy longer than the contraction it is meant to hide
+      // behind and competed with the gather for the load/store unit.  The tcgen05.ld of chunk c+1 and the residual
+      // of chunk c are in flight while chunk c is transposed.
       constexpr int kChunks = N / 16;
-      constexpr int kResVecs = kTf32 ? 4 : 2;  // 16-byte vectors of residual per chunk
-      const bool live = row < n_out && dbg != 6;
-      const uint8_t *res_row = static_cast<const uint8_t *>(ep.residual) + (size_t)row * N * kElem;
-      uint8_t *out_row = static_cast<uint8_t *>(ep.out) + (size_t)row * N * kElem;
-      uint32_t acc_regs[2][16];
-      uint4 res_regs[2][kResVecs];
-      tmem_ld16_issue(taddr, acc_regs[0]);  // warp-collective: executed by all lanes even for rows past the end
-      if (live && ep.residual) {
+      constexpr int kLanesPerRow = kTf32 ? 4 : 2;          // lanes that share a row segment
+      constexpr int kRowsPerInstr = 32 / kLanesPerRow;     // 8 / 16
+      constexpr int kPasses = 32 / kRowsPerInstr;          // 4 / 2
+      constexpr int kColsPerLane = 16 / kLanesPerRow;      // 4 / 8 columns of the chunk per lane
+      uint8_t *stage = epi_stage + warp * (32 * kEpiRowPitch);
+      const int sub = lane / kLanesPerRow, seg = lane % kLanesPerRow;
+      int grow[kPasses];  // the output row this lane serves in pass q (the row of lane q * kRowsPerInstr + sub)
 #pragma unroll
-        for (int q = 0; q < kResVecs; ++q) res_regs[0][q] = __ldg(reinterpret_cast<const uint4 *>(res_row) + q);
-      }
+      for (int q = 0; q < kPasses; ++q) grow[q] = __shfl_sync(0xFFFFFFFFu, row, q * kRowsPerInstr + sub);
+      const bool body = dbg != 6;
+      uint32_t acc_regs[2][16];
+      tmem_ld16_issue(taddr, acc_regs[0]);  // warp-collective: executed by all lanes even for rows past the end
 #pragma unroll
       for (int c = 0; c < kChunks; ++c) {
         const int c0 = c * 16;
         uint32_t *cur = acc_regs[c & 1];
-        const uint4 *rcur = res_regs[c & 1];
-        tmem_ld_wait(cur);
-        if (c + 1 < kChunks) {
-          tmem_ld16_issue(taddr + c0 + 16, acc_regs[(c + 1) & 1]);
-          if (live && ep.residual) {
+        // residual segments of this chunk: issued before the transposition so that their latency hides behind it
+        uint4 res[kPasses];
+        if (body && ep.residual) {
 #pragma unroll
-            for (int q = 0; q < kResVecs; ++q)
-              res_regs[(c + 1) & 1][q] = __ldg(reinterpret_cast<const uint4 *>(res_row + (size_t)(c0 + 16) * kElem) + q);
-          }
+          for (int q = 0; q < kPasses; ++q)
+            if (grow[q] < n_out)
+              res[q] = __ldg(reinterpret_cast<const uint4 *>(static_cast<const uint8_t *>(ep.residual) +
+                                                             ((size_t)grow[q] * N + c0 + seg * kColsPerLane) * kElem));
         }
-        if (live) {
-          float v[16];
+        tmem_ld_wait(cur);
+        if (c + 1 < kChunks) tmem_ld16_issue(taddr + c0 + 16, acc_regs[(c + 1) & 1]);
+        if (!body) continue;
+        __syncwarp();  // the previous chunk has been read back by every lane
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float x = __uint_as_float(cur[i]);
-            if (ep.bias) x += __ldg(&ep.bias[c0 + i]);
-            if (ep.scale) x = fmaf(x, __ldg(&ep.scale[c0 + i]), __ldg(&ep.shift[c0 + i]));
+        for (int q4 = 0; q4 < 4; ++q4)
+          *reinterpret_cast<uint4 *>(stage + lane * kEpiRowPitch + q4 * 16) =
+              make_uint4(cur[4 * q4], cur[4 * q4 + 1], cur[4 * q4 + 2], cur[4 * q4 + 3]);
+        __syncwarp();
+        // folded BatchNorm (and bias) of this lane's columns
+        float sc[kColsPerLane], sh[kColsPerLane], bi[kColsPerLane];
+#pragma unroll
+        for (int v4 = 0; v4 < kColsPerLane / 4; ++v4) {
+          const int col = c0 + seg * kColsPerLane + 4 * v4;
+          const float4 a = ep.scale ? __ldg(reinterpret_cast<const float4 *>(ep.scale + col)) : make_float4(1, 1, 1, 1);
+          const float4 b = ep.scale ? __ldg(reinterpret_cast<const float4 *>(ep.shift + col)) : make_float4(0, 0, 0, 0);
+          const float4 d = ep.bias ? __ldg(reinterpret_cast<const float4 *>(ep.bias + col)) : make_float4(0, 0, 0, 0);
+          sc[4 * v4] = a.x, sc[4 * v4 + 1] = a.y, sc[4 * v4 + 2] = a.z, sc[4 * v4 + 3] = a.w;
+          sh[4 * v4] = b.x, sh[4 * v4 + 1] = b.y, sh[4 * v4 + 2] = b.z, sh[4 * v4 + 3] = b.w;
+          bi[4 * v4] = d.x, bi[4 * v4 + 1] = d.y, bi[4 * v4 + 2] = d.z, bi[4 * v4 + 3] = d.w;
+        }
+#pragma unroll
+        for (int q = 0; q < kPasses; ++q) {
+          const int r = q * kRowsPerInstr + sub;  // row of the warp's 32
+          float v[kColsPerLane];
+#pragma unroll
+          for (int v4 = 0; v4 < kColsPerLane / 4; ++v4) {
+            const float4 x = *reinterpret_cast<const float4 *>(stage + r * kEpiRowPitch + (seg * kColsPerLane + 4 * v4) * 4);
+            v[4 * v4] = x.x, v[4 * v4 + 1] = x.y, v[4 * v4 + 2] = x.z, v[4 * v4 + 3] = x.w;
+          }
+          if (grow[q] >= n_out) continue;
+#pragma unroll
+          for (int i = 0; i < kColsPerLane; ++i) {
+            float x = v[i];
+            if (ep.bias) x += bi[i];
+            if (ep.scale) x = fmaf(x, sc[i], sh[i]);
             v[i] = x;
           }
+          uint8_t *o = static_cast<uint8_t *>(ep.out) + ((size_t)grow[q] * N + c0 + seg * kColsPerLane) * kElem;
           if constexpr (kTf32) {
             if (ep.residual) {
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                v[4 * q] += __uint_as_float(rcur[q].x), v[4 * q + 1] += __uint_as_float(rcur[q].y);
-                v[4 * q + 2] += __uint_as_float(rcur[q].z), v[4 * q + 3] += __uint_as_float(rcur[q].w);
-              }
+              v[0] += __uint_as_float(res[q].x), v[1] += __uint_as_float(res[q].y);
+              v[2] += __uint_as_float(res[q].z), v[3] += __uint_as_float(res[q].w);
             }
-            float4 *o = reinterpret_cast<float4 *>(out_row + (size_t)c0 * 4);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              float4 t;
-              t.x = v[4 * q], t.y = v[4 * q + 1], t.z = v[4 * q + 2], t.w = v[4 * q + 3];
-              if (ep.relu) t.x = fmaxf(t.x, 0.f), t.y = fmaxf(t.y, 0.f), t.z = fmaxf(t.z, 0.f), t.w = fmaxf(t.w, 0.f);
-              o[q] = t;
-            }
+            float4 t = make_float4(v[0], v[1], v[2], v[3]);
+            if (ep.relu) t.x = fmaxf(t.x, 0.f), t.y = fmaxf(t.y, 0.f), t.z = fmaxf(t.z, 0.f), t.w = fmaxf(t.w, 0.f);
+            *reinterpret_cast<float4 *>(o) = t;
           } else {
             if (ep.residual) {
-#pragma unroll
-              for (int q = 0; q < 2; ++q) {
-                const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&rcur[q]);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  float2 f = __bfloat1622float2(h[e]);
-                  v[8 * q + 2 * e] += f.x;
-                  v[8 * q + 2 * e + 1] += f.y;
-                }
-              }
-            }
-            uint4 *o = reinterpret_cast<uint4 *>(out_row + (size_t)c0 * 2);
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-              uint4 t;
-              __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&t);
+              const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&res[q]);
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                float a = v[8 * q + 2 * e], b = v[8 * q + 2 * e + 1];
-                if (ep.relu) a = fmaxf(a, 0.f), b = fmaxf(b, 0.f);
-                h[e] = __floats2bfloat162_rn(a, b);
+                const float2 f = __bfloat1622float2(h[e]);
+                v[2 * e] += f.x;
+                v[2 * e + 1] += f.y;
               }
-              o[q] = t;
             }
+            uint4 t;
+            __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&t);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float a = v[2 * e], b = v[2 * e + 1];
+              if (ep.relu) a = fmaxf(a, 0.f), b = fmaxf(b, 0.f);
+              h[e] = __floats2bfloat162_rn(a, b);
+            }
+            *reinterpret_cast<uint4 *>(o) = t;
           }
         }
       }

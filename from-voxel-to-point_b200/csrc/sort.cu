@@ -78,27 +78,30 @@ GroupWs carve(void *ws, int64_t n_cap) {
   return w;
 }
 
-// masks, digests and the digest histogram; the last CTA to finish turns the bins into their exclusive scan.
+// masks, digests and the digest histogram; the last CTA to finish turns the bins into their exclusive scan.  The
+// histogram goes straight to the global bins, one atomic per distinct digest per warp: no shared-memory histogram, so
+// the kernel fits next to a persistent conv CTA that has left it only a few KB of shared memory.
 __global__ void __launch_bounds__(kThreads)
 group_hist_kernel(const int *__restrict__ nbr, int64_t nbr_stride, int kvol, int kx, int lines, const int *n_dev,
                   int64_t n_cap, uint32_t *masks, uint16_t *digests, int *bins, int *bin_base, int *done) {
-  __shared__ int hist[kBins];
   __shared__ int scan_smem[kThreads / 32 + 1];
   __shared__ int s_last;
   const int n = live_n(n_dev, n_cap);
-  for (int b = threadIdx.x; b < kBins; b += kThreads) hist[b] = 0;
-  __syncthreads();
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+  const int lane = threadIdx.x & 31;
+  const int n_round = (n + 31) & ~31;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+    const bool live = i < n;
     uint32_t m = 0;
-    for (int k = 0; k < kvol; ++k) m |= (__ldg(&nbr[(size_t)k * nbr_stride + i]) >= 0 ? 1u : 0u) << k;
-    const uint32_t d = mask_digest(m, kvol, kx, lines);
-    masks[i] = m;
-    digests[i] = (uint16_t)d;
-    atomicAdd(&hist[d], 1);
+    if (live)
+      for (int k = 0; k < kvol; ++k) m |= (__ldg(&nbr[(size_t)k * nbr_stride + i]) >= 0 ? 1u : 0u) << k;
+    const int d = live ? (int)mask_digest(m, kvol, kx, lines) : kBins + lane;
+    const unsigned peers = __match_any_sync(0xFFFFFFFFu, d);
+    if (live) {
+      masks[i] = m;
+      digests[i] = (uint16_t)d;
+      if (lane == __ffs(peers) - 1) atomicAdd(&bins[d], __popc(peers));
+    }
   }
-  __syncthreads();
-  for (int b = threadIdx.x; b < kBins; b += kThreads)
-    if (hist[b]) atomicAdd(&bins[b], hist[b]);
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) s_last = atomicAdd(&done[0], 1) == (int)gridDim.x - 1;

@@ -412,9 +412,36 @@ class BackboneEngine(object):
         return total
 
     # ------------------------------------------------------------------ run
-    def launch(self, voxel_features, voxel_coords, batch_size, n0_dev=None, cap0=None, features_ready=None):
+    def _streams(self, device):
+        if self._side is None or self._side[0].device != device:
+            self._side = [torch.cuda.Stream(device=device) for _ in range(self.SIDE_STREAMS + 3)]
+        return self._side[:-3], self._side[-3], self._side[-2], self._side[-1]
+
+    def prefill(self, device, cap0, batch_size):
+        """Enqueues the step's ONE clearing launch (tables, scan states, -1 fills) on a side stream forked from the
+        current stream, so that it runs next to whatever the caller enqueues next (the voxelizer).  Returns the event
+        to hand to launch(prefilled=...).  Nothing of the previous step may still be reading the arena on another
+        stream (launch() joins its streams before it returns)."""
+        a = self._ensure_arena(device, max(int(cap0), 1), int(batch_size))
+        if not self.concurrent:
+            return None
+        s_fill = self._streams(device)[3]
+        main = torch.cuda.current_stream(device)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        s_fill.wait_event(ev)
+        items, n_items = a["prefill"]
+        with torch.cuda.device(device), torch.cuda.stream(s_fill):
+            _lib.check(_lib.load().fv2p_geometry_prefill(items, n_items, _lib.stream_ptr(device)), "geometry_prefill")
+        done = torch.cuda.Event()
+        done.record(s_fill)
+        return done
+
+    def launch(self, voxel_features, voxel_coords, batch_size, n0_dev=None, cap0=None, features_ready=None,
+               prefilled=None):
         """Enqueues geometry + feature passes on the current stream.  No host sync.
         ``features_ready``: event after which voxel_features may be read (None: already ordered on this stream).
+        ``prefilled``: event from prefill() when the clearing launch was already enqueued (None: done here).
 
         voxel_features [>=cap0, F] fp32, voxel_coords [>=cap0, 4] int32, both CUDA and contiguous;
         live row count = *n0_dev (device int32) if given, else cap0 (defaults to voxel_coords.shape[0]).
@@ -435,9 +462,7 @@ class BackboneEngine(object):
         with torch.cuda.device(dev):
             main = torch.cuda.current_stream(device)
             if self.concurrent:
-                if self._side is None or self._side[0].device != device:
-                    self._side = [torch.cuda.Stream(device=device) for _ in range(self.SIDE_STREAMS + 2)]
-                side, s_pairs, s_conv = self._side[:-2], self._side[-2], self._side[-1]
+                side, s_pairs, s_conv, _ = self._streams(device)
             else:
                 side, s_pairs, s_conv = [main], main, main
             counts[len(caps):].zero_()
@@ -447,7 +472,10 @@ class BackboneEngine(object):
             else:
                 counts[0:1].copy_(n0_dev.view(-1)[0:1])
             level_ind = [voxel_coords] + a["indices"][1:]
-            level_cap = [cap0] + caps[1:]
+            # Row capacities as the ARENA knows them, for every geometry call: the library carves its workspaces by the
+            # capacity it is given, and the prefill items were computed from these.  (The voxel buffers may hold fewer
+            # rows than caps[0]; the kernels only touch live rows, and the live count never exceeds either bound.)
+            level_cap = list(caps)
             n_ptr = [_lib.ctypes.c_void_p(counts.data_ptr() + 4 * i) for i in range(len(caps))]
             status_ptr = _lib.ctypes.c_void_p(counts.data_ptr() + 4 * len(caps))
 
@@ -466,8 +494,11 @@ class BackboneEngine(object):
                 ev.record(stream)
                 return ev
 
-            items, n_items = a["prefill"]
-            _lib.check(lib.fv2p_geometry_prefill(items, n_items, _lib.stream_ptr(device)), "geometry_prefill")
+            if prefilled is not None:
+                main.wait_event(prefilled)
+            else:
+                items, n_items = a["prefill"]
+                _lib.check(lib.fv2p_geometry_prefill(items, n_items, _lib.stream_ptr(device)), "geometry_prefill")
             _lib.check(lib.fv2p_table_build(_lib.ptr(voxel_coords), cap0, n_ptr[0], _lib.i32x3(self.level_shapes[0]),
                                             _lib.ptr(a["tables"][0]), caps[0], status_ptr, PRE,
                                             _lib.stream_ptr(device)), "table_build")

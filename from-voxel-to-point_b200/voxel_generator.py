@@ -121,6 +121,10 @@ class BatchVoxelizer(object):
             self.gen += 1
         return b
 
+    def capacity(self, device, total_points, batch, f):
+        """Row capacity of the output buffers a call with these sizes will use (allocates them if needed)."""
+        return self._ensure(device, total_points, batch, f)["cap"]
+
     def __call__(self, points, frame_offsets, max_frame_points=None, features_stream=None):
         """points [P,F] fp32 CUDA, frame_offsets [B+1] int32 CUDA.  Returns a dict of device buffers sized at
         capacity plus 'voxel_offsets' [B+1]; live rows are [:voxel_offsets[B]].
