@@ -153,15 +153,18 @@ __device__ __forceinline__ uint32_t slot_insert(Slot *t, uint32_t mask, unsigned
 }
 
 // Value stored under `key` (read-only table, one 16-byte load per probe), or kValEmpty when the key is absent.
+// The walk is bounded by the table size: a table that overflowed its caller-stated capacity may have no empty slot
+// left, and an absent key must still terminate (the step is then flagged and run again with larger bounds).
 __device__ __forceinline__ int slot_lookup(const Slot *__restrict__ t, uint32_t mask, unsigned long long key) {
   uint32_t s = mix64(key) & mask;
-  while (true) {
+  for (uint32_t probes = 0; probes <= mask; ++probes) {
     const uint4 q = __ldg(reinterpret_cast<const uint4 *>(&t[s]));
     const unsigned long long seen = ((unsigned long long)q.y << 32) | q.x;
     if (seen == key) return (int)q.z;
     if (seen == kEmptyKey) return kValEmpty;
     s = (s + 1) & mask;
   }
+  return kValEmpty;
 }
 
 // ------------------------------------------------------------------------- single-pass ordered scan

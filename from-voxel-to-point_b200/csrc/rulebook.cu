@@ -142,7 +142,7 @@ subm_probe_sym_kernel(const int4 *__restrict__ indices, const int *n_dev, int64_
       if (key[p] != kEmptyKey) {
         uint4 q = first[p];
         uint32_t s = slot[p];
-        while (true) {
+        for (uint32_t probes = 0; probes <= tmask; ++probes) {  // bounded: an overflowed table may be full
           const unsigned long long seen = ((unsigned long long)q.y << 32) | q.x;
           if (seen == key[p]) {
             const int v = (int)q.z;
