@@ -75,9 +75,12 @@ __device__ __forceinline__ float centre(int idx, float vs, float lo) {
   return __fadd_rn(__fmul_rn(__fadd_rn((float)idx, 0.5f), vs), lo);
 }
 
-// interpolate_gpu.cu:44 verbatim (the compiler contracts it the same way in both builds)
+// interpolate_gpu.cu:44 / voxel_query_gpu.cu:63 as nvcc compiles them (SASS of the reference's kernels built for
+// sm_100: FMUL dy*dy, FFMA dx*dx + ., FFMA dz*dz + .).  Spelled with intrinsics: left to the compiler, a loop-invariant
+// square gets hoisted and added unfused, which changes the last bit of the distance.
 __device__ __forceinline__ float dist2_ref(float ux, float uy, float uz, float x, float y, float z) {
-  return (ux - x) * (ux - x) + (uy - y) * (uy - y) + (uz - z) * (uz - z);
+  const float dx = __fsub_rn(ux, x), dy = __fsub_rn(uy, y), dz = __fsub_rn(uz, z);
+  return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
 }
 
 constexpr int kInitIdx = 0x7FFFFFFF;
@@ -258,8 +261,7 @@ voxel_query_kernel(int64_t M, int R1, int R2, int R3, int nsample, float radius,
           const int neighbor_idx = ~v;
           const float x_per = xyz[(size_t)neighbor_idx * 3 + 0], y_per = xyz[(size_t)neighbor_idx * 3 + 1],
                       z_per = xyz[(size_t)neighbor_idx * 3 + 2];
-          const float dist2 = (x_per - new_x) * (x_per - new_x) + (y_per - new_y) * (y_per - new_y) +
-                              (z_per - new_z) * (z_per - new_z);
+          const float dist2 = dist2_ref(x_per, y_per, z_per, new_x, new_y, new_z);
           if (dist2 > radius2) continue;
           if (cnt < nsample) {
             if (cnt == 0)

@@ -438,10 +438,11 @@ class BackboneEngine(object):
         return done
 
     def launch(self, voxel_features, voxel_coords, batch_size, n0_dev=None, cap0=None, features_ready=None,
-               prefilled=None):
+               prefilled=None, run_convs=True):
         """Enqueues geometry + feature passes on the current stream.  No host sync.
         ``features_ready``: event after which voxel_features may be read (None: already ordered on this stream).
         ``prefilled``: event from prefill() when the clearing launch was already enqueued (None: done here).
+        ``run_convs``: False enqueues the geometry pass only (bench.py times it on its own that way).
 
         voxel_features [>=cap0, F] fp32, voxel_coords [>=cap0, 4] int32, both CUDA and contiguous;
         live row count = *n0_dev (device int32) if given, else cap0 (defaults to voxel_coords.shape[0]).
@@ -554,7 +555,7 @@ class BackboneEngine(object):
             s_conv.wait_event(level_ready[0])
             if features_ready is not None:
                 s_conv.wait_event(features_ready)
-            for i, (st_, p) in enumerate(zip(self.steps, prm)):
+            for i, (st_, p) in enumerate(zip(self.steps, prm) if run_convs else ()):
                 d = a["books"][st_.key]
                 ev = grouped[id(d)] if self.conv_operands(a, st_, p)[1] is not None else built[id(d)]
                 if id(ev) not in waited:

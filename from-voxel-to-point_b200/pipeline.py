@@ -94,7 +94,13 @@ class HotPath(object):
             s["dev_pts"][:total].copy_(s["host_pts"][:total], non_blocking=True)
             s["dev_off"].copy_(s["host_off"], non_blocking=True)
         nbytes = total * f * 4 + (len(frames) + 1) * 4
-        return s["dev_pts"][:total], s["dev_off"], max(sizes) if sizes else 0, nbytes
+        s["total"], s["mfp"] = total, max(sizes) if sizes else 0
+        return s["dev_pts"][:total], s["dev_off"], s["mfp"], nbytes
+
+    def staged(self, slot=0):
+        """(points_dev, frame_offsets_dev, max_frame_points) of the batch last uploaded into `slot`."""
+        s = self._slots[slot]
+        return s["dev_pts"][:s["total"]], s["dev_off"], s["mfp"]
 
     # ------------------------------------------------------------------ device step
     def _lane(self, lane):

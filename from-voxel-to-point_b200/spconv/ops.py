@@ -49,9 +49,10 @@ def candidate_fanout(ksize, stride, padding, dilation):
 
 
 def get_indice_pairs(indices, batch_size, spatial_shape, ksize=3, stride=1, padding=0, dilation=1, out_padding=0,
-                     subm=False, transpose=False, grid=None, return_nbr=False):
+                     subm=False, transpose=False, grid=None, return_nbr=False, want_pairs=True):
     """ops.py:46-105.  Returns (outids, indice_pairs [K,2,N] int32, indice_pair_num [K] int32), bit-identical
-    to the reference's CPU path.  With return_nbr=True also returns the output-major neighbour map [K,Nout]."""
+    to the reference's CPU path.  With return_nbr=True also returns the output-major neighbour map [K,Nout];
+    want_pairs=False skips the reference-layout pair lists (both come back as None)."""
     ndim = indices.shape[1] - 1
     ksize, stride, padding, dilation, out_padding = (_listify(v, ndim) for v in
                                                      (ksize, stride, padding, dilation, out_padding))
@@ -77,8 +78,8 @@ def get_indice_pairs(indices, batch_size, spatial_shape, ksize=3, stride=1, padd
         out_cap = max(1, min(n * candidate_fanout(ksize, stride, padding, dilation),
                              int(batch_size) * int(np.prod(out_shape))))
     device = indices.device
-    pairs = torch.empty((kvol, 2, n), dtype=torch.int32, device=device)
-    pair_num = torch.empty((kvol,), dtype=torch.int32, device=device)
+    pairs = torch.empty((kvol, 2, n), dtype=torch.int32, device=device) if want_pairs else None
+    pair_num = torch.empty((kvol,), dtype=torch.int32, device=device) if want_pairs else None
     nbr = torch.empty((kvol, out_cap), dtype=torch.int32, device=device)
     outids = indices if subm else torch.empty((out_cap, 4), dtype=torch.int32, device=device)
     ws_bytes = lib.fv2p_rulebook_workspace_bytes(n, out_cap, kvol) + 256
