@@ -228,7 +228,8 @@ def measure(hp, batches, device, steps, warmup, flush, barrier):
 
 
 def serial_call_ms(hp, frames, device, n=5):
-    """The plain call a detector makes, fully serialised: upload -> kernels -> download of the stride-8 result."""
+    """The plain call a detector makes, fully serialised: upload -> kernels -> download of the stride-8 result.
+    Returns (ms per call, breakdown in ms of one call taken apart with a synchronise after every phase)."""
     import torch
     hp(frames, device, fetch="encoded")
     torch.cuda.synchronize()
@@ -236,7 +237,21 @@ def serial_call_ms(hp, frames, device, n=5):
     for _ in range(n):
         hp(frames, device, fetch="encoded")
     torch.cuda.synchronize()
-    return (time.perf_counter() - t) * 1000.0 / n
+    ms = (time.perf_counter() - t) * 1000.0 / n
+    t0 = time.perf_counter()
+    pts, off, mfp, _ = hp.upload(frames, device)
+    t1 = time.perf_counter()
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    handle = hp.launch_graph() if hp.use_graph else hp.launch_resident(pts, off, mfp)
+    t3 = time.perf_counter()
+    torch.cuda.synchronize()
+    t4 = time.perf_counter()
+    hp.finish(handle, "encoded")
+    t5 = time.perf_counter()
+    parts = dict(pack_and_enqueue_h2d=t1 - t0, h2d_wait=t2 - t1, launch=t3 - t2, kernels_wait=t4 - t3,
+                 counts_and_d2h=t5 - t4)
+    return ms, {k: round(v * 1e3, 3) for k, v in parts.items()}
 
 
 def quick_value(name, precision, device, steps, flush):
@@ -406,8 +421,10 @@ def run_ours(args, wl, rank, world, device):
                                    gbs=round(r["bytes"] / (r["ms"] * 1e-3) / 1e9, 1)) for r in recs]},
     }
     if world == 1:
-        line["e2e"]["serial_call_ms"] = round(serial_call_ms(hp, frames, device), 4)
-        line["e2e"]["serial_call_frames_per_s"] = round(nb / (line["e2e"]["serial_call_ms"] / 1e3), 2)
+        ms, parts = serial_call_ms(hp, frames, device)
+        line["e2e"]["serial_call_ms"] = round(ms, 4)
+        line["e2e"]["serial_call_frames_per_s"] = round(nb / (ms / 1e3), 2)
+        line["e2e"]["serial_call_breakdown_ms"] = parts
     if world == 1 and not args.no_extras:
         del hp, net
         torch.cuda.empty_cache()

@@ -217,29 +217,27 @@ def indice_conv_backward(features, filters, out_bp, indice_pairs, indice_pair_nu
     """ops.py:143-158 / spconv_ops.h:365-457.  NOT on the hot path.
 
     grad_input is the same contraction as the forward pass with the roles of the two row sets swapped and W
-    transposed -- dX[j] = sum_k dY[out(k, j)] W[k]^T -- so on CUDA fp32 it runs through fv2p_conv_fwd on the
-    input-major neighbour map (fv2p_pairs_to_nbr with the pair columns swapped); every input row accumulates its
-    offsets in ascending k, no atomics.  grad_filters[k] = X[in]^T dY[out] stays a gather + library GEMM per
-    offset, as in the reference (torch::mm, spconv_ops.h:433-436)."""
+    transposed -- dX[j] = sum_k dY[out(k, j)] W[k]^T -- so it runs through fv2p_conv_fwd on the input-major neighbour
+    map (fv2p_pairs_to_nbr with the pair columns swapped); every input row accumulates its offsets in ascending k, no
+    atomics.  grad_filters[k] = X[in]^T dY[out] is ONE fv2p_conv_grad_filters launch on the forward map (the reference
+    runs a gather + gather + torch::mm per offset inside a host loop over the D2H-copied pair counts,
+    spconv_ops.h:378, 399-436).  Nothing here synchronises with the host."""
     cin, cout = filters.shape[-2], filters.shape[-1]
-    w = filters.reshape(-1, cin, cout)
-    grad_w = torch.zeros_like(w)
-    nums = indice_pair_num.tolist()
-    use_cuda = features.is_cuda and features.dtype == torch.float32 and out_bp.dtype == torch.float32 and \
-        indice_pairs.dtype == torch.int32
-    if use_cuda:
-        nbr_in = pairs_to_nbr(indice_pairs, indice_pair_num, features.shape[0], inverse=not inverse)
-        grad_in = conv_forward(out_bp.contiguous(), w.transpose(1, 2).contiguous(), nbr_in.contiguous(),
-                               features.shape[0], mode=_lib.MODE_F32)
-    else:
-        grad_in = torch.zeros_like(features)
-    for k, hot in enumerate(nums):
-        if hot <= 0:
-            continue
-        src = indice_pairs[k, 1 if inverse else 0, :hot].long()
-        dst = indice_pairs[k, 0 if inverse else 1, :hot].long()
-        go = out_bp[dst]
-        grad_w[k] = features[src].t() @ go
-        if not use_cuda:
-            grad_in.index_add_(0, src, go @ w[k].t())
-    return grad_in, grad_w.view_as(filters)
+    if not (features.is_cuda and features.dtype == torch.float32 and out_bp.dtype == torch.float32 and
+            indice_pairs.dtype == torch.int32):
+        raise ValueError("indice_conv_backward runs on CUDA float32 tensors and int32 pairs only (no CPU fallback)")
+    dev = _lib.require_device(features)
+    w = filters.reshape(-1, cin, cout).float()
+    kvol = w.shape[0]
+    feats, go = features.contiguous(), out_bp.contiguous()
+    n_in, n_out = feats.shape[0], go.shape[0]
+    nbr_in = pairs_to_nbr(indice_pairs, indice_pair_num, n_in, inverse=not inverse)
+    grad_in = conv_forward(go, w.transpose(1, 2).contiguous(), nbr_in.contiguous(), n_in, mode=_lib.MODE_F32)
+    nbr_out = pairs_to_nbr(indice_pairs, indice_pair_num, n_out, inverse=inverse).contiguous()
+    grad_w = torch.empty((kvol, cin, cout), dtype=torch.float32, device=feats.device)
+    with torch.cuda.device(dev):
+        st = _lib.load().fv2p_conv_grad_filters(_lib.ptr(feats), _lib.ptr(go), _lib.ptr(nbr_out), nbr_out.stride(0),
+                                                kvol, n_out, None, cin, cout, _lib.ptr(grad_w),
+                                                _lib.stream_ptr(feats.device))
+    _lib.check(st, "conv_grad_filters")
+    return grad_in, grad_w.view_as(filters).to(filters.dtype)

@@ -48,7 +48,11 @@ extern "C" {
 #define FV2P_STATUS_OUT_OVERFLOW 1   /* more active outputs than out_cap */
 #define FV2P_STATUS_VOXEL_OVERFLOW 2 /* more voxels than the output capacity */
 
-/* conv arithmetic modes */
+/* conv arithmetic modes.  The reference's second dtype, fp16 (sparse_conv_ext.indice_conv_half, all.cc:43,
+ * pcdet/ops/spconv/ops.py:115-126), is deliberately NOT built: the reduced-precision path of this library is bf16
+ * (BASELINE.json north_star: "fp32 ... and a stated bf16 tolerance"), which keeps fp32's exponent range through 21
+ * unnormalised-by-design layers; half tensors are rejected with NotImplementedError / FV2P_ERR_UNSUPPORTED rather than
+ * silently converted. */
 #define FV2P_MODE_F32 0      /* fp32 in/out, fp32 FMA on CUDA cores (any channel count)            */
 #define FV2P_MODE_BF16_TC 1  /* bf16 in/out, tcgen05 kind::f16, fp32 accumulation in TMEM          */
 #define FV2P_MODE_TF32X3_TC 2 /* fp32 in/out, tcgen05 kind::tf32 with 3-term split, fp32-accurate  */
@@ -288,6 +292,17 @@ FV2P_API int fv2p_indice_conv_fp32(const float *features, const float *filters, 
                           const int32_t *pair_num, int64_t pair_stride, int64_t num_act_out,
                           int inverse, int subm, int kvol, int cin, int cout, float *out,
                           void *workspace, size_t workspace_bytes, fv2p_stream_t stream);
+
+/* Filter gradient of the sparse convolution (training path).  Replaces the per-offset
+ * gather + gather + torch::mm_out and the host loop over the D2H-copied pair counts of indiceConvBackward
+ * (include/spconv/spconv_ops.h:365-457, :378, :399-436) with ONE launch and no host synchronisation:
+ *     grad_filters[k][ci][co] = sum_i features[nbr[k][i]][ci] * grad_out[i][co]
+ * on the forward pass's output-major neighbour map.  fp32; grad_filters [K,cin,cout] is zeroed by the call; partial
+ * sums are combined with atomics, so results match the reference to rounding.  The input gradient is
+ * fv2p_conv_fwd on the transposed map with W^T (no kernel of its own). */
+FV2P_API int fv2p_conv_grad_filters(const float *features, const float *grad_out, const int32_t *nbr,
+                                    int64_t nbr_stride, int kvol, int64_t n_out_cap, const int32_t *n_out_dev,
+                                    int cin, int cout, float *grad_filters, fv2p_stream_t stream);
 
 /* SparseConvTensor.dense() (pcdet/ops/spconv/structure.py:57-66) in channels-first layout
  * [batch, C, D, H, W]; `dense` must be zero-filled by the caller. features fp32. */

@@ -79,3 +79,22 @@ def test_single_process_identities():
     assert sharding.max_over_ranks(3.5) == 3.5
     assert sharding.gather_counts([1, 2]) == [[1, 2]]
     assert len(sharding.shard_frames(list(range(6)), 1, 3)) == 2
+
+
+def test_bench_shards_the_fixed_batch_into_equal_launches(monkeypatch):
+    """bench.py's waymo_64 workload: the 64 frames are split per frame over the ranks and run in 4-frame launches;
+    every frame is processed exactly once whatever the world size (frames stand in as their sequence numbers)."""
+    import bench
+    monkeypatch.setattr(bench, "make_frames", lambda wl, first, n: list(range(first, first + n)))
+    wl = bench.WORKLOADS["waymo_64"]
+    for world in (1, 2, 4, 8, 3):
+        seen = []
+        for rank in range(world):
+            batches, (lo, hi) = bench._batches_for_rank(wl, rank, world)
+            assert all(1 <= len(b) <= wl["batch"] for b in batches)
+            flat = [f for b in batches for f in b]
+            assert flat == list(range(lo, hi))
+            seen += flat
+        assert seen == list(range(wl["frames"]))
+    one, _ = bench._batches_for_rank(bench.WORKLOADS["waymo_b4"], 0, 1)
+    assert one == [[0, 1, 2, 3]]
