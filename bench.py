@@ -320,7 +320,8 @@ def run_ours(args, wl, rank, world, device):
     gbs = dom["bytes"] / (dom["ms"] * 1e-3) / 1e9
     ai = dom["flops"] / max(dom["bytes"], 1)
     ridge = pk["bf16_tflops"] * 1e12 / (pk["hbm_gbs"] * 1e9)
-    if ai >= ridge / 8:  # contraction-dominated layer: judge it against the tensor pipe
+    # roofline model: attainable = min(tensor peak, AI x HBM peak); the layer is judged against whichever bounds it
+    if ai >= ridge:
         roof = dict(bound="tensor", achieved=round(tflops, 3), peak=pk["bf16_tflops"], unit="TFLOP/s",
                     frac=round(tflops / pk["bf16_tflops"], 5))
     else:
@@ -333,7 +334,8 @@ def run_ours(args, wl, rank, world, device):
     tpath = os.path.join(ROOT, "profiles", "r2_traffic.json")
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get("%s:%s:l%d" % (wkey, precision, dom["layer"]))
-    roof.update(traffic=traffic, peak_source=pk["source"],
+    roof.update(traffic=traffic, peak_source=pk["source"], arithmetic_intensity=round(ai, 1), ridge=round(ridge, 1),
+                achieved_tflops=round(tflops, 3), achieved_gbs=round(gbs, 1),
                 kernel="conv_fwd layer %d (%s, %d->%d, N_out=%d, pairs=%d, mode=%d)" % (
                     dom["layer"], dom["key"], dom["cin"], dom["cout"], dom["n_out"], dom["pairs"], dom["mode"]),
                 kernel_ms=round(dom["ms"], 4), kernel_share_of_conv=round(dom["ms"] / conv_ms, 3),

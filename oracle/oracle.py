@@ -356,7 +356,13 @@ def three_nn(unknown, known, chunk=2048):
         for s in range(0, n, chunk):
             diff = (unknown[s:s + chunk, None, :] - known[None, :, :]).astype(np.float32).astype(np.float64)
             d = (diff * diff).sum(-1)
-            order = np.argsort(d, axis=1, kind="stable")[:, :3]
+            # the 16 smallest (any order), put in ascending index order, then a stable sort by distance: the three
+            # smallest by (distance, index), like the kernel's strict-< ascending scan
+            kk = min(16, m)
+            cand = np.sort(np.argpartition(d, kk - 1, axis=1)[:, :kk], axis=1)
+            dc = np.take_along_axis(d, cand, 1)
+            pick = np.argsort(dc, axis=1, kind="stable")[:, :3]
+            order = np.take_along_axis(cand, pick, 1)
             k = order.shape[1]
             d2[s:s + chunk, :k] = np.take_along_axis(d, order, 1)
             idx[s:s + chunk, :k] = order
