@@ -202,6 +202,41 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// Explicit shared-state-space accesses: pointers derived from the aligned dynamic shared memory base are generic to
+// the compiler, which then emits generic LD / ST (address-space check per access) in the gather and epilogue loops.
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ int4 lds128i(uint32_t addr) {
+  int4 v;
+  asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ int lds32i(uint32_t addr) {
+  int v;
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+
+// Small int arrays in shared memory that the roles use as mailboxes (ordered by the mbarriers around them): volatile
+// accesses through the shared window (a `volatile int *` compiles to generic LD/ST.STRONG.SYS).
+struct SmemInts {
+  uint32_t base;
+  __device__ __forceinline__ int get(int i) const {
+    int v;
+    asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(base + 4u * (uint32_t)i) : "memory");
+    return v;
+  }
+  __device__ __forceinline__ void set(int i, int v) const {
+    asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(base + 4u * (uint32_t)i), "r"(v) : "memory");
+  }
+};
+
 // Split form for software pipelining: the load is issued into `r` without waiting; tmem_ld_wait makes every register
 // of `r` depend on the tcgen05.wait::ld (in/out operands), so no consumer can be scheduled above it.
 __device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t *r) {
@@ -347,12 +382,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
   const uint32_t bar_tfull = bar_landed + 8 * C::kStages, bar_tempty = bar_tfull + 16;
   const uint32_t bar_nfull = bar_tempty + 16, bar_nempty = bar_nfull + 8 * C::kNbrBufs;
   const uint32_t bar_wfull = bar_nempty + 8 * C::kNbrBufs;
-  volatile int *stage_flags =
-      reinterpret_cast<volatile int *>(bars + 3 * C::kStages + 4 + 2 * C::kNbrBufs + kWBars);  // [kStages]
-  volatile int *stage_ks = stage_flags + C::kStages;  // [kStages] packed: the stage's offsets, one byte each (0xFF = none)
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(const_cast<int *>(stage_ks + C::kStages));
-  volatile int *tile_ring = reinterpret_cast<volatile int *>(tmem_slot + 1);  // [kTileRing] tile id per sequence no.
-  volatile int *tile_info = tile_ring + kTileRing;                            // [kNbrBufs][2]: tile id, offset mask
+  int *misc = reinterpret_cast<int *>(bars + 3 * C::kStages + 4 + 2 * C::kNbrBufs + kWBars);
+  const SmemInts stage_flags{smem_u32(misc)};                   // [kStages]
+  const SmemInts stage_ks{stage_flags.base + 4u * C::kStages};  // [kStages] packed: the stage's offsets, one byte each
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(misc + 2 * C::kStages);
+  const SmemInts tile_ring{smem_u32(tmem_slot + 1)};            // [kTileRing] tile id per sequence number
+  const SmemInts tile_info{tile_ring.base + 4u * kTileRing};    // [kNbrBufs][2]: tile id, offset mask
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int dbg = g_tc_debug;
@@ -447,9 +482,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
         mbar_wait(bar_nfull + 8 * nb, (seq / C::kNbrBufs) & 1);
         TC_ACC(tm_ppro);
       }
-      const int tile = tile_info[2 * nb];
-      uint32_t mask = (uint32_t)tile_info[2 * nb + 1];
+      const int tile = tile_info.get(2 * nb);
+      uint32_t mask = (uint32_t)tile_info.get(2 * nb + 1);
       const int *nbr_b = nbr_s + nb * kNbrBufInts;
+      const uint32_t nbr_b32 = smem_u32(nbr_b);
       if (tile < 0) {
         // Sentinel stage: same arrivals as a real stage, no copies; tells the other roles to stop.
         const uint32_t s = issued % C::kStages;
@@ -457,7 +493,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
           mbar_wait(bar_empty + 8 * s, ((issued / C::kStages) & 1) ^ 1);
           const uint32_t a_bar = kTf32 ? bar_landed + 8 * s : bar_full + 8 * s;
           if (lane == 0 && my_part == 0) {
-            stage_flags[s] = kFlagStop;
+            stage_flags.set(s, kFlagStop);
             mbar_arrive(a_bar);
           }
           __syncwarp();
@@ -501,18 +537,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
           const uint32_t a_u32 = smem_u32(stage_base + (size_t)s * C::kABytes);
           const uint32_t a_bar = kTf32 ? bar_landed + 8 * s : bar_full + 8 * s;
           if (lane == 0 && my_part == 0) {
-            stage_flags[s] = (g == 0 ? kFlagFirst : 0) | (g == n_st - 1 ? kFlagLast : 0);
-            stage_ks[s] = (int)ks;
+            stage_flags.set(s, (g == 0 ? kFlagFirst : 0) | (g == n_st - 1 ? kFlagLast : 0));
+            stage_ks.set(s, (int)ks);
             mbar_arrive(a_bar);
           }
           __syncwarp();
           if (my_k >= 0) {  // lanes of an unused slot of the last group copy nothing (no MMA reads those columns)
             const int rpg = rows_here >> 2;  // rows per 8-lane group
             const int r_first = row_base + (lane >> 3) * rpg;
-            const int4 *idx4 = reinterpret_cast<const int4 *>(nbr_b + my_k * kTileM + r_first);
+            const uint32_t idx4 = nbr_b32 + (uint32_t)(my_k * kTileM + r_first) * 4u;
             const uint32_t dst0 = a_u32 + (uint32_t)r_first * 128u;
             for (int q4 = 0; q4 < (rpg >> 2); ++q4) {
-              const int4 v = idx4[q4];
+              const int4 v = lds128i(idx4 + 16u * (uint32_t)q4);
               const int srcs[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
               for (int u = 0; u < 4; ++u) {
@@ -550,8 +586,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
           const uint32_t a_u32 = smem_u32(stage_base + (size_t)s * C::kABytes);
           const uint32_t a_bar = kTf32 ? bar_landed + 8 * s : bar_full + 8 * s;
           if (lane == 0 && my_part == 0) {
-            stage_flags[s] = ((k == (int)first_k && sl == 0) ? kFlagFirst : 0) |
-                             ((k == (int)last_k && sl == slices - 1) ? kFlagLast : 0);
+            stage_flags.set(s, ((k == (int)first_k && sl == 0) ? kFlagFirst : 0) |
+                             ((k == (int)last_k && sl == slices - 1) ? kFlagLast : 0));
             if (use_tma) mbar_arrive_expect_tx(a_bar, a_stage_bytes);
             else mbar_arrive(a_bar);
           }
@@ -572,10 +608,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
             // 128-byte slices) and writes conflict-free thanks to the swizzle.
             const uint8_t *src_base = feat + (size_t)sl * row_bytes + my_chunk * 16;
             if (chunks < 8) {  // narrow rows: interleaved rows per instruction measured faster (0.046 vs 0.053 ms, 16->16)
-              const int *rows_k = nbr_b + k * kTileM;
+              const uint32_t rows_k = nbr_b32 + (uint32_t)(k * kTileM) * 4u;
 #pragma unroll 4
               for (int r = row_base + my_row0; r < row_base + rows_here; r += rows_per_instr) {
-                const int src = rows_k[r];
+                const int src = lds32i(rows_k + 4u * (uint32_t)r);
                 const uint32_t swz = (uint32_t)(my_chunk ^ ((r >> (3 - cshift)) & (chunks - 1)));
                 cp_async16(a_u32 + (uint32_t)r * row_bytes + (swz << 4),
                            src_base + (src >= 0 ? (size_t)src * feat_row_bytes : 0), src >= 0 ? 16u : 0u);
@@ -586,10 +622,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
             }
             const int rpg = rows_here >> (5 - cshift);  // rows per lane group: 32, 16 or 8 (half with two owners)
             const int r_first = row_base + (lane >> cshift) * rpg;
-            const int4 *idx4 = reinterpret_cast<const int4 *>(nbr_b + k * kTileM + r_first);
+            const uint32_t idx4 = nbr_b32 + (uint32_t)(k * kTileM + r_first) * 4u;
             const uint32_t dst0 = a_u32 + (uint32_t)r_first * row_bytes;
             for (int q = 0; q < (rpg >> 2); ++q) {
-              const int4 v = idx4[q];
+              const int4 v = lds128i(idx4 + 16u * (uint32_t)q);
               const int srcs[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
               for (int u = 0; u < 4; ++u) {
@@ -655,11 +691,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
       const uint32_t nb = seq % C::kNbrBufs;
       mbar_wait(bar_nempty + 8 * nb, ((seq / C::kNbrBufs) & 1) ^ 1);
       int *dst = nbr_s + nb * kNbrBufInts;
-      if (lane == 0) tile_ring[seq % kTileRing] = tile;
+      if (lane == 0) tile_ring.set(seq % kTileRing, tile);
       if (tile < 0) {
         if (lane == 0) {
-          tile_info[2 * nb] = -1;
-          tile_info[2 * nb + 1] = 0;
+          tile_info.set(2 * nb, -1);
+          tile_info.set(2 * nb + 1, 0);
           mbar_arrive(bar_nfull + 8 * nb);
         }
         break;
@@ -668,8 +704,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
       const int valid = min(kTileM, n_out - row0);
       if (bulk_ok && order2 && mask != 0u && valid == kTileM) {
         if (elect_one_sync()) {
-          tile_info[2 * nb] = tile;
-          tile_info[2 * nb + 1] = (int)mask;
+          tile_info.set(2 * nb, tile);
+          tile_info.set(2 * nb + 1, (int)mask);
           mbar_arrive_expect_tx(bar_nfull + 8 * nb, (uint32_t)__popc(mask) * (kTileM * 4u));
           uint32_t m = mask;
           while (m) {
@@ -703,8 +739,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
         }
         __syncwarp();
         if (lane == 0) {
-          tile_info[2 * nb] = tile;
-          tile_info[2 * nb + 1] = (int)found;
+          tile_info.set(2 * nb, tile);
+          tile_info.set(2 * nb + 1, (int)found);
           mbar_arrive(bar_nfull + 8 * nb);
         }
       }
@@ -748,7 +784,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
           mbar_wait(bar_full + 8 * s, phase);
           TC_ACC(tm_mfull);
         }
-        const int flags = stage_flags[s];
+        const int flags = stage_flags.get(s);
         {
           TC_T0();
           if (flags & (kFlagFirst | kFlagStop)) mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);  // accumulator drained
@@ -770,7 +806,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
         if constexpr (kPacked) {
           // one MMA per 32 bytes of the A row: K step t belongs to the (t >> kpo_shift)-th offset of the stage and
           // reads that offset's resident weight image
-          const uint32_t ks = (uint32_t)stage_ks[s];
+          const uint32_t ks = (uint32_t)stage_ks.get(s);
           if (dbg != 4) {
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
@@ -857,8 +893,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
         for (uint32_t seq = 0;; ++seq) {
           const uint32_t nb = seq % C::kNbrBufs;
           mbar_wait(bar_nfull + 8 * nb, (seq / C::kNbrBufs) & 1);
-          const int tile = tile_info[2 * nb];
-          uint32_t mask = (uint32_t)tile_info[2 * nb + 1];
+          const int tile = tile_info.get(2 * nb);
+          uint32_t mask = (uint32_t)tile_info.get(2 * nb + 1);
           if (tile < 0) break;
           if (mask == 0u) mask = 1u;
           while (mask) {
@@ -905,9 +941,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
           TC_ACC(tm_xwait);
         }
         TC_T0();
-        const bool stop = (stage_flags[s] & kFlagStop) != 0;
+        const bool stop = (stage_flags.get(s) & kFlagStop) != 0;
         if (!stop) {
-          const uint8_t *row = stage_base + (size_t)s * C::kABytes + (size_t)r * row_bytes;
+          const uint32_t row = smem_u32(stage_base) + s * (uint32_t)C::kABytes + (uint32_t)r * (uint32_t)row_bytes;
           const uint32_t a_cols = lane_addr + s * (uint32_t)C::kAColsPerStage;
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
@@ -915,7 +951,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
               float4 x[4];
 #pragma unroll
               for (int c = 0; c < 4; ++c)
-                x[c] = *reinterpret_cast<const float4 *>(row + (((uint32_t)(half * 4 + c) ^ swz_row) << 4));
+                x[c] = lds128f(row + (((uint32_t)(half * 4 + c) ^ swz_row) << 4));
               // corr: per 8-channel K step, [lo0..lo7 | hi0..hi7] as bf16 pairs = 8 columns, the A operand of the
               // correction MMA (its B operand is [W_hi; W_lo] in bf16, see pack_weight_kernel).  hi is what the
               // tensor core sees when it reads the raw tile as tf32: the value with its low 13 mantissa bits cleared.
@@ -972,7 +1008,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
       }
       TC_T0();
       tc_fence_after();
-      const int tile = tile_ring[seq % kTileRing];
+      const int tile = tile_ring.get(seq % kTileRing);
       if (tile < 0) {
 #ifdef FV2P_TC_TIMERS
         if (threadIdx.x == 0) {
@@ -1000,7 +1036,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
       constexpr int kRowsPerInstr = 32 / kLanesPerRow;     // 8 / 16
       constexpr int kPasses = 32 / kRowsPerInstr;          // 4 / 2
       constexpr int kColsPerLane = 16 / kLanesPerRow;      // 4 / 8 columns of the chunk per lane
-      uint8_t *stage = epi_stage + warp * (32 * kEpiRowPitch);
+      const uint32_t stage = smem_u32(epi_stage) + (uint32_t)warp * (32 * kEpiRowPitch);
       const int sub = lane / kLanesPerRow, seg = lane % kLanesPerRow;
       int grow[kPasses];  // the output row this lane serves in pass q (the row of lane q * kRowsPerInstr + sub)
 #pragma unroll
@@ -1027,8 +1063,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
         __syncwarp();  // the previous chunk has been read back by every lane
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4)
-          *reinterpret_cast<uint4 *>(stage + lane * kEpiRowPitch + q4 * 16) =
-              make_uint4(cur[4 * q4], cur[4 * q4 + 1], cur[4 * q4 + 2], cur[4 * q4 + 3]);
+          sts128(stage + (uint32_t)(lane * kEpiRowPitch + q4 * 16), cur[4 * q4], cur[4 * q4 + 1], cur[4 * q4 + 2],
+                 cur[4 * q4 + 3]);
         __syncwarp();
         // folded BatchNorm (and bias) of this lane's columns
         float sc[kColsPerLane], sh[kColsPerLane], bi[kColsPerLane];
@@ -1048,7 +1084,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
           float v[kColsPerLane];
 #pragma unroll
           for (int v4 = 0; v4 < kColsPerLane / 4; ++v4) {
-            const float4 x = *reinterpret_cast<const float4 *>(stage + r * kEpiRowPitch + (seg * kColsPerLane + 4 * v4) * 4);
+            const float4 x = lds128f(stage + (uint32_t)(r * kEpiRowPitch + (seg * kColsPerLane + 4 * v4) * 4));
             v[4 * v4] = x.x, v[4 * v4 + 1] = x.y, v[4 * v4 + 2] = x.z, v[4 * v4 + 3] = x.w;
           }
           if (grow[q] >= n_out) continue;

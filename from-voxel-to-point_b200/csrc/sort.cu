@@ -92,8 +92,17 @@ group_hist_kernel(const int *__restrict__ nbr, int64_t nbr_stride, int kvol, int
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
     const bool live = i < n;
     uint32_t m = 0;
-    if (live)
-      for (int k = 0; k < kvol; ++k) m |= (__ldg(&nbr[(size_t)k * nbr_stride + i]) >= 0 ? 1u : 0u) << k;
+    if (live) {
+      // nine of the row's loads in flight at a time: the kernel is a pure stream over the map (more would cost the
+      // registers that let it sit next to a conv CTA)
+      for (int k0 = 0; k0 < kvol; k0 += 9) {
+        int v[9];
+#pragma unroll
+        for (int q = 0; q < 9; ++q) v[q] = k0 + q < kvol ? __ldg(&nbr[(size_t)(k0 + q) * nbr_stride + i]) : -1;
+#pragma unroll
+        for (int q = 0; q < 9; ++q) m |= (v[q] >= 0 ? 1u : 0u) << (k0 + q);
+      }
+    }
     const int d = live ? (int)mask_digest(m, kvol, kx, lines) : kBins + lane;
     const unsigned peers = __match_any_sync(0xFFFFFFFFu, d);
     if (live) {
@@ -154,9 +163,16 @@ group_scatter_kernel(const int *__restrict__ nbr, int64_t nbr_stride, int kvol, 
     const uint32_t tm = __reduce_or_sync(tpeers, m);
     if (live) {
       perm[pos] = i;
-      if (nbr_sorted)
-        for (int k = 0; k < kvol; ++k)
-          nbr_sorted[(size_t)k * sorted_stride + pos] = __ldg(&nbr[(size_t)k * nbr_stride + i]);
+      if (nbr_sorted) {
+        for (int k0 = 0; k0 < kvol; k0 += 9) {
+          int v[9];
+#pragma unroll
+          for (int q = 0; q < 9; ++q) v[q] = k0 + q < kvol ? __ldg(&nbr[(size_t)(k0 + q) * nbr_stride + i]) : -1;
+#pragma unroll
+          for (int q = 0; q < 9; ++q)
+            if (k0 + q < kvol) nbr_sorted[(size_t)(k0 + q) * sorted_stride + pos] = v[q];
+        }
+      }
       if (tile_order && lane == __ffs(tpeers) - 1) atomicOr(&tile_masks[tile], tm);
     }
   }
@@ -248,7 +264,7 @@ extern "C" int fv2p_group_rows(const int32_t *nbr, int64_t nbr_stride, int kvol,
                          "group_rows");
     if (st) return st;
   }
-  const int grid = persistent_grid();
+  const int grid = persistent_grid(6);
   group_hist_kernel<<<grid, kThreads, 0, stream>>>(nbr, nbr_stride, kvol, kx, kvol / kx, n_dev, n_cap, w.masks,
                                                    w.digests, w.bins, w.bin_base, w.done);
   group_scatter_kernel<<<grid, kThreads, 0, stream>>>(nbr, nbr_stride, kvol, n_dev, n_cap, w.masks, w.digests,
