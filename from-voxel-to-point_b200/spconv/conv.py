@@ -8,6 +8,7 @@ import torch
 from torch.nn import init
 from torch.nn.parameter import Parameter
 
+from .. import _lib
 from . import functional as Fsp
 from . import ops
 from .modules import SparseModule
@@ -109,19 +110,59 @@ class SparseConvolution(SparseModule):
             input.indice_dict[self.indice_key] = (outids, indices, indice_pairs, indice_pair_num, spatial_shape)
             if self.indice_key is not None:
                 input.nbr_dict[self.indice_key] = nbr
-        if self.subm:
-            out_features = Fsp.indice_subm_conv(features, self.weight, indice_pairs, indice_pair_num,
-                                                outids.shape[0], nbr)
-        else:
-            out_features = Fsp.indice_conv(features, self.weight, indice_pairs, indice_pair_num, outids.shape[0],
-                                           nbr)
-        if self.bias is not None:
-            out_features += self.bias
+        out_features = self._tensor_core_forward(input, features, outids, indice_pairs, indice_pair_num, nbr)
+        if out_features is None:
+            if self.subm:
+                out_features = Fsp.indice_subm_conv(features, self.weight, indice_pairs, indice_pair_num,
+                                                    outids.shape[0], nbr)
+            else:
+                out_features = Fsp.indice_conv(features, self.weight, indice_pairs, indice_pair_num, outids.shape[0],
+                                               nbr)
+            if self.bias is not None:
+                out_features += self.bias
         out_tensor = SparseConvTensor(out_features, outids, out_spatial_shape, batch_size)
         out_tensor.indice_dict = input.indice_dict
         out_tensor.nbr_dict = input.nbr_dict
         out_tensor.grid = input.grid
         return out_tensor
+
+
+    def _tensor_core_forward(self, input, features, outids, indice_pairs, indice_pair_num, nbr):
+        """Inference through the module API (any module graph, FUSED: False, trees the engine does not recognise): when
+        nothing can ask for gradients and the shape fits, the tcgen05 kernel runs here too - fp32 features through the
+        fp32-accurate 3xTF32 mode, bf16 features through the bf16 mode, bias fused - on the rulebook's grouped row
+        order, which is built once per indice_key and cached next to the neighbour map.  Returns None when the plain
+        path (fp32 FMA + autograd) has to be taken."""
+        if torch.is_grad_enabled() and (features.requires_grad or self.weight.requires_grad or
+                                        (self.bias is not None and self.bias.requires_grad)):
+            return None
+        if not features.is_cuda or features.dtype not in (torch.float32, torch.bfloat16):
+            return None
+        mode = _lib.MODE_TF32X3_TC if features.dtype == torch.float32 else _lib.MODE_BF16_TC
+        kvol = int(np.prod(self.kernel_size))
+        if _lib.load().fv2p_pack_weight_bytes(kvol, self.in_channels, self.out_channels, mode) == 0:
+            return None
+        n_out = int(outids.shape[0])
+        if n_out == 0:
+            return None
+        if nbr is None:
+            nbr = ops.pairs_to_nbr(indice_pairs, indice_pair_num, n_out, False)
+        gkey = ("grouped", self.indice_key)
+        grouped = input.nbr_dict.get(gkey) if self.indice_key is not None else None
+        if grouped is None:
+            perm, nbr_sorted, order = ops.sort_rows_by_mask(nbr.contiguous(), n_out, return_tile_order=True)
+            grouped = (perm.contiguous(), nbr_sorted.contiguous(), order.contiguous())
+            if self.indice_key is not None:
+                input.nbr_dict[gkey] = grouped
+        wkey = (self.weight.data_ptr(), self.weight._version, mode)
+        cached = getattr(self, "_packed", None)
+        if cached is None or cached[0] != wkey:
+            w = self.weight.detach().reshape(kvol, self.in_channels, self.out_channels).float().contiguous()
+            cached = (wkey, ops.pack_weight(w, mode))
+            object.__setattr__(self, "_packed", cached)
+        bias = self.bias.detach().float().contiguous() if self.bias is not None else None
+        return ops.conv_forward(features.contiguous(), cached[1], grouped[1], n_out, bias=bias, mode=mode,
+                                row_perm=grouped[0], tile_order=grouped[2])
 
 
 class SparseConv3d(SparseConvolution):

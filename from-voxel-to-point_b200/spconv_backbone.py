@@ -139,6 +139,18 @@ class _BackboneBase(nn.Module):
         wants_grad = torch.is_grad_enabled() and (voxel_features.requires_grad or
                                                   any(p.requires_grad for p in self.parameters()))
         fused = (not self.training) and bool(self._cfg('FUSED', True)) and voxel_features.is_cuda and not wants_grad
+        if fused and getattr(self, '_engine_unavailable', False):
+            fused = False
+        if fused:
+            try:
+                self.get_engine()
+            except NotImplementedError as e:
+                # a module tree the engine's tracer does not recognise (edited backbone): say so once and run the module
+                # graph, whose convolutions still use the tensor-core kernels when no gradients are needed
+                import warnings
+                warnings.warn("fv2p_b200: %s; running the module graph instead of the fused engine" % e)
+                object.__setattr__(self, '_engine_unavailable', True)
+                fused = False
         if fused:
             with torch.no_grad():
                 outs = self.get_engine()(voxel_features.float().contiguous(), coords.contiguous(), batch_size)

@@ -284,3 +284,56 @@ def test_data_processor_hook_matches_reference_voxelizer_fixture():
     assert np.array_equal(dd["voxels"], g[case + "_voxels"][..., 3:])
     with pytest.raises(NotImplementedError):
         DataProcessor([dict(NAME="shuffle_points")], np.array(g[case + "_range"]), training=False)
+
+
+def test_module_api_runs_tensor_cores_for_inference_on_any_module_graph():
+    """a SparseSequential that is not one of the two backbones, under torch.no_grad(): the
+    convolutions take the tcgen05 kernel (3xTF32 for fp32 features) on a grouped row order cached per indice_key, and
+    match the oracle to the fp32 bar; with gradients enabled the same modules take the differentiable path."""
+    shape = [9, 40, 36]
+    ind = synth.random_voxels(shape, 2500, 2, seed=21)
+    rng = np.random.default_rng(2)
+    feats = rng.standard_normal((ind.shape[0], 16)).astype(np.float32)
+    torch.manual_seed(0)
+    net = spconv.SparseSequential(
+        spconv.SubMConv3d(16, 32, 3, padding=1, bias=True, indice_key="a"),
+        spconv.SubMConv3d(32, 32, 3, padding=1, bias=False, indice_key="a"),
+        spconv.SparseConv3d(32, 64, 3, stride=2, padding=1, bias=True, indice_key="b"),
+    ).to(DEV)
+    x = spconv.SparseConvTensor(cuda(feats), cuda(ind), shape, 2)
+    with torch.no_grad():
+        y = net(x)
+    assert ("grouped", "a") in y.nbr_dict and ("grouped", "b") in y.nbr_dict
+    convs = [m for m in net.modules() if isinstance(m, spconv.conv.SparseConvolution)]
+    assert all(getattr(m, "_packed", None) is not None for m in convs)
+    # oracle chain
+    _, p_a, n_a = O.rulebook_subm(ind, 2, shape, 3, 1)
+    f = O.indice_conv(feats, convs[0].weight.detach().cpu().numpy(), p_a, n_a, ind.shape[0], False, True)
+    f = f + convs[0].bias.detach().cpu().numpy()
+    f = O.indice_conv(f, convs[1].weight.detach().cpu().numpy(), p_a, n_a, ind.shape[0], False, True)
+    o_b, p_b, n_b, _ = O.rulebook_conv(ind, 2, shape, 3, 2, 1, 1)
+    f = O.indice_conv(f, convs[2].weight.detach().cpu().numpy(), p_b, n_b, o_b.shape[0], False, False)
+    f = f + convs[2].bias.detach().cpu().numpy()
+    assert np.array_equal(y.indices.cpu().numpy(), o_b)
+    assert rel_err(y.features.cpu().numpy(), f) < FP32_TOL
+    # gradients enabled: the differentiable path, same numbers, and it trains
+    x2 = spconv.SparseConvTensor(cuda(feats).requires_grad_(True), cuda(ind), shape, 2)
+    y2 = net(x2)
+    assert rel_err(y2.features.detach().cpu().numpy(), f) < FP32_TOL
+    y2.features.sum().backward()
+    assert convs[0].weight.grad is not None and x2.features.grad is not None
+
+
+def test_unrecognised_backbone_tree_warns_and_runs_the_module_graph():
+    g = load_golden("backbone_kitti_VoxelResBackBone8x")
+    net = fv2p_b200.VoxelResBackBone8x({}, 4, np.array(g["grid_size"])).eval()
+    state = synth.randomize_state(net.state_dict(), seed=int(g["seed"]))
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in state.items()}, strict=False)
+    net.conv_out.add(torch.nn.Identity())  # something the engine's tracer does not know
+    net = net.to(DEV)
+    bd = {"voxel_features": cuda(g["voxel_features"]), "voxel_coords": cuda(g["voxel_coords"]),
+          "batch_size": int(g["batch_size"])}
+    with torch.no_grad(), pytest.warns(UserWarning, match="module graph"):
+        bd = net(bd)
+    assert rel_err(bd["encoded_spconv_tensor"].features.cpu().numpy(), g["out_features"]) < FP32_TOL
+    assert np.array_equal(bd["encoded_spconv_tensor"].indices.cpu().numpy(), g["out_indices"])
