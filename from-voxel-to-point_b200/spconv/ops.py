@@ -52,7 +52,8 @@ def get_indice_pairs(indices, batch_size, spatial_shape, ksize=3, stride=1, padd
                      subm=False, transpose=False, grid=None, return_nbr=False, want_pairs=True):
     """ops.py:46-105.  Returns (outids, indice_pairs [K,2,N] int32, indice_pair_num [K] int32), bit-identical
     to the reference's CPU path.  With return_nbr=True also returns the output-major neighbour map [K,Nout];
-    want_pairs=False skips the reference-layout pair lists (both come back as None)."""
+    want_pairs=False skips the reference-layout pair lists (both come back as None).  `indices` must hold each
+    coordinate once (include/fv2p_b200.h, "Coordinates must be UNIQUE")."""
     ndim = indices.shape[1] - 1
     ksize, stride, padding, dilation, out_padding = (_listify(v, ndim) for v in
                                                      (ksize, stride, padding, dilation, out_padding))

@@ -24,6 +24,11 @@
  *  - The neighbour map `nbr` [K, nbr_stride] int32 is this library's own conv operand: nbr[k][i] is
  *    the INPUT row feeding OUTPUT row i through kernel offset k, or -1.  It carries the same
  *    information as the pair tensor, output-major.
+ *  - Coordinates must be UNIQUE (one row per voxel), which is what the voxelizer and every rulebook of this library
+ *    produce.  The reference tolerates duplicate input coordinates in a particular way (its grid keeps the last
+ *    duplicate, geometry.h:276-280, while its pair lists still carry one pair per duplicate, which the gather-scatter
+ *    loop then accumulates); the output-major map holds ONE input row per (offset, output) cell, so with duplicates
+ *    the convolution result would differ from the reference's.  Duplicates are the caller's error here.
  */
 #ifndef FV2P_B200_H_
 #define FV2P_B200_H_
