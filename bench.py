@@ -116,12 +116,16 @@ def make_frames(wl, first, n):
     return [synth.lidar_frame(wl["dataset"], seed=first + i) for i in range(n)]
 
 
+SORT_ROWS = True  # --group-rows: which rulebooks get a grouped row order (engine.BackboneEngine sort_rows)
+
+
 def build_model(wl, device, precision, use_graph=False):
     import torch
     import fv2p_b200
     from fv2p_b200 import synth
     cfg = synth.DATASETS[wl["dataset"]]
-    net = getattr(fv2p_b200, wl["backbone"])({"PRECISION": precision}, cfg["num_point_features"],
+    net = getattr(fv2p_b200, wl["backbone"])({"PRECISION": precision, "SORT_ROWS": SORT_ROWS},
+                                             cfg["num_point_features"],
                                              np.array(synth.grid_size(cfg))).eval()
     state = synth.randomize_state(net.state_dict(), seed=0)
     net.load_state_dict({k: torch.from_numpy(v) for k, v in state.items()}, strict=False)
@@ -671,8 +675,12 @@ def main():
                     help="skip reference_gpu and the other workloads' extra keys (profiling runs)")
     ap.add_argument("--gather", default="auto", choices=["auto", "lsu", "tma"],
                     help="A-tile producer of the tensor-core conv (fv2p_tc_gather_mode); auto = cp.async for every shape")
+    ap.add_argument("--group-rows", default="all", choices=["all", "subm", "none"],
+                    help="rulebooks whose rows are grouped by neighbour-mask digest for the tensor-core conv")
     ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
+    global SORT_ROWS
+    SORT_ROWS = {"all": True, "subm": "subm", "none": False}[args.group_rows]
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

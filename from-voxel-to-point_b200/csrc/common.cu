@@ -22,6 +22,9 @@ int cuda_status(cudaError_t e, const char *what) {
   return (int)e;
 }
 
+static int g_geo_ctas = 0;
+int geo_ctas_override() { return g_geo_ctas; }
+
 constexpr int kMaxDevices = 64;
 
 int current_device() {
@@ -116,6 +119,11 @@ void launch_scan_chunk_counts(int *counts, int segments, int64_t seg_stride, con
 extern "C" {
 
 int fv2p_abi_version(void) { return FV2P_ABI_VERSION; }
+
+__attribute__((visibility("default"))) int fv2p_debug_geo_ctas(int v) {
+  fv2p::g_geo_ctas = v > 0 ? v : 0;
+  return 0;
+}
 
 const char *fv2p_last_error(void) { return fv2p::g_error; }
 

@@ -37,7 +37,11 @@ constexpr int kThreads = 256;
 constexpr int kItemsPerThread = 2;
 constexpr int kChunk = kThreads * kItemsPerThread;  // rows per work item of the ordered passes
 
-inline int persistent_grid(int ctas_per_sm = 4) { return sm_count() * ctas_per_sm; }
+int geo_ctas_override();  // 0 = none (debug switch fv2p_debug_geo_ctas: CTAs per SM of the persistent geometry grids)
+inline int persistent_grid(int ctas_per_sm = 4) {
+  const int o = geo_ctas_override();
+  return sm_count() * (o > 0 ? o : ctas_per_sm);
+}
 
 // workspace carving (256-byte aligned)
 struct Carver {

@@ -194,7 +194,9 @@ class BackboneEngine(object):
         # indice_dict[key] is first read; False: never (indice_dict stays empty)
         self.materialize_pairs = materialize_pairs
         self.use_tensor_cores = use_tensor_cores
-        self.sort_rows = sort_rows  # mask-sorted row order for the tensor-core layers (same results, fewer stages)
+        # grouped row order for the tensor-core layers (same results, fewer stages): True = every rulebook, 'subm' =
+        # the submanifold ones only (a strided rulebook feeds ONE layer: grouping it costs more than it saves), False
+        self.sort_rows = sort_rows
         self.concurrent = concurrent  # geometry and feature pass on forked streams (joined before launch returns)
         # Row capacity of level l+1 = min(cap_growth * capacity of level l, hard bound).  The hard bound
         # (fan-out 8 per strided conv, or the dense volume) is 10-100x what LiDAR frames produce - a KITTI batch
@@ -342,7 +344,7 @@ class BackboneEngine(object):
                                           dtype=torch.uint8, device=device)
                 geo[gk] = d
             d["keys"].append(bk.key)
-            if self.sort_rows and bk.key in tc_books and not d["sorted"]:
+            if self._groups(bk) and bk.key in tc_books and not d["sorted"]:
                 cout_cap = caps[bk.out_level]
                 cols = d["nbr"].shape[1]
                 d["sorted"] = True
@@ -598,10 +600,13 @@ class BackboneEngine(object):
                                      _lib.ptr(d["pair_ws"]), d["pair_ws"].numel(), _lib.stream_ptr(device))
         _lib.check(st, "pairs[%s]" % bk.key)
 
+    def _groups(self, bk):
+        return bool(self.sort_rows) and (self.sort_rows != 'subm' or bk.subm)
+
     def conv_operands(self, a, step, prm):
         """(neighbour map, row order, tile order) a conv step reads: the mask-sorted set for the tensor-core modes."""
         d = a["books"][step.key]
-        if self.sort_rows and prm["mode"] in (_lib.MODE_BF16_TC, _lib.MODE_TF32X3_TC):
+        if d["sorted"] and prm["mode"] in (_lib.MODE_BF16_TC, _lib.MODE_TF32X3_TC):
             return d["nbr_sorted"], d["perm"], d["tile_order"]
         return d["nbr"], None, None
 
@@ -695,7 +700,7 @@ class BackboneEngine(object):
                 if gk not in seen:
                     seen.add(gk)
                     geo.append(dict(book=bk, sorted=False))
-                if self.sort_rows and bk.key in tc_books:
+                if self._groups(bk) and bk.key in tc_books:
                     [g for g in geo if self._geo_key(g["book"]) == gk][0]["sorted"] = True
         for d in geo:
             n += 1 if d["book"].subm else 3

@@ -115,7 +115,7 @@ class _BackboneBase(nn.Module):
         mp = self._cfg('MATERIALIZE_PAIRS', True if materialize_pairs is None else materialize_pairs)
         return BackboneEngine(self, precision=self._cfg('PRECISION', 'fp32'),
                               materialize_pairs=mp if mp in (True, False, 'lazy') else bool(mp),
-                              sort_rows=bool(self._cfg('SORT_ROWS', True)),
+                              sort_rows=self._cfg('SORT_ROWS', True),
                               cap_growth=self._cfg('CAP_GROWTH', 'auto'))
 
     def get_engine(self):
