@@ -388,6 +388,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(misc + 2 * C::kStages);
   const SmemInts tile_ring{smem_u32(tmem_slot + 1)};            // [kTileRing] tile id per sequence number
   const SmemInts tile_info{tile_ring.base + 4u * kTileRing};    // [kNbrBufs][2]: tile id, offset mask
+  // [1] number of tile_ring entries the scheduler has published (release / acquire): lets the epilogue look one tile
+  // ahead of the accumulator it is waiting for
+  const uint32_t tiles_posted = tile_info.base + 4u * 2u * C::kNbrBufs;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int dbg = g_tc_debug;
@@ -437,6 +440,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
       // every producer warp and (with a weight ring) the W loader are done with the buffer
       mbar_init(bar_nempty + 8 * b, kProdWarps + (kPacked ? 0 : 1));
     }
+    asm volatile("st.shared.s32 [%0], %1;" ::"r"(tiles_posted), "r"(0) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&feat_map) : "memory");
   }
@@ -691,7 +695,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
       const uint32_t nb = seq % C::kNbrBufs;
       mbar_wait(bar_nempty + 8 * nb, ((seq / C::kNbrBufs) & 1) ^ 1);
       int *dst = nbr_s + nb * kNbrBufInts;
-      if (lane == 0) tile_ring.set(seq % kTileRing, tile);
+      if (lane == 0) {
+        tile_ring.set(seq % kTileRing, tile);
+        asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(tiles_posted), "r"((int)seq + 1) : "memory");
+      }
       if (tile < 0) {
         if (lane == 0) {
           tile_info.set(2 * nb, -1);
@@ -1000,7 +1007,43 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
     TC_TIMER_DECL(tm_ewait);
     TC_TIMER_DECL(tm_ework);
     griddep_wait();  // residual rows come from an earlier layer; the output buffer may still be read by the previous one
+    // The epilogue's own latency chain per tile used to be: accumulator ready -> row order (a global load) -> residual
+    // (a dependent global load) -> tcgen05.ld -> store, i.e. two L2 round trips before the first useful instruction;
+    // with 128 x 16 / 32 outputs per tile that chain, not the contraction, paced the narrow layers (2-4 k cycles per
+    // tile).  Now the tile id of the NEXT accumulator is read from the scheduler's ring while the current one is
+    // processed (`tiles_posted` says whether it is there yet), its output rows are loaded one tile ahead, and the
+    // first residual chunk is issued before waiting for the accumulator.
+    constexpr int kLanesPerRow = kTf32 ? 4 : 2;          // lanes that share a row segment
+    constexpr int kRowsPerInstr = 32 / kLanesPerRow;     // 8 / 16
+    constexpr int kPasses = 32 / kRowsPerInstr;          // 4 / 2
+    constexpr int kColsPerLane = 16 / kLanesPerRow;      // 4 / 8 columns of a 16-column chunk per lane
+    const int sub = lane / kLanesPerRow, seg = lane % kLanesPerRow;
+    const bool body = dbg != 6;
+    // sorted position -> output row (identity without a row order from fv2p_sort_rows_by_mask)
+    auto load_row = [&](int tile) {
+      const int srow = tile * kTileM + warp * 32 + lane;
+      return srow < n_out ? (row_perm ? __ldg(&row_perm[srow]) : srow) : n_out;
+    };
+    auto load_residual = [&](const int *grow, int c0, uint4 *res) {
+#pragma unroll
+      for (int q = 0; q < kPasses; ++q)
+        if (grow[q] < n_out)
+          res[q] = __ldg(reinterpret_cast<const uint4 *>(static_cast<const uint8_t *>(ep.residual) +
+                                                         ((size_t)grow[q] * N + c0 + seg * kColsPerLane) * kElem));
+    };
+    int tile_next = -1, row_next = 0;
+    bool have_next = false;
     for (uint32_t seq = 0;; ++seq) {
+      int tile = -1, row = 0;
+      int grow[kPasses];  // the output row this lane serves in pass q (the row of lane q * kRowsPerInstr + sub)
+      uint4 res0[kPasses];
+      const bool early = have_next;
+      if (early) {
+        tile = tile_next, row = row_next;
+#pragma unroll
+        for (int q = 0; q < kPasses; ++q) grow[q] = __shfl_sync(0xFFFFFFFFu, row, q * kRowsPerInstr + sub);
+        if (body && ep.residual) load_residual(grow, 0, res0);
+      }
       {
         TC_T0();
         mbar_wait(bar_tfull + 8 * acc, acc_phase);
@@ -1008,19 +1051,36 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
       }
       TC_T0();
       tc_fence_after();
-      const int tile = tile_ring.get(seq % kTileRing);
-      if (tile < 0) {
+      if (!early) {
+        tile = tile_ring.get(seq % kTileRing);
+        if (tile < 0) {
 #ifdef FV2P_TC_TIMERS
-        if (threadIdx.x == 0) {
-          g_tc_timers[blockIdx.x][9] = tm_ewait;
-          g_tc_timers[blockIdx.x][10] = tm_ework;
-        }
+          if (threadIdx.x == 0) {
+            g_tc_timers[blockIdx.x][9] = tm_ewait;
+            g_tc_timers[blockIdx.x][10] = tm_ework;
+          }
 #endif
-        break;
+          break;
+        }
+        row = load_row(tile);
+#pragma unroll
+        for (int q = 0; q < kPasses; ++q) grow[q] = __shfl_sync(0xFFFFFFFFu, row, q * kRowsPerInstr + sub);
+        if (body && ep.residual) load_residual(grow, 0, res0);
       }
-      // sorted position -> output row (identity without a row order from fv2p_sort_rows_by_mask)
-      const int srow = tile * kTileM + warp * 32 + lane;
-      const int row = srow < n_out ? (row_perm ? __ldg(&row_perm[srow]) : srow) : n_out;
+      {
+        // one tile ahead: only when the scheduler has already published it (it usually has - it runs ahead of the
+        // producers); the sentinel is left to the slow path above, which runs after the MMA thread's final arrive
+        int posted;
+        asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(posted) : "r"(tiles_posted) : "memory");
+        have_next = false;
+        if (posted > (int)seq + 1) {
+          tile_next = tile_ring.get((seq + 1) % kTileRing);
+          if (tile_next >= 0) {
+            row_next = load_row(tile_next);
+            have_next = true;
+          }
+        }
+      }
       const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * N);
       // Per 16-column chunk: tcgen05.ld hands every lane ITS row (32 rows x 16 fp32 per warp); the warp writes them to
       // its staging buffer and reads them back transposed - lanes side by side along a row - so that every global
@@ -1032,16 +1092,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
       // behind and competed with the gather for the load/store unit.  The tcgen05.ld of chunk c+1 and the residual
       // of chunk c are in flight while chunk c is transposed.
       constexpr int kChunks = N / 16;
-      constexpr int kLanesPerRow = kTf32 ? 4 : 2;          // lanes that share a row segment
-      constexpr int kRowsPerInstr = 32 / kLanesPerRow;     // 8 / 16
-      constexpr int kPasses = 32 / kRowsPerInstr;          // 4 / 2
-      constexpr int kColsPerLane = 16 / kLanesPerRow;      // 4 / 8 columns of the chunk per lane
       const uint32_t stage = smem_u32(epi_stage) + (uint32_t)warp * (32 * kEpiRowPitch);
-      const int sub = lane / kLanesPerRow, seg = lane % kLanesPerRow;
-      int grow[kPasses];  // the output row this lane serves in pass q (the row of lane q * kRowsPerInstr + sub)
-#pragma unroll
-      for (int q = 0; q < kPasses; ++q) grow[q] = __shfl_sync(0xFFFFFFFFu, row, q * kRowsPerInstr + sub);
-      const bool body = dbg != 6;
       uint32_t acc_regs[2][16];
       tmem_ld16_issue(taddr, acc_regs[0]);  // warp-collective: executed by all lanes even for rows past the end
 #pragma unroll
@@ -1050,15 +1101,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
         uint32_t *cur = acc_regs[c & 1];
         // residual segments of this chunk: issued before the transposition so that their latency hides behind it
         uint4 res[kPasses];
-        if (body && ep.residual) {
+        if (c == 0) {
 #pragma unroll
-          for (int q = 0; q < kPasses; ++q)
-            if (grow[q] < n_out)
-              res[q] = __ldg(reinterpret_cast<const uint4 *>(static_cast<const uint8_t *>(ep.residual) +
-                                                             ((size_t)grow[q] * N + c0 + seg * kColsPerLane) * kElem));
+          for (int q = 0; q < kPasses; ++q) res[q] = res0[q];
+        } else if (body && ep.residual) {
+          load_residual(grow, c0, res);
         }
         tmem_ld_wait(cur);
-        if (c + 1 < kChunks) tmem_ld16_issue(taddr + c0 + 16, acc_regs[(c + 1) & 1]);
+        if (c + 1 < kChunks) {
+          tmem_ld16_issue(taddr + c0 + 16, acc_regs[(c + 1) & 1]);
+        } else {
+          // the whole accumulator is in registers: the MMA thread may start the tile after next on it
+          tc_fence_before();
+          mbar_arrive(bar_tempty + 8 * acc);
+        }
         if (!body) continue;
         __syncwarp();  // the previous chunk has been read back by every lane
 #pragma unroll
@@ -1126,8 +1182,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
           }
         }
       }
-      tc_fence_before();
-      mbar_arrive(bar_tempty + 8 * acc);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
       TC_ACC(tm_ework);
