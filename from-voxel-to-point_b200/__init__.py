@@ -16,6 +16,7 @@ from .pipeline import HotPath
 from . import sharding
 from . import pointops
 from .data_processor import DataProcessor
+from .batchnorm import BatchNorm1d
 
 # name lookup tables like pcdet/models/backbones_3d/__init__.py:6-12 and vfe/__init__.py:5-9
 BACKBONES_3D = {'VoxelBackBone8x': VoxelBackBone8x, 'VoxelResBackBone8x': VoxelResBackBone8x}
@@ -24,4 +25,4 @@ MAP_TO_BEV = {'HeightCompression': HeightCompression}  # backbones_2d/map_to_bev
 
 __all__ = ['spconv', 'synth', 'MeanVFE', 'VoxelGenerator', 'BatchVoxelizer', 'VoxelBackBone8x',
            'VoxelResBackBone8x', 'SparseBasicBlock', 'post_act_block', 'BackboneEngine', 'HotPath', 'BACKBONES_3D',
-           'VFE', 'HeightCompression', 'MAP_TO_BEV', 'pointops', 'DataProcessor']
+           'VFE', 'HeightCompression', 'MAP_TO_BEV', 'pointops', 'DataProcessor', 'BatchNorm1d']

@@ -70,6 +70,11 @@ PROTOTYPES = {
     "fv2p_indice_conv_fp32": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_int, _c_int, _c_int, _c_int,
                                        _c_int, _c_vp, _c_vp, _c_sz, _c_vp]),
     "fv2p_conv_grad_filters": (_c_int, [_c_vp, _c_vp, _c_vp, _c_i64, _c_int, _c_i64, _c_vp, _c_int, _c_int, _c_vp, _c_vp]),
+    "fv2p_batchnorm_workspace_bytes": (_c_sz, [_c_int]),
+    "fv2p_batchnorm_train_fwd": (_c_int, [_c_vp, _c_i64, _c_int, _c_vp, _c_vp, ctypes.c_float, ctypes.c_float, _c_vp,
+                                          _c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_sz, _c_vp]),
+    "fv2p_batchnorm_train_bwd": (_c_int, [_c_vp, _c_vp, _c_i64, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp,
+                                          _c_vp, _c_sz, _c_vp]),
     "fv2p_dense_ncdhw": (_c_int, [_c_vp, _c_vp, _c_i64, _c_vp, _c_int, _c_vp, _c_vp, _c_vp]),
     "fv2p_height_compression_workspace_bytes": (_c_sz, [_c_int, _c_vp]),
     "fv2p_height_compression": (_c_int, [_c_vp, _c_vp, _c_i64, _c_vp, _c_int, _c_int, _c_vp, _c_int, _c_vp, _c_vp, _c_sz,

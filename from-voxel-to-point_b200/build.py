@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libfv2p_b200.so")
-SOURCES = ["common.cu", "voxelize.cu", "rulebook.cu", "sort.cu", "conv_simt.cu", "conv_tc.cu", "pointops.cu", "conv_bwd.cu"]
+SOURCES = ["common.cu", "voxelize.cu", "rulebook.cu", "sort.cu", "conv_simt.cu", "conv_tc.cu", "pointops.cu", "conv_bwd.cu", "batchnorm.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--use_fast_math=false",
          "-Xcompiler", "-fPIC,-fvisibility=hidden,-O2", "-Xptxas", "-v", "--fmad=true"]

@@ -18,6 +18,7 @@ import torch
 import torch.nn as nn
 
 from . import spconv
+from .batchnorm import BatchNorm1d
 from .engine import BackboneEngine
 
 
@@ -175,7 +176,7 @@ class VoxelBackBone8x(_BackboneBase):
     def __init__(self, model_cfg, input_channels, grid_size, **kwargs):
         super().__init__()
         self.model_cfg = model_cfg
-        norm_fn = partial(nn.BatchNorm1d, eps=1e-3, momentum=0.01)
+        norm_fn = partial(BatchNorm1d, eps=1e-3, momentum=0.01)
         self.sparse_shape = grid_size[::-1] + [1, 0, 0]
         self.conv_input = spconv.SparseSequential(
             spconv.SubMConv3d(input_channels, 16, 3, padding=1, bias=False, indice_key='subm1'),
@@ -216,7 +217,7 @@ class VoxelResBackBone8x(_BackboneBase):
     def __init__(self, model_cfg, input_channels, grid_size, **kwargs):
         super().__init__()
         self.model_cfg = model_cfg
-        norm_fn = partial(nn.BatchNorm1d, eps=1e-3, momentum=0.01)
+        norm_fn = partial(BatchNorm1d, eps=1e-3, momentum=0.01)
         self.sparse_shape = grid_size[::-1] + [1, 0, 0]
         self.conv_input = spconv.SparseSequential(
             spconv.SubMConv3d(input_channels, 16, 3, padding=1, bias=False, indice_key='subm1'),

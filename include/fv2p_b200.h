@@ -309,6 +309,28 @@ FV2P_API int fv2p_conv_grad_filters(const float *features, const float *grad_out
                                     int64_t nbr_stride, int kvol, int64_t n_out_cap, const int32_t *n_out_dev,
                                     int cin, int cout, float *grad_filters, fv2p_stream_t stream);
 
+/* Training-mode BatchNorm1d over the N active rows of a feature matrix.  Replaces the
+ * `nn.BatchNorm1d(eps=1e-3, momentum=0.01)` the reference's backbones apply to `.features` after every conv
+ * (pcdet/models/backbones_3d/spconv_backbone.py:75, :193) when the module is in training mode: batch statistics
+ * (biased variance to normalise, unbiased into running_var), y = (x - mean) * invstd * weight + bias, optional ReLU.
+ * x, y [n, channels] fp32 row-major (y may alias x); weight / bias / running_* may be NULL (affine=False /
+ * track_running_stats=False); `momentum` is the factor actually applied (the caller resolves momentum=None).
+ * save_mean / save_invstd [channels] are what the backward needs.  n < 2 is an error, as in torch.
+ * `workspace`: fv2p_batchnorm_workspace_bytes(channels) bytes, 8-byte aligned, ZERO on first use; the calls hand it
+ * back zeroed.  Two launches, no host synchronisation; fp64 column sums, so results match torch to rounding. */
+FV2P_API size_t fv2p_batchnorm_workspace_bytes(int channels);
+FV2P_API int fv2p_batchnorm_train_fwd(const float *x, int64_t n, int channels, const float *weight, const float *bias,
+                                      float eps, float momentum, float *running_mean, float *running_var, int relu,
+                                      float *y, float *save_mean, float *save_invstd, void *workspace,
+                                      size_t workspace_bytes, fv2p_stream_t stream);
+/* Backward of the above (without the ReLU): grad_bias = sum grad_out, grad_weight = sum grad_out * xhat,
+ * grad_input = weight * invstd * (grad_out - grad_bias / n - xhat * grad_weight / n).  grad_weight / grad_bias
+ * [channels] are always written (also when weight is NULL). */
+FV2P_API int fv2p_batchnorm_train_bwd(const float *x, const float *grad_out, int64_t n, int channels,
+                                      const float *weight, const float *save_mean, const float *save_invstd,
+                                      float *grad_input, float *grad_weight, float *grad_bias, void *workspace,
+                                      size_t workspace_bytes, fv2p_stream_t stream);
+
 /* SparseConvTensor.dense() (pcdet/ops/spconv/structure.py:57-66) in channels-first layout
  * [batch, C, D, H, W]; `dense` must be zero-filled by the caller. features fp32. */
 FV2P_API int fv2p_dense_ncdhw(const float *features, const int32_t *indices, int64_t n_cap,

@@ -337,3 +337,77 @@ def test_unrecognised_backbone_tree_warns_and_runs_the_module_graph():
         bd = net(bd)
     assert rel_err(bd["encoded_spconv_tensor"].features.cpu().numpy(), g["out_features"]) < FP32_TOL
     assert np.array_equal(bd["encoded_spconv_tensor"].indices.cpu().numpy(), g["out_indices"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,c", [(2, 16), (1000, 5), (4097, 32), (120000, 128), (3000, 300)])
+def test_training_batchnorm_matches_torch(n, c):
+    """fv2p_batchnorm_train_fwd / _bwd against torch's nn.BatchNorm1d (what the reference's norm_fn is,
+    spconv_backbone.py:75): output, running statistics, batch counter and all three gradients, fp32 <= 1e-5 of scale."""
+    g = torch.Generator().manual_seed(n + c)
+    x = (torch.randn(n, c, generator=g) * torch.linspace(0.1, 4.0, c) + torch.linspace(-30.0, 30.0, c)).cuda()
+    dy = torch.randn(n, c, generator=g).cuda()
+    ref = torch.nn.BatchNorm1d(c, eps=1e-3, momentum=0.01).cuda()
+    ours = fv2p_b200.BatchNorm1d(c, eps=1e-3, momentum=0.01).cuda()
+    with torch.no_grad():
+        ref.weight.copy_(torch.linspace(0.5, 1.5, c))
+        ref.bias.copy_(torch.linspace(-1.0, 1.0, c))
+        ref.running_mean.normal_(generator=None)
+        ref.running_var.uniform_(0.5, 2.0)
+    ours.load_state_dict(ref.state_dict())
+    assert list(ours.state_dict().keys()) == list(ref.state_dict().keys())
+    for step in range(2):
+        xr, xo = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+        yr, yo = ref(xr), ours(xo)
+        yr.backward(dy)
+        yo.backward(dy)
+        scale = float(yr.detach().abs().max())
+        assert float((yr - yo).abs().max()) <= 1e-5 * scale
+        assert float((xr.grad - xo.grad).abs().max()) <= 1e-5 * max(float(xr.grad.abs().max()), 1e-3) + 1e-7
+        assert torch.allclose(ref.weight.grad, ours.weight.grad, rtol=1e-4, atol=1e-4 * float(ref.weight.grad.abs().max()))
+        assert torch.allclose(ref.bias.grad, ours.bias.grad, rtol=1e-4, atol=1e-4 * float(ref.bias.grad.abs().max()))
+        assert torch.allclose(ref.running_mean, ours.running_mean, rtol=1e-5, atol=1e-6)
+        assert torch.allclose(ref.running_var, ours.running_var, rtol=1e-5, atol=1e-6)
+        assert int(ref.num_batches_tracked) == int(ours.num_batches_tracked) == step + 1
+    # eval mode: the same affine map of the running statistics as torch
+    ref.eval(), ours.eval()
+    assert torch.allclose(ref(x), ours(x), rtol=1e-6, atol=1e-6)
+    # one row is an error in training, as in torch
+    ours.train()
+    with pytest.raises(ValueError):
+        ours(x[:1])
+
+
+@pytest.mark.gpu
+def test_backbone_training_step_runs_on_the_library_kernels():
+    """Training mode: the module graph with the library's conv forward / backward and BatchNorm; gradients reach every
+    parameter, running statistics move, and the loss matches the same graph built on torch's BatchNorm1d."""
+    cfg = synth.DATASETS["kitti"]
+    frames = [synth.lidar_frame("kitti", seed=90 + i, az_steps=60) for i in range(2)]
+    offs = np.concatenate([[0], np.cumsum([f.shape[0] for f in frames])]).astype(np.int32)
+    bv = fv2p_b200.BatchVoxelizer(cfg["voxel_size"], cfg["point_cloud_range"], 5, 16000)
+    vox = bv(torch.from_numpy(np.concatenate(frames)).cuda(), torch.from_numpy(offs).cuda(),
+             max(f.shape[0] for f in frames))
+    m = int(vox["voxel_offsets"][-1])
+    feats, coords = vox["voxel_features"][:m].clone(), vox["voxel_coords"][:m].clone()
+    losses = []
+    for use_ours in (True, False):
+        torch.manual_seed(0)
+        net = fv2p_b200.VoxelBackBone8x({}, 4, np.array(synth.grid_size(cfg))).cuda().train()
+        if not use_ours:
+            for mod in net.modules():
+                for name, child in list(mod.named_children()):
+                    if isinstance(child, fv2p_b200.BatchNorm1d):
+                        plain = torch.nn.BatchNorm1d(child.num_features, eps=child.eps, momentum=child.momentum).cuda()
+                        plain.load_state_dict(child.state_dict())
+                        setattr(mod, name, plain)
+        out = net({"voxel_features": feats, "voxel_coords": coords, "batch_size": 2})
+        loss = out["encoded_spconv_tensor"].features.square().mean()
+        loss.backward()
+        assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in net.parameters())
+        bns = [m for m in net.modules() if isinstance(m, torch.nn.BatchNorm1d)]
+        assert all(int(m.num_batches_tracked) == 1 for m in bns)
+        losses.append((float(loss), [p.grad.clone() for p in net.parameters()]))
+    assert abs(losses[0][0] - losses[1][0]) <= 1e-4 * abs(losses[1][0])
+    for a, b in zip(losses[0][1], losses[1][1]):
+        assert float((a - b).abs().max()) <= 2e-3 * max(float(b.abs().max()), 1e-6)
