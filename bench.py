@@ -360,12 +360,14 @@ def run_ours(args, wl, rank, world, device):
             best = min(best, e0.elapsed_time(e1))
         return best
     nb = len(frames)
-    vox_ms = timed(lambda: hp.voxelizer(pts, off, mfp))
-    vox = hp.voxelizer(pts, off, mfp)
     eng = hp.engine
+    # as in HotPath.launch_resident: the voxelizer also fills the convolutions' level-0 coordinate table
+    table0 = eng.level0_table(pts.device, hp.voxelizer.capacity(pts.device, pts.shape[0], nb, pts.shape[1]), nb)
+    vox_ms = timed(lambda: hp.voxelizer(pts, off, mfp, level0_table=table0))
+    vox = hp.voxelizer(pts, off, mfp, level0_table=table0)
     n0 = vox["voxel_offsets"][nb:nb + 1]
     geo_ms = timed(lambda: eng.launch(vox["voxel_features"], vox["voxel_coords"], nb, n0_dev=n0, cap0=vox["cap"],
-                                      run_convs=False))
+                                      run_convs=False, table0_built=True))
     F = frames[0].shape[1]
     P = int(sum(f.shape[0] for f in frames))
     vox_bytes = P * F * 4 + counts[0] * (16 + F * 4 + 4)
@@ -387,7 +389,7 @@ def run_ours(args, wl, rank, world, device):
     bev_bytes = enc.features.numel() * enc.features.element_size() + enc.indices.numel() * 4 + \
         bev_buf.numel() * bev_buf.element_size()
     del bev_buf
-    launches_per_pass = (hp.engine.launch_count() + 8) * len(batches)
+    launches_per_pass = (hp.engine.launch_count(table0_built=True) + hp.voxelizer.LAUNCHES) * len(batches)
     line = {
         "metric": METRIC, "value": round(value, 2), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(total_ms / args.steps, 4), "higher_is_better": True,
@@ -413,7 +415,8 @@ def run_ours(args, wl, rank, world, device):
                    "voxelize_frac_of_hbm": round(vox_bytes / vox_ms / 1e6 / pk["hbm_gbs"], 4),
                    "rulebooks_ms": round(geo_ms, 4), "rulebooks_gbs": round(rb_bytes / geo_ms / 1e6, 1),
                    "rulebooks_frac_of_hbm": round(rb_bytes / geo_ms / 1e6 / pk["hbm_gbs"], 4),
-                   "rulebook_launches": hp.engine.launch_count() - len(hp.engine.steps),
+                   "rulebook_launches": hp.engine.launch_count(table0_built=True) - len(hp.engine.steps),
+                   "voxelize_launches": hp.voxelizer.LAUNCHES,
                    "height_compression_ms": round(bev_ms, 4),
                    "height_compression_gbs": round(bev_bytes / bev_ms / 1e6, 1),
                    "height_compression_frac_of_hbm": round(bev_bytes / bev_ms / 1e6 / pk["hbm_gbs"], 4),

@@ -30,6 +30,8 @@ PROTOTYPES = {
     "fv2p_voxelize_workspace_bytes": (_c_sz, [_c_i64, _c_int, _c_i64, _c_int, _c_i64]),
     "fv2p_voxelize_mean": (_c_int, [_c_vp, _c_vp, _c_i64, _c_int, _c_i64, _c_int, _c_vp, _c_vp, _c_int, _c_int,
                                     _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp, _c_sz, _c_vp, _c_vp]),
+    "fv2p_voxelize_mean_table": (_c_int, [_c_vp, _c_vp, _c_i64, _c_int, _c_i64, _c_int, _c_vp, _c_vp, _c_int, _c_int,
+                                    _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp, _c_sz, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp]),
     "fv2p_voxel_generate": (_c_int, [_c_vp, _c_i64, _c_int, _c_vp, _c_vp, _c_int, _c_int, _c_vp, _c_vp, _c_vp,
                                      _c_vp, _c_i64, _c_vp, _c_vp, _c_sz, _c_vp]),
     "fv2p_mean_vfe": (_c_int, [_c_vp, _c_vp, _c_i64, _c_int, _c_int, _c_vp, _c_vp]),

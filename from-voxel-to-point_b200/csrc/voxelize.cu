@@ -10,7 +10,11 @@
 //   rank     a point is its voxel's FIRST arrival iff first[slot] == its index; an ordered scan of
 //            those flags over the frame gives the voxel id the numba loop would have assigned.
 //            The point whose rank equals max_voxels is where that loop `break`s (:198-199):
-//            cut[frame] = its index, every point at or after it is dropped.
+//            cut[frame] = its index, every point at or after it is dropped.  ONE kernel: 512-point chunks
+//            handed out by ticket in frame-major order, a decoupled look-back scan per frame, frame totals
+//            (capped at max_voxels) published for the frames behind - the collate layout's row offsets -
+//            then coordinates, slot -> row, and, when the caller hands one in, the level-0 coordinate table
+//            of the sparse convolutions (the first thing they would otherwise build from these rows).
 //   select   each surviving point is pushed through a chain of atomicMin on sel[voxel][0..T): the chain
 //            conserves the multiset, so slot r ends up holding the (r+1)-th smallest point index -- the
 //            T lowest-index points of the voxel in index order, exactly what `num < max_points` keeps.
@@ -20,6 +24,7 @@
 // Coordinates use floorf((p - lo) / size) with IEEE-RN subtract and divide: reciprocal multiplies or
 // FMA contraction mis-bin points that sit on voxel faces ("hard parts").
 #include <limits.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -35,13 +40,22 @@ struct VoxGeom {
 constexpr int kMaxFeatures = 8;
 
 __global__ void __launch_bounds__(kThreads)
-vox_clear_kernel(unsigned long long *keys, int *first, uint32_t slots, int *cut, int batch) {
-  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < slots; s += gridDim.x * blockDim.x) {
+vox_clear_kernel(unsigned long long *keys, int *first, uint32_t slots, int *cut, int batch, unsigned long long *state,
+                 int chunks, int *frame_total, int *ticket, uint4 *table0, uint32_t table0_slots, uint4 table0_empty) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+  for (uint32_t s = t; s < slots; s += stride) {
     keys[s] = kEmptyKey;
     first[s] = INT_MAX;
   }
-  if (blockIdx.x == 0)
-    for (int b = threadIdx.x; b < batch; b += blockDim.x) cut[b] = INT_MAX;
+  for (uint32_t s = t; s < (uint32_t)chunks; s += stride) state[s] = 0ull;
+  for (uint32_t s = t; s < table0_slots; s += stride) table0[s] = table0_empty;
+  if (blockIdx.x == 0) {
+    for (int b = threadIdx.x; b < batch; b += blockDim.x) {
+      cut[b] = INT_MAX;
+      frame_total[b] = 0;
+    }
+    if (threadIdx.x == 0) *ticket = 0;
+  }
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -87,75 +101,81 @@ vox_insert_kernel(const float *__restrict__ points, const int *__restrict__ fram
   }
 }
 
-// flag(i) = point i opened its voxel.  counts[b][c] = number of flags in chunk c of frame b.
+// rank: see the file header.  state [batch * max_chunks] (look-back words, one chain per frame), frame_total [batch]
+// (rows of the frame + 1; 0 = not known yet) and ticket are zero when the kernel starts.
 __global__ void __launch_bounds__(kThreads)
-vox_count_first_kernel(const int *__restrict__ frame_offsets, int batch, int max_chunks,
-                       const int *__restrict__ pslot, const int *__restrict__ first, int *counts) {
-  const int work = batch * max_chunks;
-  for (int w = blockIdx.x; w < work; w += gridDim.x) {
-    const int b = w / max_chunks, c = w - b * max_chunks;
-    const int begin = frame_offsets[b], end = frame_offsets[b + 1];
-    const int base = begin + c * kChunk;
-    int total = 0;
-    if (base < end) {
-      for (int p = 0; p < kItemsPerThread; ++p) {
-        const int i = base + p * kThreads + threadIdx.x;
-        int flag = 0;
-        if (i < end) {
-          int s = pslot[i];
-          flag = (s >= 0) && (first[s] == i);
-        }
-        total += __syncthreads_count(flag);
-      }
-    }
-    if (threadIdx.x == 0) counts[w] = total;
-  }
-}
-
-__global__ void vox_offsets_kernel(const int *totals, int batch, int max_voxels, int64_t cap,
-                                   int *voxel_offsets, int *status) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  long long acc = 0;
-  voxel_offsets[0] = 0;
-  for (int b = 0; b < batch; ++b) {
-    int m = totals[b] < max_voxels ? totals[b] : max_voxels;
-    acc += m;
-    if (acc > cap) {
-      if (status) atomicOr(status, FV2P_STATUS_VOXEL_OVERFLOW);
-      acc = cap;
-    }
-    voxel_offsets[b + 1] = (int)acc;
-  }
-}
-
-__global__ void __launch_bounds__(kThreads)
-vox_assign_kernel(const int *__restrict__ frame_offsets, int batch, int max_chunks,
-                  const int *__restrict__ pslot, const int *__restrict__ first,
-                  const unsigned long long *__restrict__ keys, const int *__restrict__ chunk_prefix,
-                  const int *__restrict__ voxel_offsets, int max_voxels, int max_points, VoxGeom g,
-                  int *slot_vid, int *cut, int *coords, int *sel) {
+vox_rank_kernel(const int *__restrict__ frame_offsets, int batch, int max_chunks, const int *__restrict__ pslot,
+                const int *__restrict__ first, const unsigned long long *__restrict__ keys,
+                unsigned long long *state, int *frame_total, int *ticket, int max_voxels, int64_t cap,
+                int max_points, VoxGeom g, int *voxel_offsets, int *status, int *slot_vid, int *cut, int *coords,
+                int *sel, Slot *table0, uint32_t tmask0, int D0, int H0, int W0) {
   __shared__ int smem[kThreads / 32 + 1];
+  __shared__ int s_word;
+  __shared__ long long s_base;
   const int work = batch * max_chunks;
-  for (int w = blockIdx.x; w < work; w += gridDim.x) {
+  for (;;) {
+    if (threadIdx.x == 0) s_word = atomicAdd(ticket, 1);
+    __syncthreads();
+    const int w = s_word;
+    __syncthreads();
+    if (w >= work) break;
     const int b = w / max_chunks, c = w - b * max_chunks;
     const int begin = frame_offsets[b], end = frame_offsets[b + 1];
     const int base = begin + c * kChunk;
-    if (base >= end) continue;
-    const int vbase = voxel_offsets[b], vend = voxel_offsets[b + 1];
-    int running = chunk_prefix[w];
+    const bool empty_frame = end <= begin;
+    if (base >= end && !(empty_frame && c == 0)) continue;  // an empty frame still publishes its (zero) total
+    int flag[kItemsPerThread], slot[kItemsPerThread];
+    int total = 0;
+#pragma unroll
     for (int p = 0; p < kItemsPerThread; ++p) {
       const int i = base + p * kThreads + threadIdx.x;
-      int flag = 0, s = -1;
+      flag[p] = 0, slot[p] = -1;
       if (i < end) {
-        s = pslot[i];
-        flag = (s >= 0) && (first[s] == i);
+        slot[p] = pslot[i];
+        flag[p] = (slot[p] >= 0) && (first[slot[p]] == i);
       }
-      int total;
-      const int rank = running + block_exclusive_scan(flag, smem, total);
-      running += total;
-      if (flag) {
-        const int vid = vbase + rank;
-        if (rank < max_voxels && vid < vend) {
+      total += __syncthreads_count(flag[p]);
+    }
+    const int excl = empty_frame ? 0 : lookback_exclusive(state + (size_t)b * max_chunks, c, total, &s_word);
+    const bool last_chunk = empty_frame || base + kChunk >= end;
+    const int frame_rows = min(excl + total, max_voxels);
+    if (last_chunk && threadIdx.x == 0) *reinterpret_cast<volatile int *>(&frame_total[b]) = frame_rows + 1;
+    // rows of the frames before this one (their last chunks hold earlier tickets: they are running or done)
+    if (threadIdx.x < 32) {
+      long long acc = 0;
+      for (int bb = threadIdx.x; bb < b; bb += 32) {
+        int v;
+        do {
+          v = *reinterpret_cast<volatile int *>(&frame_total[bb]);
+        } while (v == 0);
+        acc += v - 1;
+      }
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, d);
+      if (threadIdx.x == 0) s_base = acc < (long long)cap ? acc : (long long)cap;
+    }
+    __syncthreads();
+    const long long vbase = s_base;
+    if (last_chunk && threadIdx.x == 0) {
+      long long e = vbase + frame_rows;
+      if (e > (long long)cap) {
+        if (status) atomicOr(status, FV2P_STATUS_VOXEL_OVERFLOW);
+        e = cap;
+      }
+      voxel_offsets[b + 1] = (int)e;
+      if (b == 0) voxel_offsets[0] = 0;
+    }
+    int running = excl;
+#pragma unroll
+    for (int p = 0; p < kItemsPerThread; ++p) {
+      const int i = base + p * kThreads + threadIdx.x;
+      int tot;
+      const int rank = running + block_exclusive_scan(flag[p], smem, tot);
+      running += tot;
+      if (flag[p]) {
+        const int s = slot[p];
+        const long long vid = vbase + rank;
+        if (rank < max_voxels && vid < (long long)cap) {
           unsigned long long key = keys[s];
           int x = (int)(key % (unsigned)g.grid[0]);
           key /= (unsigned)g.grid[0];
@@ -163,14 +183,22 @@ vox_assign_kernel(const int *__restrict__ frame_offsets, int batch, int max_chun
           key /= (unsigned)g.grid[1];
           int z = (int)(key % (unsigned)g.grid[2]);
           reinterpret_cast<int4 *>(coords)[vid] = make_int4(b, z, y, x);
-          slot_vid[s] = vid;
+          slot_vid[s] = (int)vid;
           for (int t = 0; t < max_points; ++t) sel[(size_t)vid * max_points + t] = INT_MAX;
+          if (table0) {  // what fv2p_table_build does with these rows (rulebook.cu:table_insert_kernel)
+            // every voxel is inserted exactly once here, so the value is a plain store (table_insert_kernel must
+            // expect duplicate coordinates from arbitrary callers and keeps the largest row with an atomicMin)
+            const uint32_t ts = slot_insert(table0, tmask0, voxel_key(b, z, y, x, D0, H0, W0));
+            if (ts != 0xFFFFFFFFu) table0[ts].val = ~(int)vid;
+            else if (status) atomicOr(status, FV2P_STATUS_OUT_OVERFLOW);
+          }
         } else {
           slot_vid[s] = -1;
           if (rank == max_voxels) cut[b] = i;  // the numba loop breaks here (voxel_generator.py:198)
         }
       }
     }
+    __syncthreads();  // s_base / s_word are rewritten by the next item
   }
 }
 
@@ -252,7 +280,8 @@ mean_vfe_kernel(const float *__restrict__ voxels, const int *__restrict__ num_po
 
 struct VoxWorkspace {
   unsigned long long *keys;
-  int *first, *slot_vid, *pslot, *counts, *totals, *cut, *sel, *scratch;
+  int *first, *slot_vid, *pslot, *frame_total, *cut, *sel, *scratch;
+  unsigned long long *state;
   uint32_t slots;
   int max_chunks;
   size_t bytes;
@@ -269,8 +298,8 @@ VoxWorkspace carve(void *ws, int64_t total_points, int batch, int64_t max_frame_
   w.first = c.take<int>(w.slots);
   w.slot_vid = c.take<int>(w.slots);
   w.pslot = c.take<int>(total_points > 0 ? total_points : 1);
-  w.counts = c.take<int>((size_t)batch * w.max_chunks);
-  w.totals = c.take<int>(batch);
+  w.state = c.take<unsigned long long>((size_t)batch * w.max_chunks);
+  w.frame_total = c.take<int>(batch);
   w.cut = c.take<int>(batch);
   w.sel = c.take<int>((size_t)(cap > 0 ? cap : 1) * max_points);
   w.scratch = c.take<int>(16);
@@ -296,7 +325,23 @@ extern "C" int fv2p_voxelize_mean(const float *points, const int32_t *frame_offs
                                   int32_t *num_points, float *voxels, int32_t *voxel_offsets, int64_t cap,
                                   int32_t *status_dev, void *workspace, size_t workspace_bytes,
                                   fv2p_stream_t stream_, fv2p_stream_t features_stream_) {
+  return fv2p_voxelize_mean_table(points, frame_offsets, total_points, batch, max_frame_points, num_features, range6,
+                                  vsize3, max_points, max_voxels, coords, voxel_features, num_points, voxels,
+                                  voxel_offsets, cap, status_dev, workspace, workspace_bytes, stream_,
+                                  features_stream_, nullptr, 0, nullptr);
+}
+
+extern "C" int fv2p_voxelize_mean_table(const float *points, const int32_t *frame_offsets, int64_t total_points,
+                                        int batch, int64_t max_frame_points, int num_features,
+                                        const float *range6, const float *vsize3, int max_points,
+                                        int max_voxels, int32_t *coords, float *voxel_features,
+                                        int32_t *num_points, float *voxels, int32_t *voxel_offsets, int64_t cap,
+                                        int32_t *status_dev, void *workspace, size_t workspace_bytes,
+                                        fv2p_stream_t stream_, fv2p_stream_t features_stream_, void *level0_table,
+                                        int64_t table_row_cap, const int32_t *shape3) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  FV2P_REQUIRE(!level0_table || (shape3 && table_row_cap >= cap && table_row_cap < (1ll << 26)),
+               "voxelize: the level-0 table needs its shape and a row capacity >= cap");
   FV2P_REQUIRE(batch >= 1 && batch <= 4096, "voxelize: batch must be in [1,4096], got %d", batch);
   FV2P_REQUIRE(num_features >= 3 && num_features <= kMaxFeatures,
                "voxelize: num_features must be in [3,%d], got %d", kMaxFeatures, num_features);
@@ -323,17 +368,27 @@ extern "C" int fv2p_voxelize_mean(const float *points, const int32_t *frame_offs
     return FV2P_ERR_WORKSPACE;
   }
   const int grid = persistent_grid();
-  vox_clear_kernel<<<grid, kThreads, 0, stream>>>(w.keys, w.first, w.slots, w.cut, batch);
+  Slot *table0 = static_cast<Slot *>(level0_table);
+  const uint32_t t0_slots = table0 ? table_slots_cap(table_row_cap) : 0u;
+  Slot empty_slot;
+  empty_slot.key = kEmptyKey, empty_slot.val = kValEmpty, empty_slot.aux = 0;
+  uint4 empty4;
+  static_assert(sizeof(Slot) == sizeof(uint4), "Slot is one 16-byte word");
+  memcpy(&empty4, &empty_slot, sizeof(uint4));
+  vox_clear_kernel<<<grid, kThreads, 0, stream>>>(w.keys, w.first, w.slots, w.cut, batch, w.state,
+                                                  batch * w.max_chunks, w.frame_total, w.scratch,
+                                                  reinterpret_cast<uint4 *>(table0), t0_slots, empty4);
   vox_insert_kernel<<<grid, kThreads, 0, stream>>>(points, frame_offsets, batch, w.max_chunks, num_features, g,
                                                    w.keys, w.first, w.slots - 1, w.pslot);
-  vox_count_first_kernel<<<grid, kThreads, 0, stream>>>(frame_offsets, batch, w.max_chunks, w.pslot, w.first,
-                                                        w.counts);
-  launch_scan_chunk_counts(w.counts, batch, w.max_chunks, nullptr, (int64_t)w.max_chunks * kChunk, w.totals,
-                           stream);
-  vox_offsets_kernel<<<1, 32, 0, stream>>>(w.totals, batch, max_voxels, cap, voxel_offsets, status_dev);
-  vox_assign_kernel<<<grid, kThreads, 0, stream>>>(frame_offsets, batch, w.max_chunks, w.pslot, w.first, w.keys,
-                                                   w.counts, voxel_offsets, max_voxels, max_points, g,
-                                                   w.slot_vid, w.cut, coords, w.sel);
+  // 40 registers: six CTAs per SM hold more of the chunks' dependent loads (point -> slot -> first arrival -> key)
+  // in flight than the default four
+  const int rank_work = batch * w.max_chunks;
+  const int rank_cap = persistent_grid(6);
+  vox_rank_kernel<<<rank_work < rank_cap ? rank_work : rank_cap, kThreads, 0, stream>>>(frame_offsets, batch, w.max_chunks, w.pslot, w.first, w.keys, w.state,
+                                                 w.frame_total, w.scratch, max_voxels, cap, max_points, g,
+                                                 voxel_offsets, status_dev, w.slot_vid, w.cut, coords, w.sel, table0,
+                                                 t0_slots ? t0_slots - 1 : 0u, shape3 ? shape3[0] : 0,
+                                                 shape3 ? shape3[1] : 0, shape3 ? shape3[2] : 0);
   // coords and voxel_offsets are final here; the point selection and the means can leave the caller's chain
   stream = fork_stream(stream, features_stream_);
   vox_select_kernel<<<grid, kThreads, 0, stream>>>(frame_offsets, batch, w.max_chunks, w.pslot, w.slot_vid, w.cut,

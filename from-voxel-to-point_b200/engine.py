@@ -368,6 +368,7 @@ class BackboneEngine(object):
             if d["sorted"]:
                 items.append((_lib.PREFILL_GROUP_WS, d["group_ws"], caps[bk.out_level], 0))
         a["prefill"] = _lib.prefill_items(items)
+        a["prefill_no_table0"] = _lib.prefill_items(items[1:])  # the voxelizer clears and builds the level-0 table
         # two scheduler words per conv step (tile counter, CTAs done); zero between launches, the kernel re-arms them
         a["sched"] = torch.zeros((len(self.steps), 2), dtype=torch.int32, device=device)
         # feature buffers with liveness-based reuse
@@ -419,7 +420,7 @@ class BackboneEngine(object):
             self._side = [torch.cuda.Stream(device=device) for _ in range(self.SIDE_STREAMS + 3)]
         return self._side[:-3], self._side[-3], self._side[-2], self._side[-1]
 
-    def prefill(self, device, cap0, batch_size):
+    def prefill(self, device, cap0, batch_size, table0_external=False):
         """Enqueues the step's ONE clearing launch (tables, scan states, -1 fills) on a side stream forked from the
         current stream, so that it runs next to whatever the caller enqueues next (the voxelizer).  Returns the event
         to hand to launch(prefilled=...).  Nothing of the previous step may still be reading the arena on another
@@ -432,19 +433,26 @@ class BackboneEngine(object):
         ev = torch.cuda.Event()
         ev.record(main)
         s_fill.wait_event(ev)
-        items, n_items = a["prefill"]
+        items, n_items = a["prefill_no_table0" if table0_external else "prefill"]
         with torch.cuda.device(device), torch.cuda.stream(s_fill):
             _lib.check(_lib.load().fv2p_geometry_prefill(items, n_items, _lib.stream_ptr(device)), "geometry_prefill")
         done = torch.cuda.Event()
         done.record(s_fill)
         return done
 
+    def level0_table(self, device, cap0, batch_size):
+        """(table buffer, row capacity, spatial shape) of the level-0 coordinate table, for a voxelizer that builds it
+        while it assigns the voxel rows (BatchVoxelizer(level0_table=...), then launch(table0_built=True))."""
+        a = self._ensure_arena(device, max(int(cap0), 1), int(batch_size))
+        return a["tables"][0], a["caps"][0], [int(v) for v in self.level_shapes[0]]
+
     def launch(self, voxel_features, voxel_coords, batch_size, n0_dev=None, cap0=None, features_ready=None,
-               prefilled=None, run_convs=True):
+               prefilled=None, run_convs=True, table0_built=False):
         """Enqueues geometry + feature passes on the current stream.  No host sync.
         ``features_ready``: event after which voxel_features may be read (None: already ordered on this stream).
         ``prefilled``: event from prefill() when the clearing launch was already enqueued (None: done here).
         ``run_convs``: False enqueues the geometry pass only (bench.py times it on its own that way).
+        ``table0_built``: the level-0 coordinate table already holds these coordinates (see level0_table()).
 
         voxel_features [>=cap0, F] fp32, voxel_coords [>=cap0, 4] int32, both CUDA and contiguous;
         live row count = *n0_dev (device int32) if given, else cap0 (defaults to voxel_coords.shape[0]).
@@ -500,11 +508,12 @@ class BackboneEngine(object):
             if prefilled is not None:
                 main.wait_event(prefilled)
             else:
-                items, n_items = a["prefill"]
+                items, n_items = a["prefill_no_table0" if table0_built else "prefill"]
                 _lib.check(lib.fv2p_geometry_prefill(items, n_items, _lib.stream_ptr(device)), "geometry_prefill")
-            _lib.check(lib.fv2p_table_build(_lib.ptr(voxel_coords), cap0, n_ptr[0], _lib.i32x3(self.level_shapes[0]),
-                                            _lib.ptr(a["tables"][0]), caps[0], status_ptr, PRE,
-                                            _lib.stream_ptr(device)), "table_build")
+            if not table0_built:
+                _lib.check(lib.fv2p_table_build(_lib.ptr(voxel_coords), cap0, n_ptr[0],
+                                                _lib.i32x3(self.level_shapes[0]), _lib.ptr(a["tables"][0]), caps[0],
+                                                status_ptr, PRE, _lib.stream_ptr(device)), "table_build")
             level_ready = {0: mark(main)}
             built, grouped = {}, {}
             forked = []  # streams that joined this step (a captured step may only be joined by streams it forked)
@@ -684,11 +693,12 @@ class BackboneEngine(object):
                     self.level_shapes[bk.in_level])
         return make
 
-    def launch_count(self):
-        """Kernels of libfv2p_b200 enqueued by one launch(): one prefill, the level-0 table, 1 launch per submanifold
+    def launch_count(self, table0_built=False):
+        """Kernels of libfv2p_b200 enqueued by one launch(): one prefill, the level-0 table (unless the voxelizer built
+        it), 1 launch per submanifold
         and 3 per strided rulebook, 2 per row grouping, one fused conv per layer (+ the pair lists when they are
         materialised with the step: counts, scan, compaction, and the input-side probe for strided rulebooks)."""
-        n = len(self.steps) + 2
+        n = len(self.steps) + (1 if table0_built else 2)
         a = self.arena
         geo = a["geo"] if a is not None else None
         if geo is None:

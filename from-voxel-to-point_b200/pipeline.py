@@ -135,11 +135,13 @@ class HotPath(object):
         # the step's clearing launch (tables, scan states, -1 fills) depends on nothing: it runs on a side stream next to
         # the voxelizer instead of between it and the first rulebook
         cap = voxelizer.capacity(points_dev.device, points_dev.shape[0], batch, points_dev.shape[1])
-        prefilled = engine.prefill(points_dev.device, cap, batch)
-        vox = voxelizer(points_dev, frame_offsets_dev, max_frame_points, features_stream=fs)
+        prefilled = engine.prefill(points_dev.device, cap, batch, table0_external=True)
+        # the voxelizer also builds the convolutions' level-0 coordinate table while it assigns the voxel rows
+        vox = voxelizer(points_dev, frame_offsets_dev, max_frame_points, features_stream=fs,
+                        level0_table=engine.level0_table(points_dev.device, cap, batch))
         n0 = vox["voxel_offsets"][batch:batch + 1]
         arena = engine.launch(vox["voxel_features"], vox["voxel_coords"], batch, n0_dev=n0, cap0=vox["cap"],
-                              features_ready=vox["features_ready"], prefilled=prefilled)
+                              features_ready=vox["features_ready"], prefilled=prefilled, table0_built=True)
         handle = dict(vox=vox, arena=arena, batch=batch)
         if self.bev:
             handle["spatial_features"] = self._height_compression(engine, arena, batch, lane)

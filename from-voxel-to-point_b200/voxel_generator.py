@@ -93,6 +93,8 @@ class BatchVoxelizer(object):
     (``voxel_offsets[batch]``).  Does not synchronise.
     """
 
+    LAUNCHES = 5  # kernels per call: clear, insert, rank (+ level-0 table), select, reduce
+
     def __init__(self, voxel_size, point_cloud_range, max_num_points, max_voxels, want_voxels=False):
         self.vg = VoxelGenerator(voxel_size, point_cloud_range, max_num_points, max_voxels)
         self.want_voxels = want_voxels
@@ -125,12 +127,16 @@ class BatchVoxelizer(object):
         """Row capacity of the output buffers a call with these sizes will use (allocates them if needed)."""
         return self._ensure(device, total_points, batch, f)["cap"]
 
-    def __call__(self, points, frame_offsets, max_frame_points=None, features_stream=None):
+    def __call__(self, points, frame_offsets, max_frame_points=None, features_stream=None, level0_table=None):
         """points [P,F] fp32 CUDA, frame_offsets [B+1] int32 CUDA.  Returns a dict of device buffers sized at
         capacity plus 'voxel_offsets' [B+1]; live rows are [:voxel_offsets[B]].
 
         With ``features_stream`` the coordinates are complete on the current stream and the means / point counts on
-        that stream; 'features_ready' is then the event to wait for before reading them."""
+        that stream; 'features_ready' is then the event to wait for before reading them.
+
+        ``level0_table`` = (table buffer, its row capacity, spatial shape [D,H,W]): the call also builds the sparse
+        convolutions' level-0 coordinate table (fv2p_voxelize_mean_table) - BackboneEngine.level0_table() hands it out
+        and launch(table0_built=True) then skips fv2p_table_build."""
         dev = _lib.require_device(points)
         assert points.dtype == torch.float32 and points.is_contiguous()
         assert frame_offsets.dtype == torch.int32 and frame_offsets.is_cuda
@@ -139,13 +145,15 @@ class BatchVoxelizer(object):
         b = self._ensure(points.device, p, batch, f)
         vg = self.vg
         with torch.cuda.device(dev):
-            st = _lib.load().fv2p_voxelize_mean(
+            table, table_cap, shape3 = level0_table if level0_table is not None else (None, 0, None)
+            st = _lib.load().fv2p_voxelize_mean_table(
                 _lib.ptr(points), _lib.ptr(frame_offsets), p, batch, int(max_frame_points or p), f,
                 _lib.f32arr(vg._point_cloud_range), _lib.f32arr(vg._voxel_size), int(vg._max_num_points),
                 int(vg._max_voxels), _lib.ptr(b["coords"]), _lib.ptr(b["feats"]), _lib.ptr(b["num"]),
                 _lib.ptr(b["voxels"]), _lib.ptr(b["voff"]), b["cap"], _lib.ptr(b["status"]), _lib.ptr(b["ws"]),
                 b["ws"].numel(), _lib.stream_ptr(points.device),
-                _lib.ctypes.c_void_p(features_stream.cuda_stream) if features_stream is not None else None)
+                _lib.ctypes.c_void_p(features_stream.cuda_stream) if features_stream is not None else None,
+                _lib.ptr(table), int(table_cap), _lib.i32x3(shape3) if shape3 is not None else None)
         _lib.check(st, "voxelize_mean")
         ready = None
         if features_stream is not None:

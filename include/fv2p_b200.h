@@ -110,6 +110,20 @@ FV2P_API int fv2p_voxelize_mean(const float *points, const int32_t *frame_offset
                        int32_t *voxel_offsets, int64_t cap, int32_t *status_dev, void *workspace,
                        size_t workspace_bytes, fv2p_stream_t stream, fv2p_stream_t features_stream);
 
+/* The same call, which ALSO builds the level-0 coordinate table of the sparse convolutions (what fv2p_table_build would
+ * make of `coords` right afterwards) while it assigns the voxel rows: one launch and one pass over the coordinates
+ * less at the head of the step.  level0_table: fv2p_table_bytes(table_row_cap) bytes, cleared by this call;
+ * table_row_cap >= cap; shape3 = the spatial shape [D,H,W] the convolutions use for these coordinates
+ * (spconv_backbone.py:80: grid_size[::-1] + [1,0,0]).  level0_table == NULL: exactly fv2p_voxelize_mean. */
+FV2P_API int fv2p_voxelize_mean_table(const float *points, const int32_t *frame_offsets, int64_t total_points,
+                                      int batch, int64_t max_frame_points, int num_features,
+                                      const float *range6, const float *vsize3, int max_points,
+                                      int max_voxels, int32_t *coords, float *voxel_features,
+                                      int32_t *num_points, float *voxels, int32_t *voxel_offsets, int64_t cap,
+                                      int32_t *status_dev, void *workspace, size_t workspace_bytes,
+                                      fv2p_stream_t stream, fv2p_stream_t features_stream, void *level0_table,
+                                      int64_t table_row_cap, const int32_t *shape3);
+
 /* Reference-shaped single-frame entry (VoxelGenerator.generate): synchronises and returns the voxel
  * count through *num_voxels_host.  Outputs as above with batch = 1 (coords still [M,4]). */
 FV2P_API int fv2p_voxel_generate(const float *points, int64_t num_points_in, int num_features,

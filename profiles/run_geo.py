@@ -27,4 +27,4 @@ for _ in range(a.steps):
     flush.zero_()
     h = hp.launch_resident(pts, off, mfp)
     outs, info = hp.finish(h)
-print("rows per level", info["counts"], "launches per step", hp.engine.launch_count() + 8)
+print("rows per level", info["counts"], "launches per step", hp.engine.launch_count(table0_built=True) + hp.voxelizer.LAUNCHES)

@@ -635,3 +635,51 @@ def test_capacity_overflow_grows_the_arena_and_reruns():
         res.append((info["counts"], enc.indices.cpu().numpy().copy(), enc.features.cpu().numpy().copy()))
     for r in res[1:]:
         assert r[0] == res[0][0] and np.array_equal(r[1], res[0][1]) and np.array_equal(r[2], res[0][2])
+
+
+def test_voxelizer_builds_the_level0_coordinate_table():
+    """fv2p_voxelize_mean_table: the table the voxelizer fills while it assigns rows serves the submanifold probe
+    exactly like the one fv2p_table_build makes from the finished coordinates - ragged batch, an empty frame, and a
+    frame that hits max_voxels (rows past the cut must not be in the table)."""
+    cfg = synth.DATASETS["kitti"]
+    frames = [synth.lidar_frame("kitti", seed=s, az_steps=a) for s, a in ((11, 200), (12, 60), (13, 500))]
+    frames.insert(1, np.zeros((0, 4), np.float32))
+    max_voxels = 7000  # the last frame has more voxels than that
+    offs = np.concatenate([[0], np.cumsum([f.shape[0] for f in frames])]).astype(np.int32)
+    lib = _lib.load()
+    shape = [int(v) for v in (np.array(synth.grid_size(cfg))[::-1] + [1, 0, 0])]
+    bv = fv2p_b200.BatchVoxelizer(cfg["voxel_size"], cfg["point_cloud_range"], 5, max_voxels)
+    pts = cuda(np.concatenate(frames))
+    cap = bv.capacity(pts.device, pts.shape[0], len(frames), 4)
+    row_cap = cap + 1000
+    table = torch.empty(lib.fv2p_table_bytes(row_cap) + 16, dtype=torch.uint8, device="cuda")
+    table.fill_(0x5A)  # garbage: the call clears it
+    out = bv(pts, cuda(offs), max(f.shape[0] for f in frames), level0_table=(table, row_cap, shape))
+    voff = out["voxel_offsets"].cpu().numpy()
+    m = int(voff[-1])
+    assert voff[2] == voff[1] and voff[4] - voff[3] == max_voxels
+    coords = out["voxel_coords"][:m].contiguous()
+    # the plain call gives the same rows (and the oracle checks of the other tests apply to it)
+    plain = fv2p_b200.BatchVoxelizer(cfg["voxel_size"], cfg["point_cloud_range"], 5, max_voxels)(
+        pts, cuda(offs), max(f.shape[0] for f in frames))
+    assert np.array_equal(plain["voxel_offsets"].cpu().numpy(), voff)
+    assert torch.equal(plain["voxel_coords"][:m], coords)
+    assert torch.equal(plain["voxel_features"][:m], out["voxel_features"][:m])
+    ref_table = torch.empty_like(table)
+    status = torch.zeros(1, dtype=torch.int32, device="cuda")
+    _lib.check(lib.fv2p_table_build(_lib.ptr(coords), m, None, _lib.i32x3(shape), _lib.ptr(ref_table), row_cap,
+                                    _lib.ptr(status), 0, _lib.stream_ptr(coords.device)), "table_build")
+    nbrs = []
+    for t in (table, ref_table):
+        nbr = torch.empty((27, (m + 127) // 128 * 128), dtype=torch.int32, device="cuda")
+        _lib.check(lib.fv2p_subm_neighbours(_lib.ptr(coords), m, None, len(frames), _lib.i32x3(shape),
+                                            _lib.i32x3([3, 3, 3]), _lib.i32x3([1, 1, 1]), _lib.ptr(t), row_cap,
+                                            _lib.ptr(nbr), nbr.shape[1], 0, _lib.stream_ptr(coords.device)),
+                   "subm_neighbours")
+        nbrs.append(nbr[:, :m])
+    assert torch.equal(nbrs[0], nbrs[1])
+    assert int((nbrs[0][13] == torch.arange(m, device="cuda", dtype=torch.int32)).all())
+    # slot-for-slot: same keys present with the same rows (probe order may place them in different slots)
+    a = np.sort(table.cpu().numpy()[:lib.fv2p_table_bytes(row_cap)].view(np.int64).reshape(-1, 2), axis=0)
+    b = np.sort(ref_table.cpu().numpy()[:lib.fv2p_table_bytes(row_cap)].view(np.int64).reshape(-1, 2), axis=0)
+    assert np.array_equal(a, b)
