@@ -192,10 +192,26 @@ def measure(hp, batches, device, steps, warmup, flush, barrier):
         h2d += hp.upload(batches[j], device, slot=j)[3]
     torch.cuda.synchronize()
 
+    # a step of several launches alternates them between two engine lanes on two streams, like HotPath.run_stream: the
+    # head of launch j+1 (voxelizer, first rulebooks - small dependent kernels) runs under the convolutions of launch j
+    n_lanes = min(2, len(batches), hp.lanes)
+    main = torch.cuda.current_stream(device)
+    lane_streams = [main] + [torch.cuda.Stream(device=device) for _ in range(n_lanes - 1)]
+
     def one_pass():
         handle = None
+        if n_lanes > 1:
+            fork = torch.cuda.Event()
+            fork.record(main)
+            for st in lane_streams[1:]:
+                st.wait_event(fork)
         for j in range(len(batches)):
-            handle = hp.launch_graph(slot=j) if hp.use_graph else hp.launch_resident(*hp.staged(j))
+            lane = j % n_lanes
+            with torch.cuda.stream(lane_streams[lane]):
+                handle = hp.launch_graph(slot=j, lane=lane) if hp.use_graph else \
+                    hp.launch_resident(*hp.staged(j), lane=lane)
+        for st in lane_streams[1:]:
+            main.wait_stream(st)
         return handle
 
     for _ in range(warmup):
@@ -217,12 +233,13 @@ def measure(hp, batches, device, steps, warmup, flush, barrier):
     # end to end through the public API with host buffers: per launch one pinned H2D of the points, one graph replay,
     # D2H of the row counts + stride-8 features and indices; copies of launch i overlap the kernels of launch i+1.
     # Every launch is synchronised on the host when its result lands.
-    for _ in hp.run_stream((b for _ in range(max(2, warmup)) for b in batches), device):
+    depth = int(os.environ.get("FV2P_STREAM_DEPTH", "2"))
+    for _ in hp.run_stream((b for _ in range(max(2 * depth, warmup)) for b in batches), device, depth):  # slots x lanes of graphs
         pass
     barrier()
     t1 = time.perf_counter()
     d2h = 0
-    for res in hp.run_stream((b for _ in range(steps) for b in batches), device):
+    for res in hp.run_stream((b for _ in range(steps) for b in batches), device, depth):
         d2h += res["d2h_bytes"]
         assert res["encoded_features"].shape[0] == res["counts"][-1]
     torch.cuda.synchronize()
@@ -400,7 +417,8 @@ def run_ours(args, wl, rank, world, device):
                    "frames_per_launch": wl["batch"], "launches_per_gpu_per_step": len(batches),
                    "frames_of_rank0": [lo, hi], "precision": precision,
                    "l2": "flushed between timed steps (512 MiB memset, untimed)",
-                   "launch": "one CUDA graph replay per launch" if hp.use_graph else "eager launches",
+                   "launch": ("one CUDA graph replay per launch" if hp.use_graph else "eager launches") +
+                             ("; launches alternate between two engine lanes on two streams" if len(batches) > 1 else ""),
                    "parallelism": "frames sharded per GPU (strong scaling of the fixed batch), no collective on the "
                                   "data path" if world > 1 else "one GPU",
                    "rows_per_level_last_launch": counts, "points_last_launch": P},

@@ -47,6 +47,7 @@ class HotPath(object):
         self._slots = {}
         self._graphs = {}
         self._copy_stream = None
+        self._copy_in_stream = None
         self._enc_host = None
 
     # ------------------------------------------------------------------ host -> device
@@ -69,10 +70,10 @@ class HotPath(object):
     def _stage(self):
         return self._slots.get(0)
 
-    def upload(self, frames, device="cuda", slot=0, stream=None):
+    def upload(self, frames, device="cuda", slot=0, stream=None, after=None):
         """frames: list of [P_b,F] float32 numpy arrays (or CPU tensors).  Packs them into pinned memory and
-        enqueues the H2D copies (on `stream` if given).  Returns (points_dev [P,F], frame_offsets_dev [B+1],
-        max_frame_points, bytes)."""
+        enqueues the H2D copies (on `stream` if given, there after the event `after`: whatever still reads the slot's
+        device buffer).  Returns (points_dev [P,F], frame_offsets_dev [B+1], max_frame_points, bytes)."""
         device = torch.device(device)
         if device.index is None:
             device = torch.device("cuda", torch.cuda.current_device())
@@ -99,6 +100,8 @@ class HotPath(object):
         s["host_off"].numpy()[:] = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
         ctx = torch.cuda.stream(stream) if stream is not None else _NullCtx()
         with ctx:
+            if after is not None:
+                torch.cuda.current_stream(device).wait_event(after)
             s["dev_pts"][:total].copy_(s["host_pts"][:total], non_blocking=True)
             s["dev_off"].copy_(s["host_off"], non_blocking=True)
         nbytes = total * f * 4 + (len(frames) + 1) * 4
@@ -269,16 +272,21 @@ class HotPath(object):
         batch with HOST results: 'counts' (rows per level), 'encoded_features' [N,C] and 'encoded_indices' [N,4]
         (pinned tensors, valid until `depth` further batches have been yielded), 'h2d_bytes', 'd2h_bytes'.
 
-        Same work per batch as __call__(fetch='encoded'), but double buffered: the H2D copy of batch i+1 and the
-        D2H copy of batch i run on a copy stream while the kernels of the other batch run.  The result of a step is
-        snapshotted on the device (live rows only) right after the step, so the arena can be reused at once.
+        Same work per batch as __call__(fetch='encoded'), but pipelined: `depth` batches are in flight (staging
+        slots), their kernels alternate between the engine lanes, the H2D copy of batch i+1 and the D2H copy of
+        batch i-depth+1 run on two copy streams meanwhile, and batch i+1 is packed into pinned memory by a helper
+        thread while this one waits for a result.  Deeper pipelines (3, 4, 6 slots) measured the same throughput on
+        one B200: the kernels set the pace (profiles/r2_notes.md).  The result of a step is snapshotted on the device
+        (live rows only) right after the step, so the arena can be reused at once.
         """
         device = torch.device(device)
         if device.index is None:
             device = torch.device("cuda", torch.cuda.current_device())
         if self._copy_stream is None or self._copy_stream.device != device:
             self._copy_stream = torch.cuda.Stream(device=device)
-        copy, main = self._copy_stream, torch.cuda.current_stream(device)
+            self._copy_in_stream = torch.cuda.Stream(device=device)
+        # results leave on `copy`, points arrive on `copy_in`: PCIe is full duplex, one stream would serialise them
+        copy, copy_in, main = self._copy_stream, self._copy_in_stream, torch.cuda.current_stream(device)
         lib = _lib.load()
         out_step = [st for st in self.engine.steps if st.export == "out"][0]
         n_lanes = min(self.lanes, depth)
@@ -292,14 +300,33 @@ class HotPath(object):
                 st = self._lane_streams[(device, lane)] = torch.cuda.Stream(device=device)
             st.wait_stream(main)
             streams.append(st)
-        pending = []
-        for i, frames in enumerate(batches):
+        copy_in.wait_stream(main)
+        # Staging runs one batch ahead on a helper thread: while this thread waits for the kernels and the D2H copy of
+        # batch i-1, batch i+1 is packed into its slot's pinned buffer (the memcpy and the CUDA waits release the GIL)
+        # and its H2D copy is enqueued behind the last kernels that read the slot's device buffer.  Without it the
+        # host's serial work per batch (pack + D2H wait) was as long as the kernels and set the pace.
+        slot_busy = {}  # slot -> (H2D finished: the pinned buffer is free, kernels finished: the device buffer is free)
+
+        def stage(i, frames):
             slot = i % depth
-            lane = slot % n_lanes
+            with torch.cuda.device(device):
+                h2d_done, kernels_done = slot_busy.get(slot, (None, None))
+                if h2d_done is not None:
+                    h2d_done.synchronize()
+                pts, off, mfp, h2d = self.upload(frames, device, slot=slot, stream=copy_in, after=kernels_done)
+                up = torch.cuda.Event()
+                up.record(copy_in)
+            return slot, pts, off, mfp, h2d, up
+
+        it = iter(batches)
+        first = next(it, None)
+        fut = _stage_pool().submit(stage, 0, first) if first is not None else None
+        pending = []
+        i = 0
+        while fut is not None:
+            slot, pts, off, mfp, h2d, up = fut.result()
+            lane = i % n_lanes
             stream = streams[lane]
-            pts, off, mfp, h2d = self.upload(frames, device, slot=slot, stream=copy)
-            up = torch.cuda.Event()
-            up.record(copy)
             stream.wait_event(up)
             with torch.cuda.stream(stream):
                 handle = self.launch_graph(slot, lane) if self.use_graph else self.launch_resident(pts, off, mfp, lane)
@@ -318,13 +345,19 @@ class HotPath(object):
                     snap["counts"].copy_(arena["counts"], non_blocking=True)
                 done = torch.cuda.Event()
                 done.record(stream)
+            slot_busy[slot] = (up, done)
             pending.append((slot, snap, done, h2d, src_f.shape[1], src_f.dtype))
+            # the next batch's staging starts now (its slot was last used by batch i + 1 - depth, already launched)
+            nxt = next(it, None)
+            i += 1
+            fut = _stage_pool().submit(stage, i, nxt) if nxt is not None else None
             if len(pending) >= depth:
                 yield self._collect(pending.pop(0), copy)
         while pending:
             yield self._collect(pending.pop(0), copy)
         for st in streams[1:]:
             main.wait_stream(st)
+        main.wait_stream(copy_in)
 
     def _snapshot(self, slot, feat, ind, counts):
         key = ("snap", slot)
@@ -361,6 +394,16 @@ class HotPath(object):
 
 
 _POOL = None
+_STAGE_POOL = None
+
+
+def _stage_pool():
+    """One helper thread that packs and uploads the next batch of run_stream."""
+    global _STAGE_POOL
+    if _STAGE_POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _STAGE_POOL = ThreadPoolExecutor(max_workers=1, thread_name_prefix="fv2p-stage")
+    return _STAGE_POOL
 
 
 def _pack_pool():

@@ -478,9 +478,13 @@ def test_run_stream_matches_single_calls_and_graph_replay():
         # size the staging for the largest batch first (a graph serves anything up to its capture capacity)
         hp.upload(max(batches, key=lambda b: sum(f.shape[0] for f in b)), slot=0)
         hp.upload(max(batches, key=lambda b: sum(f.shape[0] for f in b)), slot=1)
+        hp.upload(max(batches, key=lambda b: sum(f.shape[0] for f in b)), slot=2)
         got = []
         for res in hp.run_stream(iter(batches)):
             got.append((res["counts"], res["encoded_features"].clone(), res["encoded_indices"].clone()))
+        for res in hp.run_stream(iter(batches[:3]), depth=2):  # the double-buffered form
+            got.append((res["counts"], res["encoded_features"].clone(), res["encoded_indices"].clone()))
+        expect = expect + expect[:3] if len(expect) == len(batches) else expect
         assert len(got) == len(expect)
         for (c0, f0, i0), (c1, f1, i1) in zip(expect, got):
             assert c0 == c1
