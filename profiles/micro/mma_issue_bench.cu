@@ -36,6 +36,11 @@ __device__ __forceinline__ void tc_mma(uint32_t d, uint64_t a, uint64_t b, uint3
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
 }
+// A operand from tensor memory (kind::f16)
+__device__ __forceinline__ void tc_mma_ts(uint32_t d, uint32_t a_tmem, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+               ::"r"(d), "r"(a_tmem), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
 __device__ __forceinline__ uint32_t elect_one_sync() {
   uint32_t pred = 0, laneid = 0;
   asm volatile("{\n\t.reg .b32 %%rx;\n\t.reg .pred %%px;\n\telect.sync %%rx|%%px, %2;\n\t@%%px mov.s32 %1, 1;\n\tmov.s32 %0, %%rx;\n\t}"
@@ -57,6 +62,8 @@ __host__ __device__ constexpr uint32_t instr_desc(int n, bool tf32) {
 // 128 = wait for the stage's own commit right away (issue -> execute -> arrive latency),
 // 256 = one elect.sync outside the stage loop: the elected thread alone runs it (no per-stage elect / syncwarp),
 //       no slot waits; with 32 also no commits except every 4th stage
+// 512 = with 256: the A operand comes from TMEM (columns 128.. of the allocation) instead of shared memory (kind::f16 only);
+// 1024 = with 256: alternate SS (tf32 / f16 as the template says) and TS f16 MMAs, the 3xTF32 path's mix
 template <bool kTf32>
 __global__ void __launch_bounds__(128, 1)
 issue_kernel(int n, int mmas_per_stage, int stages, int variant, unsigned long long *cycles) {
@@ -95,8 +102,20 @@ issue_kernel(int n, int mmas_per_stage, int stages, int variant, unsigned long l
       if (elect_one_sync()) {
         for (int st = 0; st < stages; ++st) {
           const int s = st & 7;
-          for (int j = 0; j < mmas_per_stage; ++j)
-            tc_mma<kTf32>(tmem, a0 + 2 * (j & 3), b0 + 2 * (j & 3), idesc, (st | j) ? 1u : 0u);
+          if (variant & 512) {
+            const uint32_t idesc16 = instr_desc(n, false);
+            for (int j = 0; j < mmas_per_stage; ++j)
+              tc_mma_ts(tmem, tmem + 128u + 8u * (j & 3), b0 + 2 * (j & 3), idesc16, (st | j) ? 1u : 0u);
+          } else if (variant & 1024) {
+            const uint32_t idesc16 = instr_desc(n, false);
+            for (int j = 0; j < mmas_per_stage; ++j) {
+              if (j & 1) tc_mma_ts(tmem, tmem + 128u + 8u * ((j >> 1) & 3), b0 + 2 * (j & 3), idesc16, 1u);
+              else tc_mma<kTf32>(tmem, a0 + 2 * ((j >> 1) & 3), b0 + 2 * ((j >> 1) & 3), idesc, (st | j) ? 1u : 0u);
+            }
+          } else {
+            for (int j = 0; j < mmas_per_stage; ++j)
+              tc_mma<kTf32>(tmem, a0 + 2 * (j & 3), b0 + 2 * (j & 3), idesc, (st | j) ? 1u : 0u);
+          }
           if (!sparse_commit || (s & 3) == 3) tc_commit(smem_u32(&bars[s]));
         }
       }
@@ -147,14 +166,13 @@ int main() {
   unsigned long long *cyc, h[256];
   CK(cudaMalloc(&cyc, sizeof(unsigned long long) * sms));
   const int stages = 4096;
-  printf("%-6s %4s %5s %8s %12s %14s\n", "kind", "N", "mmas", "variant", "cyc/stage", "ideal(exec)");
+  printf("%-6s %4s %5s %8s %12s %10s\n", "kind", "N", "mmas", "variant", "cyc/stage", "cyc/mma");
   for (int tf32 = 0; tf32 < 2; ++tf32)
     for (int n : {16, 32, 64, 128})
-      for (int mmas : {1, 2, 4, 12})
-        for (int variant : {16 + 64, 256, 256 + 32}) {
-          if (n == 32 || n == 64) continue;
-          if (!tf32 && mmas == 12) continue;
-          if (tf32 && mmas != 12 && mmas != 4) continue;
+      for (int mmas : {4, 6, 8, 12})
+        for (int variant : {256, 256 + 512, 256 + 1024}) {
+          if (tf32 && (variant & 512)) continue;    // the TS form is f16 only here
+          if (!tf32 && (variant & 1024)) continue;  // the mix is the fp32 path's
           for (int rep = 0; rep < 2; ++rep) {
             if (tf32) issue_kernel<true><<<sms, 128, 64 * 1024>>>(n, mmas, stages, variant, cyc);
             else issue_kernel<false><<<sms, 128, 64 * 1024>>>(n, mmas, stages, variant, cyc);
@@ -163,9 +181,8 @@ int main() {
           CK(cudaMemcpy(h, cyc, sizeof(unsigned long long) * sms, cudaMemcpyDeviceToHost));
           unsigned long long mx = 0;
           for (int i = 0; i < sms; ++i) mx = h[i] > mx ? h[i] : mx;
-          // 128 x N x 32 B of K per MMA: 8192 dense bf16 flop/cyc/SM (4096 for tf32)
-          const double ideal = mmas * (128.0 * n * (tf32 ? 8 : 16) * 2) / (tf32 ? 4096.0 : 8192.0);
-          printf("%-6s %4d %5d %8d %12.1f %14.1f\n", tf32 ? "tf32" : "f16", n, mmas, variant, (double)mx / stages, ideal);
+          printf("%-6s %4d %5d %8d %12.1f %10.1f\n", tf32 ? "tf32" : "f16", n, mmas, variant, (double)mx / stages,
+                 (double)mx / stages / mmas);
         }
   return 0;
 }
