@@ -361,8 +361,9 @@ def run_ours(args, wl, rank, world, device):
                     dom["layer"], dom["key"], dom["cin"], dom["cout"], dom["n_out"], dom["pairs"], dom["mode"]),
                 kernel_ms=round(dom["ms"], 4), kernel_share_of_conv=round(dom["ms"] / conv_ms, 3),
                 algorithmic_flops=dom["flops"], algorithmic_bytes=dom["bytes"],
-                tensor_flops_note="fp32 mode issues 2 tensor passes per product (tf32 + bf16 correction): the tensor "
-                                  "pipe does twice the algorithmic flops" if precision == "fp32" else None)
+                tensor_flops_note="fp32 mode issues 3 bf16 tensor products per algorithmic product (hi*hi + hi*lo + "
+                                  "lo*hi of the split operands): the tensor pipe does three times the algorithmic "
+                                  "flops" if precision == "fp32" else None)
 
     # ---- the HBM-class stages, each timed directly with CUDA events (L2 flushed first, best of 3)
     def timed(fn):

@@ -14,6 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libfv2p_b200.so")
 
 MODE_F32, MODE_BF16_TC, MODE_TF32X3_TC, MODE_BF16_SIMT, MODE_F32_IN_BF16_OUT = 0, 1, 2, 3, 4
+MODE_FP32_TC = MODE_TF32X3_TC  # the fp32 tensor-core mode (split bf16 operands today; the older name stays valid)
 MAX_KVOL = 32
 ABI_VERSION = 2
 FLAG_PREFILLED = 1

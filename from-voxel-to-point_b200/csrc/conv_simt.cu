@@ -278,7 +278,7 @@ extern "C" int fv2p_conv_fwd(const void *features, int64_t n_in_cap, const void 
   FV2P_REQUIRE((scale == nullptr) == (shift == nullptr), "conv_fwd: scale and shift come together");
   if (n_out_cap == 0) return FV2P_OK;
   FV2P_REQUIRE(features && weight && nbr && out, "conv_fwd: null pointer argument");
-  FV2P_REQUIRE((!row_perm && !tile_order && !sched) || mode == FV2P_MODE_BF16_TC || mode == FV2P_MODE_TF32X3_TC,
+  FV2P_REQUIRE((!row_perm && !tile_order && !sched) || mode == FV2P_MODE_BF16_TC || mode == FV2P_MODE_FP32_TC,
                "conv_fwd: row_perm / tile_order / sched are only used by the tensor-core modes");
   FV2P_REQUIRE(!tile_order || row_perm, "conv_fwd: tile_order comes with the row order it was computed for");
   FV2P_REQUIRE((reinterpret_cast<uintptr_t>(tile_order) & 7) == 0, "conv_fwd: tile_order must be 8-byte aligned");
@@ -296,7 +296,7 @@ extern "C" int fv2p_conv_fwd(const void *features, int64_t n_in_cap, const void 
                                                kvol, n_out_cap, n_out_dev, cin, cout, bias, scale, shift,
                                                residual, relu, out, stream);
     case FV2P_MODE_BF16_TC:
-    case FV2P_MODE_TF32X3_TC:
+    case FV2P_MODE_FP32_TC:
       return launch_conv_tc(features, n_in_cap, weight, nbr, nbr_stride, row_perm, tile_order, sched, kvol, n_out_cap,
                             n_out_dev, cin, cout, bias, scale, shift, residual, relu, mode, out, stream);
     default:

@@ -22,7 +22,7 @@
 //                 pulled with one TMA bulk copy per stage by warp 14 into a ring of their own (three slots; the
 //                 gathered tiles have a deeper ring of 16 KB slots, since their round trip is the long one)
 //   MMA           one elected thread of warp 12 runs the whole tcgen05.mma issue loop (kind::f16 for bf16,
-//                 kind::tf32 for fp32); tcgen05.commit releases the smem stage / publishes the accumulator
+//                 A from TMEM for fp32); tcgen05.commit releases the smem stage / publishes the accumulator
 //   epilogue      warps 0-3 read TMEM with tcgen05.ld (one accumulator row per thread), apply
 //                 bias + folded BatchNorm + residual + ReLU and store 16-byte vectors
 //   tiles         warp 13 is the scheduler: it claims tiles in the order fv2p_sort_rows_by_mask computed (most
@@ -33,18 +33,23 @@
 //                 bulk copies, a few tiles ahead of the producers.  Tile ids reach the epilogue through a small
 //                 ring; a sentinel tile / stage ends the stream for every role.
 //
-// fp32 path = 3xTF32, x = hi + lo with hi = x with its low 13 mantissa bits cleared - which is exactly what a
-// kind::tf32 MMA sees when it reads fp32 data - and lo = x - hi (exact).  Per 8-channel K step two MMAs:
-//   A_hi*W_hi   kind::tf32, A read straight from the landed fp32 tile in shared memory, W_hi = rn_tf32(W);
-//   A_lo*W_hi + A_hi*W_lo   ONE kind::f16 MMA of K = 16 on bf16 copies (the products are already 2^-11 down, bf16's
-//               2^-9 is enough): A = [lo | hi] from tensor memory, B = the packed [W_hi; W_lo] bf16 image.
-// Four transform warps (15-18, one per TMEM lane quadrant, one row per thread) read the landed tile, form the bf16
-// pairs and tcgen05.st them into a TMEM ring (32 columns per A slot); the MMA reads them with tcgen05.mma [d], [a], b.
-// History: with hi/lo tiles in shared memory and three tf32 passes the kernel was bound by the shared-memory pipe
-// (16 KB landed + 48 KB split traffic + 12 x 8 KB operand reads per stage ~ 1500 cycles at 128 B/cycle); cvt.rna
-// pairs on the conversion pipe cost another ~500 cycles per stage.  The dropped lo*lo term is O(2^-22) relative, the
-// bf16 rounding of the correction operands O(2^-20), both unbiased.  What remains (measured 1-2e-5 at 27*128 terms)
-// is the tensor core's truncating fp32 accumulation, 5x inside the 1e-4 bar.
+// fp32 path = split bf16 ("3xBF16"): x = hi + lo (+ <= 2^-18 |x|) with hi = bf16_rn(x), lo = bf16_rn(x - hi), the same
+// for W.  Per 16-channel K step THREE kind::f16 MMAs whose A operand sits in TMEM:
+//   A_hi*W_hi + A_hi*W_lo + A_lo*W_hi        (the dropped A_lo*W_lo is <= 2^-18 of the product)
+// - the transform warps (15-18, one per TMEM lane quadrant, thread = tile row) read the landed fp32 row from shared
+// memory, split it and write [hi(16) | lo(16)] as bf16 pairs to the stage's TMEM columns with tcgen05.st (32 columns
+// per A slot); B = the weight row [W_hi | W_lo] (bf16) of the packed image.  Measured against a float64 contraction:
+// 3.5e-6 ... 1.3e-5 relative at 27*16 ... 27*128 terms, 1.0-1.3e-5 on the stride-8 output of the 21-layer backbone
+// at benchmark size (bar 1e-4).
+// History: (1) hi/lo tiles in shared memory and three tf32 passes: bound by the shared-memory pipe (16 KB landed +
+// 48 KB split traffic + 12 x 8 KB operand reads per stage ~ 1500 cycles at 128 B/cycle; cvt.rna pairs another ~500);
+// (2) round 1 and most of round 2, "3xTF32": A_hi*W_hi as kind::tf32 straight from the landed tile (a tf32 MMA ignores
+// the low 13 mantissa bits) + ONE bf16 MMA of K = 16 per 8 channels for both corrections, A = [lo | hi] in TMEM - two
+// MMAs per EIGHT channels, the tf32 one at half rate and reading 4 KB of A from shared memory; (3) now three bf16
+// MMAs per SIXTEEN channels, none of which reads A from shared memory: 25 % less tensor time on the 128-wide layers,
+// ~25 % less issue / operand-feed time on the narrow ones (micro/mma_issue_bench.cu, N = 32: 6 TS MMAs 363 cycles
+// against 459 for the 4 + 4 mix), half the weight bytes - and a SMALLER error (fewer accumulating MMAs, each of which
+// truncates toward zero): waymo_b4 fp32 2.98 -> 2.72 ms per step.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -59,7 +64,7 @@ constexpr int kProdWarps = kProdThreads / 32;
 constexpr int kMmaWarp = (kEpiThreads + kProdThreads) / 32;  // warp 12
 constexpr int kSchedWarp = kMmaWarp + 1;                     // warp 13: tile scheduler + neighbour-map loader
 constexpr int kWLoadWarp = kSchedWarp + 1;                   // warp 14: weight-slice loader (W ring)
-constexpr int kXformThreads = 128;                           // warps 15-18, fp32 (3xTF32) kernels only
+constexpr int kXformThreads = 128;                           // warps 15-18, fp32 (split bf16) kernels only
 constexpr int kTcThreadsBase = kEpiThreads + kProdThreads + 96;
 constexpr int kMaxStages = 8;
 constexpr int kSmemLimit = 232448;                 // 227 KB of dynamic shared memory per CTA
@@ -143,22 +148,14 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-template <bool kTf32>
+template <bool kUnused>
 __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                        uint32_t accumulate) {
-  if constexpr (kTf32) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-  } else {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-  }
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 // A operand from tensor memory (lane = tile row, two 16-bit elements per 32-bit column, K-consecutive), B from
 // shared memory
@@ -181,13 +178,6 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t *r) {
       "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
       "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
-}
-// Round-to-nearest fp32 -> tf32 (kept in an fp32 container).  Truncation instead would bias every product the
-// same way and the bias grows linearly with the 27*Cin-term reduction; rounding keeps the split unbiased.
-__device__ __forceinline__ float tf32_rn(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
 }
 // 16 consecutive fp32 accumulator columns of this thread's TMEM lane
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
@@ -304,44 +294,42 @@ int g_tc_pdl = 1;  // programmatic dependent launch of the tensor-core conv kern
 // - row r = [x(k0) | x(k1) | ...] - and issue one MMA per 32 bytes of it against that offset's weight image, which for
 // these widths is small enough (<= 108 KB for all 27 offsets) to stay RESIDENT in shared memory: no weight ring, no
 // weight traffic per stage, and 2-4x fewer stages, barriers and commits per tile.
-template <bool kTf32, int N, bool kPacked = false>
+template <bool kFp32, int N, bool kPacked = false>
 struct Cfg {
   static constexpr int kABytes = kTileM * 128;  // one (up to) 128-byte slice per row
   static constexpr int kWBytes = N * 128;
   // Two rings.  A: the gathered tile (bf16 rows, or the raw fp32 rows), kStages slots of 16 KB - deep, because a
   // slot's round trip (gather issue -> L2 -> [split] -> MMA -> commit, ~5000 cycles) sets the pace of the kernel.
-  // W: the weight slice of the stage (bf16: N x 128 B; fp32: W_hi tf32 + [W_hi; W_lo] bf16), kWStages slots - one
-  // sequential bulk copy each, so three are enough (two at fp32 N = 128, where a slice is 32 KB and the shared
-  // memory is better spent on the A ring: 0.080 ms with 5 A slots, 0.073 with 6, 0.070 with 8).  (One ring of A+W
-  // slots was 4 deep at N = 128.)
-  static constexpr int kWSlotBytes = (kTf32 ? 2 : 1) * kWBytes;
-  static constexpr int kWStages = kPacked ? 0 : ((kTf32 && N == 128) ? 2 : 3);
+  // W: the weight slice of the stage (N rows of 128 B: bf16 channels, or for fp32 [W_hi | W_lo] bf16 halves),
+  // kWStages slots - one sequential bulk copy each, so three are enough.  (One ring of A+W slots was 4 deep at
+  // N = 128.)
+  static constexpr int kWSlotBytes = kWBytes;  // fp32: [W_hi | W_lo] bf16 halves of one 128-byte row per output channel
+  static constexpr int kWStages = kPacked ? 0 : 3;
   // packed: all (<= 27) offsets' images, sized for the widest packed row (64 bytes: bf16 cin 32 / fp32 cin 16)
   static constexpr int kMaxPackedKvol = 27;
-  static constexpr int kWResBytes = kPacked ? kMaxPackedKvol * (kTf32 ? 2 : 1) * N * 64 : 0;
+  static constexpr int kWResBytes = kPacked ? kMaxPackedKvol * N * 64 : 0;
   // The scheduler warp streams neighbour-map tiles into a ring of kNbrBufs buffers ahead of the producers.
   static constexpr int kNbrBufs = kPacked ? (kWResBytes > 100000 ? 2 : 3) : (N == 128 ? 2 : (N == 64 ? 3 : 4));
   static constexpr int kNbrBytes = kNbrBufs * kNbrBufInts * 4;
-  // fp32: the hi product reads the landed fp32 tile straight from shared memory (kind::tf32 ignores the low 13
-  // mantissa bits, i.e. hi = trunc(x)); only the correction operand goes through the transform warps and TMEM,
-  // kAColsPerStage columns per A slot.
+  // fp32: the tensor core never reads the landed fp32 tile; the transform warps split it into the stage's
+  // kAColsPerStage TMEM columns (per 16-channel K step: 8 columns of hi pairs, 8 of lo pairs).
   static constexpr int kAColsPerStage = 32;
   // The geometry of later levels (and of the next batch) runs on other streams under the feature pass; it only
   // gets onto an SM if the conv CTA leaves it some shared memory.  The fp32 128-wide layers come last, when little
   // geometry is left, and take it all.
-  static constexpr int kSmemAvail = kSmemLimit - ((kTf32 && N == 128) ? 0 : kSmemGuest);
+  static constexpr int kSmemAvail = kSmemLimit - ((kFp32 && N == 128) ? 0 : kSmemGuest);
   static constexpr int kStagesSmem =
       (kSmemAvail - kSmemMisc - kEpiStageBytes - kNbrBytes - kWStages * kWSlotBytes - kWResBytes) / kABytes;
-  static constexpr int kStagesTmem = kTf32 ? (512 - 2 * N) / kAColsPerStage : kMaxStages;
+  static constexpr int kStagesTmem = kFp32 ? (512 - 2 * N) / kAColsPerStage : kMaxStages;
   static constexpr int kStagesRaw = kStagesSmem < kStagesTmem ? kStagesSmem : kStagesTmem;
   static constexpr int kStages = kStagesRaw > kMaxStages ? kMaxStages : kStagesRaw;
   static constexpr int kWRegion = kPacked ? kWResBytes : kWStages * kWSlotBytes;
   static constexpr int kSmemBytes = kStages * kABytes + kWRegion + kNbrBytes + kEpiStageBytes + kSmemMisc;
-  static constexpr int kTmemCols = kTf32 ? 512 : (2 * N < 32 ? 32 : 2 * N);  // power of two
-  static constexpr int kThreads = kTcThreadsBase + (kTf32 ? kXformThreads : 0);
+  static constexpr int kTmemCols = kFp32 ? 512 : (2 * N < 32 ? 32 : 2 * N);  // power of two
+  static constexpr int kThreads = kTcThreadsBase + (kFp32 ? kXformThreads : 0);
   // Register cap: leaves >= 10 K of the 64 K registers so that one 256-thread geometry CTA (<= 40 registers per
   // thread) fits next to the conv CTA.
-  static constexpr int kMaxRegs = kTf32 ? 88 : 112;
+  static constexpr int kMaxRegs = kFp32 ? 88 : 112;
   static_assert(kStages >= 3, "pipeline too shallow");
 };
 
@@ -358,15 +346,15 @@ struct Epilogue {
   int relu;
 };
 
-template <bool kTf32, int N, bool kPacked>
-__global__ void __launch_bounds__((Cfg<kTf32, N, kPacked>::kThreads)) __maxnreg__((Cfg<kTf32, N, kPacked>::kMaxRegs))
+template <bool kFp32, int N, bool kPacked>
+__global__ void __launch_bounds__((Cfg<kFp32, N, kPacked>::kThreads)) __maxnreg__((Cfg<kFp32, N, kPacked>::kMaxRegs))
 conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restrict__ feat_ptr,
                const uint8_t *__restrict__ wpacked,
                const int *__restrict__ nbr, int64_t nbr_stride, const int *__restrict__ row_perm,
                const int *__restrict__ tile_order, int *sched, int kvol, int64_t n_out_cap,
                const int *__restrict__ n_out_dev, int cin, int oob_row, int use_tma_arg, Epilogue ep) {
-  using C = Cfg<kTf32, N, kPacked>;
-  constexpr int kElem = kTf32 ? 4 : 2;
+  using C = Cfg<kFp32, N, kPacked>;
+  constexpr int kElem = kFp32 ? 4 : 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t *stage_base = smem;                               // A ring
@@ -424,7 +412,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
       // publishes the stage flags (TMA gather: that arrive carries the expected bytes instead), land on `full`
       // for bf16 and on `landed` for fp32, where the 128 transform threads then complete `full`.
       const uint32_t a_arrivals = use_tma ? 1u : 32u * (uint32_t)slot_parts<C::kStages>(s) + 1u;
-      mbar_init(bar_full + 8 * s, kTf32 ? (uint32_t)kXformThreads : a_arrivals);
+      mbar_init(bar_full + 8 * s, kFp32 ? (uint32_t)kXformThreads : a_arrivals);
       mbar_init(bar_empty + 8 * s, 1);
       mbar_init(bar_landed + 8 * s, a_arrivals);
     }
@@ -495,7 +483,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
         const uint32_t s = issued % C::kStages;
         if ((int)s == my_slot && my_part < 2) {
           mbar_wait(bar_empty + 8 * s, ((issued / C::kStages) & 1) ^ 1);
-          const uint32_t a_bar = kTf32 ? bar_landed + 8 * s : bar_full + 8 * s;
+          const uint32_t a_bar = kFp32 ? bar_landed + 8 * s : bar_full + 8 * s;
           if (lane == 0 && my_part == 0) {
             stage_flags.set(s, kFlagStop);
             mbar_arrive(a_bar);
@@ -539,7 +527,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
           }
           TC_T0();
           const uint32_t a_u32 = smem_u32(stage_base + (size_t)s * C::kABytes);
-          const uint32_t a_bar = kTf32 ? bar_landed + 8 * s : bar_full + 8 * s;
+          const uint32_t a_bar = kFp32 ? bar_landed + 8 * s : bar_full + 8 * s;
           if (lane == 0 && my_part == 0) {
             stage_flags.set(s, (g == 0 ? kFlagFirst : 0) | (g == n_st - 1 ? kFlagLast : 0));
             stage_ks.set(s, (int)ks);
@@ -588,7 +576,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
           }
           TC_T0();
           const uint32_t a_u32 = smem_u32(stage_base + (size_t)s * C::kABytes);
-          const uint32_t a_bar = kTf32 ? bar_landed + 8 * s : bar_full + 8 * s;
+          const uint32_t a_bar = kFp32 ? bar_landed + 8 * s : bar_full + 8 * s;
           if (lane == 0 && my_part == 0) {
             stage_flags.set(s, ((k == (int)first_k && sl == 0) ? kFlagFirst : 0) |
                              ((k == (int)last_k && sl == slices - 1) ? kFlagLast : 0));
@@ -754,22 +742,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
     }
   } else if (warp == kMmaWarp) {
     // =============================== MMA issuer ===============================
-    constexpr uint32_t idesc = instr_desc(N, kTf32);
+    constexpr uint32_t idesc = instr_desc(N, false);
     constexpr uint32_t idesc_corr = instr_desc(N, false);  // fp32 path: bf16 correction MMAs
     (void)idesc_corr;
     const uint32_t sbo = 8u * (uint32_t)row_bytes;
     const uint32_t layout = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
     const uint32_t w_sbo = 8u * (uint32_t)w_row_bytes;
     const uint32_t w_layout = w_row_bytes == 128 ? 2u : (w_row_bytes == 64 ? 4u : 6u);
-    const int ksteps = row_bytes >> 5;  // 32 bytes of K per MMA (16 bf16 / 8 tf32)
+    const int ksteps = row_bytes >> 5;  // 32 bytes of the A row per bf16 MMA; fp32 rows: 64 bytes (16 channels) per K step
     // This loop is a single thread's instruction stream, so it is kept short: the descriptor of a slot is the
     // descriptor of slot 0 plus a constant in the 16-byte start-address field (no carry: smem is < 256 KB).
     const uint64_t a_desc0 = smem_desc(smem_u32(stage_base), sbo, layout);
     const uint64_t w_desc0 = smem_desc(smem_u32(w_base), w_sbo, w_layout);
     constexpr uint64_t kStageStep = (uint64_t)(C::kABytes >> 4);
     constexpr uint64_t kWSlotStep = (uint64_t)(C::kWSlotBytes >> 4);
-    const uint64_t w_lo_off = (uint64_t)(w_stage_bytes >> 4);
-    const uint64_t w_img_step = (uint64_t)((w_stage_bytes * (kTf32 ? 2u : 1u)) >> 4);  // packed: one offset's image(s)
+    const uint64_t w_lo_off = (uint64_t)(w_row_bytes >> 5);  // fp32: W_lo is the second half of every weight row
+    const uint64_t w_img_step = (uint64_t)(w_stage_bytes >> 4);  // packed: one offset's image
     const int kpo_shift = (w_row_bytes >> 5) - 1;  // packed: MMA K steps per offset = 1 << kpo_shift (1 or 2)
     (void)w_img_step, (void)kpo_shift, (void)kWSlotStep;
     const uint32_t a_tmem0 = tmem_base + 2u * (uint32_t)N;  // fp32: TMEM ring of split A tiles behind the accumulators
@@ -815,20 +803,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
           // reads that offset's resident weight image
           const uint32_t ks = (uint32_t)stage_ks.get(s);
           if (dbg != 4) {
+            if constexpr (kFp32) {
+              // fp32 rows of 64 bytes: two offsets per stage, 16 channels = ONE K step of the split operands each
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              const uint32_t k = (ks >> (8 * (t >> kpo_shift))) & 0xFFu;
-              if (k != 0xFFu) {
-                const uint64_t b = w_desc0 + (uint64_t)k * w_img_step + (uint64_t)(2 * (t & ((1 << kpo_shift) - 1)));
-                const uint64_t adv = (uint64_t)(2 * t);
-                if constexpr (kTf32) {
-                  const uint32_t a_cols = a_tmem0 + s * (uint32_t)C::kAColsPerStage + 8u * (uint32_t)t;
-                  tc_mma_ts_f16(d_tmem, a_cols, b + w_lo_off, idesc_corr, accumulate);
-                  tc_mma<true>(d_tmem, a_desc + adv, b, idesc, 1u);
-                } else {
-                  tc_mma<false>(d_tmem, a_desc + adv, b, idesc, accumulate);
+              for (int q = 0; q < 2; ++q) {
+                const uint32_t k = (ks >> (8 * q)) & 0xFFu;
+                if (k != 0xFFu) {
+                  const uint64_t b = w_desc0 + (uint64_t)k * w_img_step;
+                  const uint32_t a_hi = a_tmem0 + s * (uint32_t)C::kAColsPerStage + 16u * (uint32_t)q;
+                  tc_mma_ts_f16(d_tmem, a_hi, b, idesc_corr, accumulate);
+                  tc_mma_ts_f16(d_tmem, a_hi, b + w_lo_off, idesc_corr, 1u);
+                  tc_mma_ts_f16(d_tmem, a_hi + 8u, b, idesc_corr, 1u);
+                  accumulate = 1u;
                 }
-                accumulate = 1u;
+              }
+            } else {
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const uint32_t k = (ks >> (8 * (t >> kpo_shift))) & 0xFFu;
+                if (k != 0xFFu) {
+                  const uint64_t b = w_desc0 + (uint64_t)k * w_img_step + (uint64_t)(2 * (t & ((1 << kpo_shift) - 1)));
+                  tc_mma<false>(d_tmem, a_desc + (uint64_t)(2 * t), b, idesc, accumulate);
+                  accumulate = 1u;
+                }
               }
             }
           }
@@ -840,19 +837,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
           }
           tc_fence_after();
           if (dbg != 4) {
+            if constexpr (kFp32) {
+              // 16 input channels per step, three bf16 MMAs with the A operand in TMEM: hi*hi + hi*lo + lo*hi
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (j < ksteps) {
-                const uint64_t adv = (uint64_t)(2 * j);  // 32 bytes of K
-                if constexpr (kTf32) {
-                  // 8 input channels per step: hi*hi as tf32, both correction terms as one bf16 MMA of K = 16
-                  const uint32_t a_cols = a_tmem0 + s * (uint32_t)C::kAColsPerStage + 8u * (uint32_t)j;
-                  tc_mma_ts_f16(d_tmem, a_cols, b_desc + w_lo_off + adv, idesc_corr, accumulate);
-                  tc_mma<true>(d_tmem, a_desc + adv, b_desc + adv, idesc, 1u);
-                } else {
-                  tc_mma<false>(d_tmem, a_desc + adv, b_desc + adv, idesc, accumulate);
+              for (int j = 0; j < 2; ++j) {
+                if (2 * j < ksteps) {
+                  const uint64_t b = b_desc + (uint64_t)(2 * j);  // 16 bf16 = 32 bytes of K in the W_hi half
+                  const uint32_t a_hi = a_tmem0 + s * (uint32_t)C::kAColsPerStage + 16u * (uint32_t)j;
+                  tc_mma_ts_f16(d_tmem, a_hi, b, idesc_corr, accumulate);
+                  tc_mma_ts_f16(d_tmem, a_hi, b + w_lo_off, idesc_corr, 1u);
+                  tc_mma_ts_f16(d_tmem, a_hi + 8u, b, idesc_corr, 1u);
+                  accumulate = 1u;
                 }
-                accumulate = 1u;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                if (j < ksteps) {
+                  const uint64_t adv = (uint64_t)(2 * j);  // 32 bytes of K
+                  tc_mma<false>(d_tmem, a_desc + adv, b_desc + adv, idesc, accumulate);
+                  accumulate = 1u;
+                }
               }
             }
           }
@@ -887,7 +892,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
     // the W ring full: stage i's slice goes to slot i % kWStages with one bulk copy.  A single in-order waiter per
     // barrier, so the W ring may be shallower than the A ring without a parity wait ever being two phases ahead.
     if (elect_one_sync()) {
-      const uint32_t wb = w_stage_bytes * (kTf32 ? 2 : 1);
+      const uint32_t wb = w_stage_bytes;
       if constexpr (kPacked) {
         // every offset's image once, resident for the whole kernel (weights do not depend on the previous layer, so
         // this does not wait for it either)
@@ -927,14 +932,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
     }
     __syncwarp();
   } else if (warp > kWLoadWarp) {
-    // =============================== fp32 split (warps 15-18, 3xTF32 kernels only) ===============================
+    // =============================== fp32 split (warps 15-18, fp32 kernels only) ===============================
     // Thread = tile row (the warp's TMEM lane quadrant is warp % 4): reads its landed fp32 row slice from the
     // swizzled tile, splits it and stores hi / lo to the stage's TMEM columns.
-    if constexpr (kTf32) {
+    if constexpr (kFp32) {
       const int t = threadIdx.x - kTcThreadsBase;
       const int quad = warp & 3;
       const int r = quad * 32 + lane;
-      const int chunks = row_bytes >> 4;  // 16-byte chunks per row slice: 8, 4 (cin = 16) -- 4 tf32 each
+      const int chunks = row_bytes >> 4;  // 16-byte chunks per row slice: 8, 4 (cin = 16) -- 4 floats each
       const int cshift = __ffs(chunks) - 1;
       const uint32_t swz_row = (uint32_t)((r >> (3 - cshift)) & (chunks - 1));
       const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + 2u * (uint32_t)N;
@@ -959,29 +964,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
 #pragma unroll
               for (int c = 0; c < 4; ++c)
                 x[c] = lds128f(row + (((uint32_t)(half * 4 + c) ^ swz_row) << 4));
-              // corr: per 8-channel K step, [lo0..lo7 | hi0..hi7] as bf16 pairs = 8 columns, the A operand of the
-              // correction MMA (its B operand is [W_hi; W_lo] in bf16, see pack_weight_kernel).  hi is what the
-              // tensor core sees when it reads the raw tile as tf32: the value with its low 13 mantissa bits cleared.
-              uint32_t corr[16];
+              // 16 channels = one K step: columns 0-7 = hi (bf16 round-to-nearest of x, two per column, K-consecutive),
+              // columns 8-15 = lo = bf16(x - hi); x - hi - lo <= 2^-18 |x|.  Three products per step (hi*W_hi, hi*W_lo,
+              // lo*W_hi; the dropped lo*W_lo is 2^-18 of the product) instead of the first version's tf32 product + bf16
+              // correction (two MMAs per EIGHT channels, one of them reading its A operand from shared memory).
+              uint32_t split[16];
 #pragma unroll
-              for (int u = 0; u < 2; ++u) {  // K step inside this half = chunks 2u, 2u+1
-                float h[8], l[8];
+              for (int c = 0; c < 4; ++c) {
+                const float v[4] = {x[c].x, x[c].y, x[c].z, x[c].w};
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                  const float v[4] = {x[2 * u + c].x, x[2 * u + c].y, x[2 * u + c].z, x[2 * u + c].w};
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    h[4 * c + e] = __uint_as_float(__float_as_uint(v[e]) & 0xFFFFE000u);
-                    l[4 * c + e] = v[e] - h[4 * c + e];
-                  }
-                }
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  corr[8 * u + q] = pack_bf16x2(l[2 * q], l[2 * q + 1]);
-                  corr[8 * u + 4 + q] = pack_bf16x2(h[2 * q], h[2 * q + 1]);
+                for (int e = 0; e < 2; ++e) {
+                  const uint32_t hi = pack_bf16x2(v[2 * e], v[2 * e + 1]);
+                  split[2 * c + e] = hi;
+                  split[8 + 2 * c + e] = pack_bf16x2(v[2 * e] - __uint_as_float(hi << 16),
+                                                     v[2 * e + 1] - __uint_as_float(hi & 0xFFFF0000u));
                 }
               }
-              tmem_st16(a_cols + 16u * half, corr);
+              tmem_st16(a_cols + 16u * half, split);
             }
           }
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -1013,7 +1012,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
     // tile).  Now the tile id of the NEXT accumulator is read from the scheduler's ring while the current one is
     // processed (`tiles_posted` says whether it is there yet), its output rows are loaded one tile ahead, and the
     // first residual chunk is issued before waiting for the accumulator.
-    constexpr int kLanesPerRow = kTf32 ? 4 : 2;          // lanes that share a row segment
+    constexpr int kLanesPerRow = kFp32 ? 4 : 2;          // lanes that share a row segment
     constexpr int kRowsPerInstr = 32 / kLanesPerRow;     // 8 / 16
     constexpr int kPasses = 32 / kRowsPerInstr;          // 4 / 2
     constexpr int kColsPerLane = 16 / kLanesPerRow;      // 4 / 8 columns of a 16-column chunk per lane
@@ -1152,7 +1151,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const void *__restr
             v[i] = x;
           }
           uint8_t *o = static_cast<uint8_t *>(ep.out) + ((size_t)grow[q] * N + c0 + seg * kColsPerLane) * kElem;
-          if constexpr (kTf32) {
+          if constexpr (kFp32) {
             if (ep.residual) {
               v[0] += __uint_as_float(res[q].x), v[1] += __uint_as_float(res[q].y);
               v[2] += __uint_as_float(res[q].z), v[3] += __uint_as_float(res[q].w);
@@ -1220,10 +1219,10 @@ __host__ __device__ inline size_t swizzled_offset(int n, int c, int row_bytes) {
 
 // Packs W [K,cin,cout] fp32 into per-(offset, 128-byte slice) shared-memory images of the B operand
 // (N rows x Kslice, K-major, swizzled like the A tile so one bulk copy drops it in place).
-template <bool kTf32>
+template <bool kFp32>
 __global__ void __launch_bounds__(kThreads)
 pack_weight_kernel(const float *__restrict__ w, int kvol, int cin, int cout, uint8_t *packed) {
-  constexpr int kElem = kTf32 ? 4 : 2;
+  constexpr int kElem = kFp32 ? 4 : 2;
   constexpr int kPerChunk = 16 / kElem;
   const int row_bytes = min(cin * kElem, 128);
   const int slices = (cin * kElem) / row_bytes;
@@ -1238,17 +1237,16 @@ pack_weight_kernel(const float *__restrict__ w, int kvol, int cin, int cout, uin
     const int c = within / kPerChunk, t = within % kPerChunk;
     const size_t off = swizzled_offset(n, c, row_bytes);
     const float val = w[e];
-    uint8_t *base = packed + ((size_t)k * slices + sl) * image * (kTf32 ? 2 : 1);
-    if constexpr (kTf32) {
-      // image 0: W_hi as tf32.  image 1: the B operand of the bf16 correction MMA - per 8-channel K step the 16
-      // K elements [W_hi(8) | W_lo(8)], matching A = [A_lo(8) | A_hi(8)]: sum A_lo*W_hi + A_hi*W_lo.
-      const float hi = tf32_rn(val);
-      reinterpret_cast<float *>(base + off)[t] = hi;
-      const int j = within / 8, q = within % 8;
-      uint8_t *corr = base + image;
-      reinterpret_cast<__nv_bfloat16 *>(corr + swizzled_offset(n, 2 * j, row_bytes))[q] = __float2bfloat16_rn(hi);
-      reinterpret_cast<__nv_bfloat16 *>(corr + swizzled_offset(n, 2 * j + 1, row_bytes))[q] =
-          __float2bfloat16_rn(val - hi);
+    uint8_t *base = packed + ((size_t)k * slices + sl) * image;
+    if constexpr (kFp32) {
+      // fp32: the row of output channel n holds the slice's input channels twice, as bf16: first half W_hi =
+      // bf16(w), second half W_lo = bf16(w - W_hi) (the B operands of hi*W_hi, lo*W_hi and hi*W_lo)
+      (void)off, (void)t;
+      const __nv_bfloat16 hi = __float2bfloat16_rn(val);
+      const int half_chunks = row_bytes >> 5;  // 16-byte chunks per half row
+      reinterpret_cast<__nv_bfloat16 *>(base + swizzled_offset(n, within / 8, row_bytes))[within % 8] = hi;
+      reinterpret_cast<__nv_bfloat16 *>(base + swizzled_offset(n, half_chunks + within / 8, row_bytes))[within % 8] =
+          __float2bfloat16_rn(val - __bfloat162float(hi));
     } else {
       reinterpret_cast<__nv_bfloat16 *>(base + off)[t] = __float2bfloat16_rn(val);
     }
@@ -1279,13 +1277,13 @@ EncodeTiledFn encode_fn() {
 }
 
 // 2D map over the feature matrix [rows, cin]; box = one row slice of row_bytes; gather4 fetches four boxes.
-int make_feature_map(CUtensorMap *map, const void *features, int64_t rows, int cin, bool tf32) {
+int make_feature_map(CUtensorMap *map, const void *features, int64_t rows, int cin, bool fp32) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) {
     set_error("conv_fwd(tc): cuTensorMapEncodeTiled is not available from this driver");
     return FV2P_ERR_DEVICE;
   }
-  const int elem = tf32 ? 4 : 2;
+  const int elem = fp32 ? 4 : 2;
   const int row_bytes = cin * elem < 128 ? cin * elem : 128;
   cuuint64_t gdim[2] = {(cuuint64_t)cin, (cuuint64_t)rows};
   cuuint64_t gstride[1] = {(cuuint64_t)cin * elem};
@@ -1293,7 +1291,7 @@ int make_feature_map(CUtensorMap *map, const void *features, int64_t rows, int c
   cuuint32_t estr[2] = {1, 1};
   CUtensorMapSwizzle sw = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                                            : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
-  CUresult r = fn(map, tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+  CUresult r = fn(map, fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
                   const_cast<void *>(features), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -1305,22 +1303,22 @@ int make_feature_map(CUtensorMap *map, const void *features, int64_t rows, int c
 
 int g_tc_packed = 1;  // packed stages for narrow rows (debug switch: fv2p_debug_packed)
 
-template <bool kTf32, int N, bool kPacked>
+template <bool kFp32, int N, bool kPacked>
 int launch_one(const void *features, int64_t feat_rows, const void *weight, const int *nbr, int64_t nbr_stride,
                const int *row_perm, const int *tile_order, int *sched, int kvol, int64_t n_out_cap,
                const int *n_out_dev, int cin, const Epilogue &ep, cudaStream_t stream) {
-  using C = Cfg<kTf32, N, kPacked>;
+  using C = Cfg<kFp32, N, kPacked>;
   static bool configured[64] = {false};  // the attribute is per device
   const int dev = current_device();
   if (!configured[dev]) {
-    int st = cuda_status(cudaFuncSetAttribute(conv_tc_kernel<kTf32, N, kPacked>,
+    int st = cuda_status(cudaFuncSetAttribute(conv_tc_kernel<kFp32, N, kPacked>,
                                               cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes),
                          "conv_fwd(tc) smem attribute");
     if (st) return st;
     configured[dev] = true;
   }
   CUtensorMap map;
-  int st = make_feature_map(&map, features, feat_rows, cin, kTf32);
+  int st = make_feature_map(&map, features, feat_rows, cin, kFp32);
   if (st) return st;
   // A-tile producer.  fv2p_tc_gather_mode(1) selects the TMA gather (cp.async.bulk.tensor tile::gather4), which was
   // measured faster only for fp32 rows of 128 bytes and more on KITTI-sized layers and slower everywhere else
@@ -1346,7 +1344,7 @@ int launch_one(const void *features, int64_t feat_rows, const void *weight, cons
   cfg.numAttrs = 1;
   const uint8_t *wp = static_cast<const uint8_t *>(weight);
   const int oob = (int)feat_rows;
-  return cuda_status(cudaLaunchKernelEx(&cfg, conv_tc_kernel<kTf32, N, kPacked>, map, features, wp, nbr, nbr_stride,
+  return cuda_status(cudaLaunchKernelEx(&cfg, conv_tc_kernel<kFp32, N, kPacked>, map, features, wp, nbr, nbr_stride,
                                         row_perm, tile_order, sched, kvol, n_out_cap, n_out_dev, cin, oob, use_tma, ep),
                      "conv_fwd(tc)");
 }
@@ -1367,13 +1365,13 @@ int launch_conv_tc(const void *features, int64_t feat_rows, const void *weight, 
     return FV2P_ERR_INVALID;
   }
   Epilogue ep{bias, scale, shift, residual, out, relu};
-  const bool tf32 = mode == FV2P_MODE_TF32X3_TC;
+  const bool fp32 = mode == FV2P_MODE_FP32_TC;
   // packed stages: rows narrower than 128 bytes whose 27 weight images fit the resident area
-  const int row_bytes_in = cin * (tf32 ? 4 : 2);
-  const bool packed = g_tc_packed && row_bytes_in < 128 && kvol <= 27 && (tf32 ? cout <= 32 : cout <= 64);
+  const int row_bytes_in = cin * (fp32 ? 4 : 2);
+  const bool packed = g_tc_packed && row_bytes_in < 128 && kvol <= 27 && (fp32 ? cout <= 32 : cout <= 64);
 #define FV2P_TC_ARGS features, feat_rows, weight, nbr, nbr_stride, row_perm, tile_order, sched, kvol, n_out_cap, n_out_dev, cin, ep, stream
-#define FV2P_TC(NN) return tf32 ? launch_one<true, NN, false>(FV2P_TC_ARGS) : launch_one<false, NN, false>(FV2P_TC_ARGS)
-#define FV2P_TCP(NN) return tf32 ? launch_one<true, NN, true>(FV2P_TC_ARGS) : launch_one<false, NN, true>(FV2P_TC_ARGS)
+#define FV2P_TC(NN) return fp32 ? launch_one<true, NN, false>(FV2P_TC_ARGS) : launch_one<false, NN, false>(FV2P_TC_ARGS)
+#define FV2P_TCP(NN) return fp32 ? launch_one<true, NN, true>(FV2P_TC_ARGS) : launch_one<false, NN, true>(FV2P_TC_ARGS)
   if (packed) {
     switch (cout) {
       case 16: FV2P_TCP(16);
@@ -1436,7 +1434,7 @@ extern "C" __attribute__((visibility("default"))) int fv2p_debug_set(int v) {
 extern "C" size_t fv2p_pack_weight_bytes(int kvol, int cin, int cout, int mode) {
   if (kvol < 1 || kvol > FV2P_MAX_KVOL || !tc_shape_ok(cin, cout)) return 0;
   if (mode == FV2P_MODE_BF16_TC) return (size_t)kvol * cin * cout * 2;
-  if (mode == FV2P_MODE_TF32X3_TC) return (size_t)kvol * cin * cout * 4 * 2;
+  if (mode == FV2P_MODE_FP32_TC) return (size_t)kvol * cin * cout * 4;  // W_hi and W_lo as bf16
   return 0;
 }
 
@@ -1446,7 +1444,7 @@ extern "C" int fv2p_pack_weight(const float *weight_f32, int kvol, int cin, int 
   FV2P_REQUIRE(weight_f32 && packed, "pack_weight: null pointer argument");
   FV2P_REQUIRE(fv2p_pack_weight_bytes(kvol, cin, cout, mode) > 0, "pack_weight: unsupported shape %d x %d->%d mode %d",
                kvol, cin, cout, mode);
-  if (mode == FV2P_MODE_TF32X3_TC)
+  if (mode == FV2P_MODE_FP32_TC)
     pack_weight_kernel<true><<<persistent_grid(), kThreads, 0, stream>>>(weight_f32, kvol, cin, cout,
                                                                          static_cast<uint8_t *>(packed));
   else

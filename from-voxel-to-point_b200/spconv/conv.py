@@ -130,7 +130,7 @@ class SparseConvolution(SparseModule):
     def _tensor_core_forward(self, input, features, outids, indice_pairs, indice_pair_num, nbr):
         """Inference through the module API (any module graph, FUSED: False, trees the engine does not recognise): when
         nothing can ask for gradients and the shape fits, the tcgen05 kernel runs here too - fp32 features through the
-        fp32-accurate 3xTF32 mode, bf16 features through the bf16 mode, bias fused - on the rulebook's grouped row
+        fp32 tensor-core mode (split-bf16 products), bf16 features through the bf16 mode, bias fused - on the rulebook's grouped row
         order, which is built once per indice_key and cached next to the neighbour map.  Returns None when the plain
         path (fp32 FMA + autograd) has to be taken."""
         if torch.is_grad_enabled() and (features.requires_grad or self.weight.requires_grad or

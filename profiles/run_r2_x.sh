@@ -1,0 +1,19 @@
+#!/bin/bash
+# fp32 path as split bf16 (3 TS MMAs per 16 channels): parity with measured errors, then the bench
+cd "$GRAFT_REPO_ROOT"
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -x -q -m gpu -s > gpurun_out/x_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/x_pytest.log
+grep -E "rel err" gpurun_out/x_pytest.log | head -40
+for prec in fp32; do
+  for wlx in waymo_b4 kitti_b8; do
+    timeout 300 python bench.py --workload $wlx --precision $prec --no-extras --no-cpu-baseline > gpurun_out/x_${wlx}_${prec}.json 2> gpurun_out/x_${wlx}_${prec}.err
+    echo "$wlx $prec rc=$?"; python - <<P
+import json
+try:
+    d=json.loads(open("gpurun_out/x_${wlx}_${prec}.json").read().strip().splitlines()[-1])
+    st=d.get("stages",{})
+    print(d["value"], d["ms_per_step"], "e2e", d["e2e"]["value"], "conv", st.get("conv_ms_sum"), [(l["c"], l["ms"]) for l in st.get("layers",[]) if l["l"] in (1,2,6,7,11,12,16,17)])
+except Exception as e: print("ERR", e)
+P
+  done
+done

@@ -27,7 +27,7 @@ for line in sass.splitlines():
 print("# SASS mnemonic counts of the tensor-core conv kernels (`cuobjdump -sass libfv2p_b200.so`, sm_100a, round 2)\n")
 print("UTCHMMA = tcgen05.mma, LDTM / STTM = tcgen05.ld / st, UTCBAR = tcgen05.commit, UTCATOMSWS = TMEM alloc/dealloc, "
       "UBLKCP = cp.async.bulk (weight\nslices, neighbour rows), LDGSTS = cp.async (gathered rows), UTMALDG = "
-      "cp.async.bulk.tensor tile::gather4 (optional gather), SYNCS = mbarrier ops.\nTemplate arguments: <fp32 (3xTF32) "
+      "cp.async.bulk.tensor tile::gather4 (optional gather), SYNCS = mbarrier ops.\nTemplate arguments: <fp32 (split-bf16) "
       "path, Cout, packed stages>.  No HMMA (legacy mma.sync) anywhere in the library.\n")
 print("| kernel | " + " | ".join(OPS) + " |")
 print("|---|" + "---:|" * len(OPS))

@@ -288,7 +288,7 @@ def test_data_processor_hook_matches_reference_voxelizer_fixture():
 
 def test_module_api_runs_tensor_cores_for_inference_on_any_module_graph():
     """a SparseSequential that is not one of the two backbones, under torch.no_grad(): the
-    convolutions take the tcgen05 kernel (3xTF32 for fp32 features) on a grouped row order cached per indice_key, and
+    convolutions take the tcgen05 kernel (the fp32 mode for fp32 features) on a grouped row order cached per indice_key, and
     match the oracle to the fp32 bar; with gradients enabled the same modules take the differentiable path."""
     shape = [9, 40, 36]
     ind = synth.random_voxels(shape, 2500, 2, seed=21)

@@ -226,7 +226,8 @@ def test_conv_fused_epilogue_matches_oracle(cin, cout):
 @pytest.mark.parametrize("cin,cout", [(16, 16), (16, 32), (32, 32), (32, 64), (64, 64), (64, 128), (128, 128)])
 @pytest.mark.parametrize("geom", ["subm", "s2"])
 def test_tensor_core_conv_matches_oracle(mode, cin, cout, geom):
-    """tcgen05 kernels: 3xTF32 must hold the fp32 bar, bf16 its stated tolerance, fused epilogue included."""
+    """tcgen05 kernels: the fp32 mode (split-bf16 products) must hold the fp32 bar, bf16 its stated tolerance, fused
+    epilogue included."""
     rng = np.random.default_rng(cin * 7 + cout)
     shape = [9, 40, 40]
     ind = synth.random_voxels(shape, 2200, 2, seed=cout)
@@ -270,9 +271,10 @@ def test_tensor_core_conv_matches_oracle(mode, cin, cout, geom):
         packed = spconv.ops.pack_weight(cuda(w), _lib.MODE_TF32X3_TC)
         out = spconv.ops.conv_forward(cuda(feats), packed, nbr, n_out, cuda(bias), cuda(scale), cuda(shift),
                                       cuda(res), True, mode=_lib.MODE_TF32X3_TC)
-        # measured 1-2e-5 at 27*128 terms: the tensor core adds each MMA's products into the fp32 accumulator with
-        # round-toward-zero, a bias that grows with the number of accumulating MMAs; still 5x inside the 1e-4 bar
+        # measured 3.5e-6 ... 1.3e-5 at 27*16 ... 27*128 terms (the tensor core adds each MMA's products into the fp32
+        # accumulator with round-toward-zero, a bias that grows with the number of accumulating MMAs): 8x inside 1e-4
         err = rel_err(out.cpu().numpy(), ref)
+        print("fp32 tensor-core conv vs fp64 truth: %s %d->%d rel err %.2e" % (geom, cin, cout, err))
         assert err < 5e-5, err
 
 
