@@ -696,7 +696,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true",
                     help="skip reference_gpu and the other workloads' extra keys (profiling runs)")
     ap.add_argument("--gather", default="auto", choices=["auto", "lsu", "tma"],
-                    help="A-tile producer of the tensor-core conv (fv2p_tc_gather_mode); auto = cp.async for every shape")
+                    help="A-tile producer of the tensor-core conv (fv2p_tc_gather_mode); auto = TMA gather4, cp.async for packed stages")
     ap.add_argument("--group-rows", default="all", choices=["all", "subm", "none"],
                     help="rulebooks whose rows are grouped by neighbour-mask digest for the tensor-core conv")
     ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels eagerly instead of replaying a CUDA graph")

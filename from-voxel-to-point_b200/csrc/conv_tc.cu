@@ -1320,11 +1320,14 @@ int launch_one(const void *features, int64_t feat_rows, const void *weight, cons
   CUtensorMap map;
   int st = make_feature_map(&map, features, feat_rows, cin, kFp32);
   if (st) return st;
-  // A-tile producer.  fv2p_tc_gather_mode(1) selects the TMA gather (cp.async.bulk.tensor tile::gather4), which was
-  // measured faster only for fp32 rows of 128 bytes and more on KITTI-sized layers and slower everywhere else
-  // (profiles/r1_notes.md); the default for every shape is the swizzled cp.async gather.  Packed stages always use
-  // the cp.async gather (their rows interleave several offsets).
-  const int use_tma = (!kPacked && g_tc_gather_mode > 0) ? 1 : 0;
+  // A-tile producer.  Default (auto): the TMA gather (cp.async.bulk.tensor tile::gather4: one instruction per lane
+  // fetches four rows, a warp covers the stage with one) for every kernel whose stage holds ONE offset; packed stages
+  // always use the swizzled cp.async gather (their rows interleave several offsets).  With the cp.async gather a
+  // producer warp spends ~2600 cycles issuing the 32 copies per lane of a stage (role timers, profiles/r2_notes.md),
+  // which became the longest leg of a slot's round trip once the fp32 MMA count dropped: waymo_b4 2.73 -> 2.67 ms
+  // fp32, 1.79 -> 1.77 bf16, kitti_b8 1.072 -> 1.050 / 0.779 -> 0.775.  (In round 1 it was measured faster only for
+  // fp32 rows of 128 bytes and more on KITTI-sized layers.)  fv2p_tc_gather_mode(0) forces cp.async.
+  const int use_tma = (!kPacked && g_tc_gather_mode != 0) ? 1 : 0;
   int64_t tiles = (n_out_cap + kTileM - 1) / kTileM;
   int grid = (int)(tiles < sm_count() ? tiles : sm_count());
   if (grid < 1) grid = 1;

@@ -294,9 +294,10 @@ FV2P_API int fv2p_sort_rows_by_mask(const int32_t *nbr, int64_t nbr_stride, int 
                                     int64_t sorted_stride, int32_t *tile_order, void *workspace,
                                     size_t workspace_bytes, fv2p_stream_t stream);
 
-/* Producer of the gathered A tile in the tensor-core kernels: -1 = auto (default: measured best per shape),
- * 0 = LSU (swizzled cp.async), 1 = TMA (cp.async.bulk.tensor tile::gather4).  Same results either way; a tuning
- * knob kept for measurement (profiles/r1_notes.md).  Process-wide, not stream-ordered. */
+/* Producer of the gathered A tile in the tensor-core kernels: -1 = auto (default: TMA gather for stages of one
+ * offset, cp.async for packed stages), 0 = LSU (swizzled cp.async) everywhere, 1 = TMA (cp.async.bulk.tensor
+ * tile::gather4) where possible.  Same results either way; a tuning knob kept for measurement
+ * (profiles/r2_notes.md).  Process-wide, not stream-ordered. */
 FV2P_API int fv2p_tc_gather_mode(int mode);
 
 /* Packed weight image for the tensor-core modes (done once per layer, device to device). */

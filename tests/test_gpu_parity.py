@@ -689,3 +689,36 @@ def test_voxelizer_builds_the_level0_coordinate_table():
     a = np.sort(table.cpu().numpy()[:lib.fv2p_table_bytes(row_cap)].view(np.int64).reshape(-1, 2), axis=0)
     b = np.sort(ref_table.cpu().numpy()[:lib.fv2p_table_bytes(row_cap)].view(np.int64).reshape(-1, 2), axis=0)
     assert np.array_equal(a, b)
+
+
+def test_tma_gather_and_cp_async_gather_give_identical_results():
+    """The two producers of the gathered A tile (fv2p_tc_gather_mode: TMA tile::gather4 = the default for stages of one
+    offset, swizzled cp.async) only differ in how the rows reach shared memory: bit-identical outputs, grouped and
+    ungrouped, including the zero fill of missing neighbours and a partial last tile."""
+    rng = np.random.default_rng(11)
+    shape = [9, 40, 40]
+    ind = synth.random_voxels(shape, 3001, 2, seed=6)
+    lib = _lib.load()
+    outids, pairs, num, nbr = spconv.ops.get_indice_pairs(cuda(ind), 2, shape, 3, 1, 1, 1, 0, True, False,
+                                                          return_nbr=True)
+    nbr = nbr.contiguous()
+    n_out = outids.shape[0]
+    perm, nbr_sorted, order = spconv.ops.sort_rows_by_mask(nbr, n_out, return_tile_order=True)
+    try:
+        for mode, dt, shapes in ((_lib.MODE_FP32_TC, torch.float32, ((32, 32), (64, 64), (128, 128), (64, 128))),
+                                 (_lib.MODE_BF16_TC, torch.bfloat16, ((64, 64), (128, 128), (64, 128)))):
+            for cin, cout in shapes:
+                feats = cuda(rng.standard_normal((ind.shape[0], cin)).astype(np.float32), dt)
+                packed = spconv.ops.pack_weight(cuda((rng.standard_normal((27, cin, cout)) / 40).astype(np.float32)), mode)
+                outs = []
+                for g in (0, 1):
+                    lib.fv2p_tc_gather_mode(g)
+                    outs.append(spconv.ops.conv_forward(feats, packed, nbr, n_out, relu=False, mode=mode))
+                    outs.append(spconv.ops.conv_forward(feats, packed, nbr_sorted.contiguous(), n_out, relu=False,
+                                                        mode=mode, row_perm=perm.contiguous(),
+                                                        tile_order=order.contiguous()))
+                assert float(outs[0].float().abs().max()) > 0
+                for o in outs[1:]:
+                    assert torch.equal(outs[0], o)
+    finally:
+        lib.fv2p_tc_gather_mode(-1)
