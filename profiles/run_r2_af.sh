@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 N=$(nvidia-smi -L | wc -l)
 echo "gpus visible: $N"
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/af_${N}gpu.json 2> gpurun_out/af_${N}gpu.err; echo "bench rc=$?"
-echo "ref skipped"
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29518 bench.py --impl reference --gpus $N --steps 1 --warmup 0 > gpurun_out/af_${N}gpu_ref.json 2> gpurun_out/af_${N}gpu_ref.err; echo "ref rc=$?"
 python - <<P
 import json
 for f in ("af_${N}gpu","af_${N}gpu_ref"):
