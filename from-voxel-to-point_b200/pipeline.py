@@ -62,7 +62,10 @@ class HotPath(object):
                      host_pts=torch.empty((pcap, f), dtype=torch.float32).pin_memory(),
                      host_off=torch.zeros((batch + 1,), dtype=torch.int32).pin_memory(),
                      dev_pts=torch.empty((pcap, f), dtype=torch.float32, device=device),
-                     dev_off=torch.zeros((batch + 1,), dtype=torch.int32, device=device))
+                     # empty, not zeros: a fill kernel would run on whatever stream is current here, unordered with
+                     # the H2D copy that upload() enqueues on the copy stream right afterwards (the copy writes every
+                     # entry); with the fill landing second a batch saw all-zero frame offsets = no points
+                     dev_off=torch.empty((batch + 1,), dtype=torch.int32, device=device))
             self._slots[index] = s
         return s
 

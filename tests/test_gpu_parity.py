@@ -722,3 +722,24 @@ def test_tma_gather_and_cp_async_gather_give_identical_results():
                     assert torch.equal(outs[0], o)
     finally:
         lib.fv2p_tc_gather_mode(-1)
+
+
+def test_run_stream_cold_start_with_a_busy_default_stream():
+    """The staging buffers of a fresh HotPath are created while run_stream is already enqueueing copies on its own
+    streams: nothing may depend on work queued on the default stream (a zero-filled frame-offset buffer once did - its
+    fill kernel ran on the current stream, unordered with the H2D copy on the copy stream, and a batch that lost the
+    race saw no points; found under compute-sanitizer, where the timing differs)."""
+    cfg = synth.DATASETS["kitti"]
+    net, _ = _load_backbone("VoxelResBackBone8x", 4, synth.grid_size(cfg), 9)
+    batches = [[synth.lidar_frame("kitti", seed=40 + 2 * i + j, az_steps=90) for j in range(2)] for i in range(4)]
+    ref = fv2p_b200.HotPath(net, cfg["voxel_size"], cfg["point_cloud_range"], 5, 16000)
+    expect = [ref(b, fetch="encoded")[1]["counts"] for b in batches]
+    for use_graph in (False, True):
+        hp = fv2p_b200.HotPath(net, cfg["voxel_size"], cfg["point_cloud_range"], 5, 16000, use_graph=use_graph)
+        ballast = torch.empty(1 << 28, dtype=torch.uint8, device="cuda")
+        for _ in range(40):  # tens of milliseconds of queued work on the default stream
+            ballast.zero_()
+        got = [res["counts"] for res in hp.run_stream(iter(batches))]
+        torch.cuda.synchronize()
+        assert got == expect
+        assert all(c[-1] > 0 for c in got)
