@@ -671,7 +671,7 @@ def test_voxelizer_builds_the_level0_coordinate_table():
     assert np.array_equal(plain["voxel_offsets"].cpu().numpy(), voff)
     assert torch.equal(plain["voxel_coords"][:m], coords)
     assert torch.equal(plain["voxel_features"][:m], out["voxel_features"][:m])
-    ref_table = torch.empty_like(table)
+    ref_table = torch.zeros_like(table)
     status = torch.zeros(1, dtype=torch.int32, device="cuda")
     _lib.check(lib.fv2p_table_build(_lib.ptr(coords), m, None, _lib.i32x3(shape), _lib.ptr(ref_table), row_cap,
                                     _lib.ptr(status), 0, _lib.stream_ptr(coords.device)), "table_build")
