@@ -38,6 +38,11 @@ constexpr int kItemsPerThread = 2;
 constexpr int kChunk = kThreads * kItemsPerThread;  // rows per work item of the ordered passes
 
 int geo_ctas_override();  // 0 = none (debug switch fv2p_debug_geo_ctas: CTAs per SM of the persistent geometry grids)
+// Persistent grids of the geometry pass and the voxelizer: 8 CTAs per SM.  These kernels run next to a persistent conv
+// CTA that leaves room for about one of theirs per SM, so the grid size mostly decides how much of the freed
+// resources they pick up between conv layers: measured step time at 1 / 2 / 4 / 8 CTAs per SM on waymo_b4 fp32
+// 3.08 / 2.75 / 2.66 / 2.65 ms, kitti_b8 1.129 / 1.075 / 1.069 / 1.051 (profiles/contention.py).
+constexpr int kGeoCtasPerSm = 8;
 inline int persistent_grid(int ctas_per_sm = 4) {
   const int o = geo_ctas_override();
   return sm_count() * (o > 0 ? o : ctas_per_sm);

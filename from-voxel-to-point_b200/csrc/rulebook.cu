@@ -512,7 +512,7 @@ PairWs carve_pairs(void *ws, int64_t n_in_cap, int kvol) {
 // mat (row-major [kvol][stride]) -> reference-layout pair lists
 void launch_compaction(const int *mat, int64_t mat_stride, const int *n_dev, int64_t n_cap, int kvol, int mirror,
                        const PairWs &w, int *pairs, int64_t pair_stride, int *pair_num, cudaStream_t stream) {
-  const int grid = persistent_grid();
+  const int grid = persistent_grid(kGeoCtasPerSm);
   const int *n_live = n_dev;
   if (!n_live) {  // host-known count: publish it once so the chunk scans can bound themselves the same way
     launch_set_scalar(w.scalars, (int)n_cap, stream);
@@ -631,7 +631,7 @@ extern "C" int fv2p_table_build(const int32_t *indices, int64_t n_cap, const int
   }
   if (n_cap == 0) return FV2P_OK;
   FV2P_REQUIRE(indices, "table_build: null indices");
-  table_insert_kernel<<<persistent_grid(), kThreads, 0, stream>>>(
+  table_insert_kernel<<<persistent_grid(kGeoCtasPerSm), kThreads, 0, stream>>>(
       reinterpret_cast<const int4 *>(indices), n_dev, n_cap, shape3[0], shape3[1], shape3[2],
       static_cast<Slot *>(table), table_slots_cap(table_row_cap) - 1, status_dev);
   FV2P_LAUNCH_CHECK("table_build");
@@ -652,7 +652,7 @@ extern "C" int fv2p_subm_neighbours(const int32_t *indices, int64_t n_cap, const
   if (st) return st;
   if (n_cap == 0) return FV2P_OK;
   FV2P_REQUIRE(indices, "subm_neighbours: null indices");
-  const int grid = persistent_grid();
+  const int grid = persistent_grid(kGeoCtasPerSm);
   const int4 *ind4 = reinterpret_cast<const int4 *>(indices);
   const Slot *tab = static_cast<const Slot *>(table);
   const uint32_t tmask = table_slots_cap(table_row_cap) - 1;
@@ -691,7 +691,7 @@ extern "C" int fv2p_conv_neighbours(const int32_t *indices, int64_t n_cap, const
     set_error("conv_neighbours: workspace too small (%zu < %zu)", workspace_bytes, w.bytes);
     return FV2P_ERR_WORKSPACE;
   }
-  const int grid = persistent_grid();
+  const int grid = persistent_grid(kGeoCtasPerSm);
   if (!(flags & FV2P_FLAG_PREFILLED)) {
     FillJob job;
     job.count = 0;
@@ -744,7 +744,7 @@ extern "C" int fv2p_subm_pairs(const int32_t *indices, int64_t n_cap, const int3
     launch_compaction(nbr, nbr_stride, n_dev, n_cap, g.kvol, 1, w, pairs, pair_stride, pair_num, stream);
   } else {
     FV2P_REQUIRE(indices && table, "subm_pairs: indices and table are needed for this geometry");
-    input_side_kernel<<<persistent_grid(), kThreads, 0, stream>>>(
+    input_side_kernel<<<persistent_grid(kGeoCtasPerSm), kThreads, 0, stream>>>(
         reinterpret_cast<const int4 *>(indices), n_dev, n_cap, g, static_cast<const Slot *>(table),
         table_slots_cap(table_row_cap) - 1, w.mat, n_cap);
     launch_compaction(w.mat, n_cap, n_dev, n_cap, g.kvol, 0, w, pairs, pair_stride, pair_num, stream);
@@ -775,7 +775,7 @@ extern "C" int fv2p_conv_pairs(const int32_t *indices, int64_t n_cap, const int3
     set_error("conv_pairs: workspace too small (%zu < %zu)", workspace_bytes, w.bytes);
     return FV2P_ERR_WORKSPACE;
   }
-  input_side_kernel<<<persistent_grid(), kThreads, 0, stream>>>(
+  input_side_kernel<<<persistent_grid(kGeoCtasPerSm), kThreads, 0, stream>>>(
       reinterpret_cast<const int4 *>(indices), n_dev, n_cap, g, static_cast<const Slot *>(table),
       table_slots_cap(table_row_cap) - 1, w.mat, n_cap);
   launch_compaction(w.mat, n_cap, n_dev, n_cap, g.kvol, 0, w, pairs, pair_stride, pair_num, stream);
@@ -944,7 +944,7 @@ extern "C" int fv2p_pairs_to_nbr(const int32_t *pairs, const int32_t *pair_num, 
   if (n_out == 0) return FV2P_OK;
   FV2P_REQUIRE(pairs || pair_stride == 0, "pairs_to_nbr: null pairs");
   FV2P_REQUIRE(pair_num && nbr, "pairs_to_nbr: null pointer argument");
-  fill_i32_kernel<<<persistent_grid(), kThreads, 0, stream>>>(nbr, (int64_t)kvol * nbr_stride, -1);
+  fill_i32_kernel<<<persistent_grid(kGeoCtasPerSm), kThreads, 0, stream>>>(nbr, (int64_t)kvol * nbr_stride, -1);
   if (pair_stride > 0) {
     dim3 grid(sm_count(), kvol);
     pairs_to_nbr_kernel<<<grid, kThreads, 0, stream>>>(pairs, pair_num, kvol, pair_stride, inverse, n_out, nbr,

@@ -264,7 +264,7 @@ extern "C" int fv2p_group_rows(const int32_t *nbr, int64_t nbr_stride, int kvol,
                          "group_rows");
     if (st) return st;
   }
-  const int grid = persistent_grid(6);
+  const int grid = persistent_grid(kGeoCtasPerSm);
   group_hist_kernel<<<grid, kThreads, 0, stream>>>(nbr, nbr_stride, kvol, kx, kvol / kx, n_dev, n_cap, w.masks,
                                                    w.digests, w.bins, w.bin_base, w.done);
   group_scatter_kernel<<<grid, kThreads, 0, stream>>>(nbr, nbr_stride, kvol, n_dev, n_cap, w.masks, w.digests,

@@ -367,7 +367,7 @@ extern "C" int fv2p_voxelize_mean_table(const float *points, const int32_t *fram
     set_error("voxelize: workspace too small (%zu < %zu)", workspace_bytes, w.bytes);
     return FV2P_ERR_WORKSPACE;
   }
-  const int grid = persistent_grid();
+  const int grid = persistent_grid(kGeoCtasPerSm);
   Slot *table0 = static_cast<Slot *>(level0_table);
   const uint32_t t0_slots = table0 ? table_slots_cap(table_row_cap) : 0u;
   Slot empty_slot;
@@ -431,7 +431,7 @@ extern "C" int fv2p_mean_vfe(const float *voxels, const int32_t *num_points, int
   FV2P_REQUIRE(num_voxels >= 0 && max_points >= 1 && num_features >= 1, "mean_vfe: bad sizes");
   if (num_voxels == 0) return FV2P_OK;
   FV2P_REQUIRE(voxels && num_points && out, "mean_vfe: null pointer argument");
-  mean_vfe_kernel<<<persistent_grid(), kThreads, 0, stream>>>(voxels, num_points, num_voxels, max_points,
+  mean_vfe_kernel<<<persistent_grid(kGeoCtasPerSm), kThreads, 0, stream>>>(voxels, num_points, num_voxels, max_points,
                                                              num_features, out);
   FV2P_LAUNCH_CHECK("mean_vfe");
   return FV2P_OK;
